@@ -1,0 +1,158 @@
+// fp64 tile-GEMM engine for sm_100a: cp.async (LDGSTS) multi-stage pipeline feeding
+// DMMA.8x8x4 (mma.sync.m8n8k4.f64) -- the only FP64 tensor shape Blackwell has (tcgen05 has
+// no f64 kind).  Every dense contraction of the GP hot path (Cholesky trailing updates,
+// triangular inverse, K^-1 = X^T X, predictive variance) is expressed as tile tasks that
+// run through this one main loop.
+//
+// Operand layouts (both live in row-major global matrices):
+//   KCONTIG : element (row, k) at base[row*ld + k]      ("N" for A, "T" for B)
+//   MCONTIG : element (row, k) at base[k*ld + row]      ("T" for A, "N" for B)
+// Shared-memory staging is padded so that every DMMA fragment load (8 rows x 4 k, one
+// double per lane) is bank-conflict free:
+//   KCONTIG : [rows][KC+4]   -> lane address row*20 + k   (half-warp covers 16 distinct 8B slots)
+//   MCONTIG : [KC][rows+4]   -> lane address k*(rows+4) + row
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace eb {
+
+constexpr int KC = 16;      // k extent of one pipeline stage
+constexpr int STAGES = 3;   // cp.async ring depth
+
+enum Layout : int { KCONTIG = 0, MCONTIG = 1 };
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// D(8x8) += A(8x4) * B(4x8).  Lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2*(l%4)+{0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int ROWS, int LAYOUT>
+struct OperandSmem {
+  static constexpr int STRIDE = (LAYOUT == KCONTIG) ? (KC + 4) : (ROWS + 4);
+  static constexpr int DOUBLES = (LAYOUT == KCONTIG) ? ROWS * STRIDE : KC * STRIDE;
+};
+
+// One CTA tile configuration.
+template <int BM_, int BN_, int WM_, int WN_>
+struct TileCfg {
+  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_;
+  static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+  static constexpr int THREADS = 32 * WARPS_M * WARPS_N;
+  static constexpr int MI = WM / 8, NI = WN / 8;
+};
+using Cfg128 = TileCfg<128, 128, 64, 32>;  // 256 threads, 64 accumulator doubles / thread
+using Cfg64 = TileCfg<64, 64, 32, 32>;     // 128 threads, 32 accumulator doubles / thread
+
+template <class Cfg, int LA, int LB>
+struct Engine {
+  using SA = OperandSmem<Cfg::BM, LA>;
+  using SB = OperandSmem<Cfg::BN, LB>;
+  static constexpr int STAGE_DOUBLES = SA::DOUBLES + SB::DOUBLES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);
+
+  // Stage one ROWS x KC operand slab into shared memory with 16-byte cp.async.
+  template <int ROWS, int LAYOUT>
+  static __device__ __forceinline__ void load_operand(double* s, const double* g, int ld, int tid) {
+    constexpr int STRIDE = OperandSmem<ROWS, LAYOUT>::STRIDE;
+    if (LAYOUT == KCONTIG) {
+      constexpr int CHUNKS = ROWS * (KC / 2);
+#pragma unroll
+      for (int c = tid; c < CHUNKS; c += Cfg::THREADS) {
+        int row = c >> 3, kc = (c & 7) * 2;
+        cp_async16(s + row * STRIDE + kc, g + (size_t)row * ld + kc);
+      }
+    } else {
+      constexpr int CHUNKS = KC * (ROWS / 2);
+#pragma unroll
+      for (int c = tid; c < CHUNKS; c += Cfg::THREADS) {
+        int k = c / (ROWS / 2), r2 = (c % (ROWS / 2)) * 2;
+        cp_async16(s + k * STRIDE + r2, g + (size_t)k * ld + r2);
+      }
+    }
+  }
+
+  static __device__ __forceinline__ void load_stage(double* stage, const double* Ag, int lda,
+                                                    const double* Bg, int ldb, int kt, int tid) {
+    const double* a = (LA == KCONTIG) ? Ag + (size_t)kt * KC : Ag + (size_t)kt * KC * lda;
+    const double* b = (LB == KCONTIG) ? Bg + (size_t)kt * KC : Bg + (size_t)kt * KC * ldb;
+    load_operand<Cfg::BM, LA>(stage, a, lda, tid);
+    load_operand<Cfg::BN, LB>(stage + SA::DOUBLES, b, ldb, tid);
+  }
+
+  // acc[mi][ni][2] += A(BM x nk*KC) * B(BN x nk*KC)^T for this warp's WM x WN sub-tile.
+  // `active` lets whole warps skip the math (used for the strictly-upper quadrant of
+  // diagonal tiles) while still taking part in loads and barriers.
+  static __device__ __forceinline__ void mainloop(double (&acc)[Cfg::MI][Cfg::NI][2], const double* Ag,
+                                                  int lda, const double* Bg, int ldb, int nk,
+                                                  double* smem, bool active) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM;
+    const int wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
+    const int g = lane >> 2, t = lane & 3;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      if (s < nk) load_stage(smem + s * STAGE_DOUBLES, Ag, lda, Bg, ldb, s, tid);
+      cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      {
+        int nxt = kt + STAGES - 1;
+        if (nxt < nk) load_stage(smem + (nxt % STAGES) * STAGE_DOUBLES, Ag, lda, Bg, ldb, nxt, tid);
+        cp_async_commit();
+      }
+      if (active) {
+        const double* sA = smem + (kt % STAGES) * STAGE_DOUBLES;
+        const double* sB = sA + SA::DOUBLES;
+#pragma unroll
+        for (int kk = 0; kk < KC; kk += 4) {
+          double af[Cfg::MI], bf[Cfg::NI];
+#pragma unroll
+          for (int mi = 0; mi < Cfg::MI; ++mi) {
+            int row = wm0 + mi * 8 + g;
+            af[mi] = (LA == KCONTIG) ? sA[row * SA::STRIDE + kk + t] : sA[(kk + t) * SA::STRIDE + row];
+          }
+#pragma unroll
+          for (int ni = 0; ni < Cfg::NI; ++ni) {
+            int col = wn0 + ni * 8 + g;
+            bf[ni] = (LB == KCONTIG) ? sB[col * SB::STRIDE + kk + t] : sB[(kk + t) * SB::STRIDE + col];
+          }
+#pragma unroll
+          for (int mi = 0; mi < Cfg::MI; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < Cfg::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // pipeline smem may be reused by the caller's epilogue
+  }
+};
+
+// A tile task: C tile origin plus operand origins (memory row / memory column of the first
+// element of the operand slab; for MCONTIG operands the memory row is the k index).
+struct TileTask {
+  int c_row, c_col;
+  int a_row, a_col;
+  int b_row, b_col;
+  int nk;     // number of KC-chunks in the contraction
+  int flags;  // bit0: diagonal 128-tile (skip the strictly-upper 64x64 quadrant)
+};
+
+}  // namespace eb

@@ -1,0 +1,577 @@
+// CUDA kernels of the GP hot path (fp64, sm_100a).  See DESIGN.md for the data layout.
+//
+// Matrix storage: one row-major (Np x Np) fp64 buffer `A` per GP handle, Np = N rounded up to a
+// multiple of 128; rows/columns >= N carry the identity so every kernel works on whole tiles.
+// The lower triangle goes K -> L (Cholesky factor) -> X = L^-1 in place; a second buffer `W`
+// of the same shape is scratch (T = L21*X11 during the triangular inverse, K* during
+// prediction).
+#pragma once
+#include <math.h>
+#include "engine.cuh"
+
+namespace eb {
+
+constexpr int MAXD = 16;   // maximum kernel dimension supported
+constexpr int TB = 64;     // base (panel) tile edge
+constexpr double TWO_PI_LOG = 1.8378770664093454835606594728112;  // log(2*pi)
+
+// Per-evaluation kernel parameters derived on the device from the hyperparameter vector
+// p = [log c, log M_0, ..., log M_{d-1}]  (george: `ConstantKernel * ExpSquaredKernel`,
+// reference call site swiftemulator/emulators/gaussian_process.py:181-183).
+struct KernelParams {
+  double amp;           // d * exp(p0)   (george sums the constant kernel over its d axes)
+  double inv_m[MAXD];   // 1 / exp(p_{i+1}); zero for padded dimensions
+};
+
+__global__ void prep_params_kernel(const double* __restrict__ p, int d, KernelParams* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    out->amp = (double)d * exp(p[0]);
+    for (int i = 0; i < MAXD; ++i) out->inv_m[i] = (i < d) ? 1.0 / exp(p[i + 1]) : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: kernel-matrix build.  One CTA per 64x64 tile of the lower triangle (tile list from the
+// host); inputs staged in shared memory, stores are 128-byte coalesced row segments.
+//   K_ij = amp * exp(-0.5 * sum_m (x_im - x_jm)^2 / M_m) + delta_ij * noise_i
+// (george BasicSolver.compute; reference call site gaussian_process.py:203-206).
+// Tiles listed with tj > ti are zero-filled (strictly-upper 64-blocks of diagonal 128-tiles,
+// which later hold zeros of the triangular factors).
+// ---------------------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(256) kbuild_kernel(const int2* __restrict__ tiles, const double* __restrict__ X,
+                                                      const double* __restrict__ noise,
+                                                      const KernelParams* __restrict__ kp, int n, int ld,
+                                                      double* __restrict__ A) {
+  __shared__ double sXi[DP][TB];
+  __shared__ double sXj[DP][TB];
+  __shared__ double sInv[DP];
+  const int2 tile = tiles[blockIdx.x];
+  const int i0 = tile.x * TB, j0 = tile.y * TB;
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  if (tile.y > tile.x) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) A[(size_t)(i0 + ty + 16 * a) * ld + j0 + tx + 16 * b] = 0.0;
+    return;
+  }
+  for (int e = tid; e < TB * DP; e += 256) {
+    int r = e / DP, m = e % DP;
+    sXi[m][r] = X[(size_t)(i0 + r) * DP + m];
+    sXj[m][r] = X[(size_t)(j0 + r) * DP + m];
+  }
+  if (tid < DP) sInv[tid] = kp->inv_m[tid];
+  __syncthreads();
+  const double amp = kp->amp;
+  double r2[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) r2[a][b] = 0.0;
+#pragma unroll
+  for (int m = 0; m < DP; ++m) {
+    double xi[4], xj[4];
+    const double im = sInv[m];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xi[a] = sXi[m][ty + 16 * a];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) xj[b] = sXj[m][tx + 16 * b];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        double dx = xi[a] - xj[b];
+        r2[a][b] = fma(dx * dx, im, r2[a][b]);
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int gi = i0 + ty + 16 * a;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int gj = j0 + tx + 16 * b;
+      double v;
+      if (gi < n && gj < n) {
+        v = amp * exp(-0.5 * r2[a][b]);
+        if (gi == gj) v += noise[gi];
+      } else {
+        v = (gi == gj) ? 1.0 : 0.0;
+      }
+      A[(size_t)gi * ld + gj] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2a: Cholesky of one 64x64 diagonal tile plus its triangular inverse, one CTA.
+// Writes L (zero strict upper) back into A, X = L^-1 into dinv[t], sum(log L_jj) into
+// logdet_part[t]; the first non-positive pivot is recorded in *info (1-based column), as
+// LAPACK dpotrf does for george's scipy.linalg.cholesky call.
+// ---------------------------------------------------------------------------------------
+constexpr int DS = TB + 1;  // padded smem stride
+constexpr int DIAG_SMEM_BYTES = 3 * TB * DS * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256) diag_factor_kernel(double* __restrict__ A, int ld, int t,
+                                                           double* __restrict__ dinv,
+                                                           double* __restrict__ logdet_part,
+                                                           int* __restrict__ info) {
+  extern __shared__ double dsm[];
+  double* S = dsm;                 // working copy
+  double* L = dsm + TB * DS;       // factor
+  double* X = dsm + 2 * TB * DS;   // inverse
+  const int tid = threadIdx.x;
+  double* At = A + (size_t)t * TB * ld + (size_t)t * TB;
+  for (int e = tid; e < TB * TB; e += 256) {
+    int r = e >> 6, c = e & 63;
+    S[r * DS + c] = (c <= r) ? At[(size_t)r * ld + c] : 0.0;
+    L[r * DS + c] = 0.0;
+    X[r * DS + c] = 0.0;
+  }
+  const int ty = tid >> 4, tx = tid & 15;
+  for (int j = 0; j < TB; ++j) {
+    __syncthreads();
+    const double d = S[j * DS + j];
+    if (!(d > 0.0)) {
+      if (tid == 0) atomicCAS(info, 0, t * TB + j + 1);
+    }
+    const double rinv = 1.0 / sqrt(d);
+    if (tid == 0) L[j * DS + j] = d * rinv;
+    // column j of L
+    for (int i = j + 1 + tid; i < TB; i += 256) L[i * DS + j] = S[i * DS + j] * rinv;
+    // rank-1 update of the trailing lower triangle with lazily scaled column values
+    for (int i = j + 1 + ty; i < TB; i += 16) {
+      const double li = S[i * DS + j] * rinv;
+      for (int k = j + 1 + tx; k <= i; k += 16) {
+        const double lk = S[k * DS + j] * rinv;
+        S[i * DS + k] = fma(-li, lk, S[i * DS + k]);
+      }
+    }
+  }
+  __syncthreads();
+  // X = L^-1, row by row; 4 lanes cooperate on one column's dot product.
+  const int c = tid >> 2, q = tid & 3;
+  for (int i = 0; i < TB; ++i) {
+    double part = 0.0;
+    for (int k = c + q; k < i; k += 4) part = fma(L[i * DS + k], X[k * DS + c], part);
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (q == 0 && c <= i) {
+      const double di = 1.0 / L[i * DS + i];
+      X[i * DS + c] = (c == i) ? di : -part * di;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < TB * TB; e += 256) {
+    int r = e >> 6, cc = e & 63;
+    At[(size_t)r * ld + cc] = L[r * DS + cc];
+    dinv[(size_t)t * TB * TB + e] = X[r * DS + cc];
+  }
+  if (tid == 0) {
+    double s = 0.0;
+    for (int j = 0; j < TB; ++j) s += log(L[j * DS + j]);
+    logdet_part[t] = s;
+  }
+}
+
+// Copy the 64x64 diagonal inverses into the diagonal of A (start of the triangular inverse).
+__global__ void __launch_bounds__(256) place_dinv_kernel(double* __restrict__ A, int ld,
+                                                          const double* __restrict__ dinv) {
+  const int t = blockIdx.x;
+  double* At = A + (size_t)t * TB * ld + (size_t)t * TB;
+  for (int e = threadIdx.x; e < TB * TB; e += 256) At[(size_t)(e >> 6) * ld + (e & 63)] = dinv[(size_t)t * TB * TB + e];
+}
+
+// ---------------------------------------------------------------------------------------
+// Generic tile GEMM:  C_tile = beta * C_tile + alpha * A_slab * B_slab^T  over a task list.
+// ---------------------------------------------------------------------------------------
+template <class Cfg, int LA, int LB>
+__global__ void __launch_bounds__(Cfg::THREADS) tile_gemm_kernel(const TileTask* __restrict__ tasks, double* C,
+                                                                  int ldc, const double* A, int lda,
+                                                                  const double* B, int ldb, double alpha,
+                                                                  double beta) {
+  extern __shared__ __align__(16) double gsm[];
+  using E = Engine<Cfg, LA, LB>;
+  const TileTask tk = tasks[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM;
+  const int wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
+  // strictly-upper quadrant of a diagonal 128-tile: nothing to compute or store
+  const bool active = !((tk.flags & 1) && (wm0 + Cfg::WM <= Cfg::BM / 2) && (wn0 >= Cfg::BN / 2));
+  double acc[Cfg::MI][Cfg::NI][2];
+#pragma unroll
+  for (int mi = 0; mi < Cfg::MI; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < Cfg::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  E::mainloop(acc, A + (size_t)tk.a_row * lda + tk.a_col, lda, B + (size_t)tk.b_row * ldb + tk.b_col, ldb, tk.nk,
+              gsm, active);
+  if (!active) return;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < Cfg::MI; ++mi) {
+    double* crow = C + (size_t)(tk.c_row + wm0 + mi * 8 + g) * ldc + tk.c_col + wn0 + 2 * t;
+#pragma unroll
+    for (int ni = 0; ni < Cfg::NI; ++ni) {
+      double2* pc = reinterpret_cast<double2*>(crow + ni * 8);
+      double2 v;
+      if (beta != 0.0) {
+        v = *pc;
+        v.x = fma(alpha, acc[mi][ni][0], beta * v.x);
+        v.y = fma(alpha, acc[mi][ni][1], beta * v.y);
+      } else {
+        v.x = alpha * acc[mi][ni][0];
+        v.y = alpha * acc[mi][ni][1];
+      }
+      *pc = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// z = X r  (X lower triangular, row-major): one warp per row, coalesced.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restrict__ X, int ld, int np,
+                                                          const double* __restrict__ r, double* __restrict__ z) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= np) return;
+  const double* xr = X + (size_t)row * ld;
+  double s = 0.0;
+  for (int j = lane; j <= row; j += 32) s = fma(xr[j], r[j], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) z[row] = s;
+}
+
+// alpha = X^T z, stage 1: partial[rc][j] = sum_{i in row chunk rc, i >= j} X[i][j] z[i].
+__global__ void __launch_bounds__(128) trmv_t_partial_kernel(const double* __restrict__ X, int ld, int np,
+                                                              const double* __restrict__ z,
+                                                              double* __restrict__ partial) {
+  const int cb = blockIdx.x, rc = blockIdx.y;  // 128-column block, 128-row chunk
+  const int j = cb * 128 + threadIdx.x;
+  double s = 0.0;
+  if (rc >= cb) {
+    const int i0 = rc * 128;
+    __shared__ double sz[128];
+    sz[threadIdx.x] = z[i0 + threadIdx.x];
+    __syncthreads();
+    const double* xp = X + (size_t)i0 * ld + j;
+#pragma unroll 8
+    for (int ii = 0; ii < 128; ++ii) {
+      const int i = i0 + ii;
+      double v = (i >= j) ? xp[(size_t)ii * ld] : 0.0;
+      s = fma(v, sz[ii], s);
+    }
+  }
+  partial[(size_t)rc * np + j] = s;
+}
+// stage 2: alpha[j] = sum over row chunks in fixed order.
+__global__ void __launch_bounds__(128) trmv_t_reduce_kernel(const double* __restrict__ partial, int np,
+                                                             double* __restrict__ alpha) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= np) return;
+  double s = 0.0;
+  for (int rc = j / 128; rc < np / 128; ++rc) s += partial[(size_t)rc * np + j];
+  alpha[j] = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: K^-1 tile = sum_k X[k][i] X[k][j] (never written to HBM) fused with the gradient traces
+//   g_0     = 1/2 sum_ij (a_i a_j - Kinv_ij) k_ij
+//   g_{m+1} = 1/2 sum_ij (a_i a_j - Kinv_ij) k_ij * 1/2 (x_im - x_jm)^2 / M_m
+// (george GP.grad_log_likelihood: A = alpha alpha^T - K^-1, einsum("ijk,ij", dK, A); reference
+// call site gaussian_process.py:212-214).  dK is regenerated in registers; per-CTA partial sums
+// go to `partial[task][DP+1]` and are combined in fixed order by finalize_kernel.
+// If kinv_out != nullptr the lower-triangle tile is also stored (debug / tests).
+// ---------------------------------------------------------------------------------------
+constexpr int LAUUM_CS = 129;  // odd stride of the staged K^-1 tile
+template <int DP>
+struct LauumSmem {
+  static constexpr int XS = DP | 1;  // odd stride: conflict-free row reads
+  static constexpr int C_OFF = 0;
+  static constexpr int XI_OFF = 128 * LAUUM_CS;
+  static constexpr int XJT_OFF = XI_OFF + 128 * XS;
+  static constexpr int AI_OFF = XJT_OFF + DP * 128;
+  static constexpr int AJ_OFF = AI_OFF + 128;
+  static constexpr int INV_OFF = AJ_OFF + 128;
+  static constexpr int RED_OFF = INV_OFF + DP;
+  static constexpr int DOUBLES = RED_OFF + 8 * (DP + 1);
+  static constexpr int EPI_BYTES = DOUBLES * (int)sizeof(double);
+  static constexpr int ENGINE_BYTES = Engine<Cfg128, MCONTIG, MCONTIG>::SMEM_BYTES;
+  static constexpr int BYTES = EPI_BYTES > ENGINE_BYTES ? EPI_BYTES : ENGINE_BYTES;
+};
+
+template <int DP>
+__global__ void __launch_bounds__(256) lauum_trace_kernel(const TileTask* __restrict__ tasks, const double* X, int ld,
+                                                           const double* __restrict__ Xtr,
+                                                           const double* __restrict__ alpha,
+                                                           const KernelParams* __restrict__ kp, int n,
+                                                           double* __restrict__ partial, double* kinv_out) {
+  extern __shared__ __align__(16) double gsm[];
+  using Cfg = Cfg128;
+  using E = Engine<Cfg, MCONTIG, MCONTIG>;
+  using SM = LauumSmem<DP>;
+  constexpr int XS = SM::XS;
+  const TileTask tk = tasks[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM;
+  const int wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
+  const bool diag = tk.flags & 1;
+  const bool active = !(diag && (wm0 + Cfg::WM <= 64) && (wn0 >= 64));
+  double acc[Cfg::MI][Cfg::NI][2];
+#pragma unroll
+  for (int mi = 0; mi < Cfg::MI; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < Cfg::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  E::mainloop(acc, X + (size_t)tk.a_row * ld + tk.a_col, ld, X + (size_t)tk.b_row * ld + tk.b_col, ld, tk.nk, gsm,
+              active);
+
+  // ---- epilogue: park the K^-1 tile in shared memory, stage the tile's inputs ----
+  double* sC = gsm + SM::C_OFF;
+  double* sXi = gsm + SM::XI_OFF;
+  double* sXjT = gsm + SM::XJT_OFF;
+  double* sAi = gsm + SM::AI_OFF;
+  double* sAj = gsm + SM::AJ_OFF;
+  double* sInv = gsm + SM::INV_OFF;
+  double* sRed = gsm + SM::RED_OFF;
+  const int i0 = tk.c_row, j0 = tk.c_col;
+  {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < Cfg::MI; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < Cfg::NI; ++ni) {
+        double* pc = sC + (wm0 + mi * 8 + g) * LAUUM_CS + wn0 + ni * 8 + 2 * t;
+        pc[0] = acc[mi][ni][0];
+        pc[1] = acc[mi][ni][1];
+      }
+  }
+  for (int e = threadIdx.x; e < 128 * DP; e += 256) {
+    int r = e / DP, m = e % DP;
+    sXi[r * XS + m] = Xtr[(size_t)(i0 + r) * DP + m];
+    sXjT[m * 128 + r] = Xtr[(size_t)(j0 + r) * DP + m];
+  }
+  if (threadIdx.x < 128) {
+    sAi[threadIdx.x] = alpha[i0 + threadIdx.x];
+    sAj[threadIdx.x] = alpha[j0 + threadIdx.x];
+  }
+  if (threadIdx.x < DP) sInv[threadIdx.x] = kp->inv_m[threadIdx.x];
+  __syncthreads();
+  const double amp = kp->amp;
+  double s[DP + 1];
+#pragma unroll
+  for (int m = 0; m <= DP; ++m) s[m] = 0.0;
+  // warp w owns rows 16w..16w+15; lanes own columns lane + 32*cb
+  double aj[4];
+#pragma unroll
+  for (int cb = 0; cb < 4; ++cb) aj[cb] = sAj[lane + 32 * cb];
+#pragma unroll 1
+  for (int rr = 0; rr < 16; ++rr) {
+    const int li = warp * 16 + rr;
+    const int gi = i0 + li;
+    if (gi >= n) break;
+    const double ai = sAi[li];
+    double r2[4];
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) r2[cb] = 0.0;
+#pragma unroll
+    for (int m = 0; m < DP; ++m) {
+      const double xi = sXi[li * XS + m], im = sInv[m];
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        const double dx = xi - sXjT[m * 128 + lane + 32 * cb];
+        r2[cb] = fma(dx * dx, im, r2[cb]);
+      }
+    }
+    double wa[4];
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+      const int lj = lane + 32 * cb;
+      const int gj = j0 + lj;
+      wa[cb] = 0.0;
+      if (gj <= gi) {
+        const double kinv = sC[li * LAUUM_CS + lj];
+        if (kinv_out != nullptr) kinv_out[(size_t)gi * ld + gj] = kinv;
+        const double w = (gi == gj) ? 1.0 : 2.0;
+        wa[cb] = w * (ai * aj[cb] - kinv) * (amp * exp(-0.5 * r2[cb]));
+      }
+      s[0] += wa[cb];
+    }
+#pragma unroll
+    for (int m = 0; m < DP; ++m) {
+      const double xi = sXi[li * XS + m], hm = 0.5 * sInv[m];
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        const double dx = xi - sXjT[m * 128 + lane + 32 * cb];
+        s[m + 1] = fma(wa[cb], dx * dx * hm, s[m + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m <= DP; ++m) {
+    double v = s[m];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sRed[warp * (DP + 1) + m] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x <= DP) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += sRed[w * (DP + 1) + threadIdx.x];
+    partial[(size_t)blockIdx.x * (DP + 1) + threadIdx.x] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Final scalar assembly (one CTA):  out = [lml, grad_0..grad_{P-1}, info, logdet, quad].
+//   lml = -1/2 (N log 2pi + 2 sum log L_jj) - 1/2 z^T z      (george GP.log_likelihood)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ logdet_part, int nt,
+                                                        const double* __restrict__ z, int n,
+                                                        const double* __restrict__ partial, int ntask, int dp,
+                                                        int d, int want_grad, const int* __restrict__ info,
+                                                        double* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s = fma(z[i], z[i], s);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double ld = 0.0;
+    for (int t = 0; t < nt; ++t) ld += logdet_part[t];
+    ld *= 2.0;
+    const double quad = red[0];
+    out[0] = -0.5 * ((double)n * TWO_PI_LOG + ld) - 0.5 * quad;
+    out[1 + d + 1] = (double)(*info);
+    out[1 + d + 2] = ld;
+    out[1 + d + 3] = quad;
+  }
+  if (want_grad && threadIdx.x <= d) {
+    double v = 0.0;
+    for (int k = 0; k < ntask; ++k) v += partial[(size_t)k * (dp + 1) + threadIdx.x];
+    out[1 + threadIdx.x] = 0.5 * v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4a: prediction mean fused with the cross-covariance build.  One warp per 4 query rows;
+// lanes stride over training points.  mu[q] = sum_j k(t_q, x_j) alpha_j; when ks != nullptr the
+// K* rows are also written (row-major, ld = ldk) for the variance GEMM.
+// (george GP.predict: Kxs = kernel.get_value(xs, x); mu = Kxs @ alpha; reference call site
+// gaussian_process.py:285-287.)
+// ---------------------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(256) predict_mean_kernel(const double* __restrict__ T, int m_rows,
+                                                            const double* __restrict__ Xtr,
+                                                            const double* __restrict__ alpha,
+                                                            const KernelParams* __restrict__ kp, int n, int np,
+                                                            double* __restrict__ mu, double* ks, int ldk) {
+  constexpr int RQ = 4;
+  __shared__ double sT[8][RQ][DP];
+  __shared__ double sInv[DP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = (blockIdx.x * 8 + warp) * RQ;
+  if (threadIdx.x < DP) sInv[threadIdx.x] = kp->inv_m[threadIdx.x];
+  for (int e = lane; e < RQ * DP; e += 32) {
+    int q = e / DP, m = e % DP;
+    sT[warp][q][m] = (q0 + q < m_rows) ? T[(size_t)(q0 + q) * DP + m] : 0.0;
+  }
+  __syncthreads();
+  if (q0 >= m_rows) {
+    return;
+  }
+  const double amp = kp->amp;
+  double accq[RQ];
+#pragma unroll
+  for (int q = 0; q < RQ; ++q) accq[q] = 0.0;
+  for (int j = lane; j < np; j += 32) {
+    double r2[RQ];
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) r2[q] = 0.0;
+    const double* xj = Xtr + (size_t)j * DP;
+#pragma unroll
+    for (int m = 0; m < DP; ++m) {
+      const double x = xj[m], im = sInv[m];
+#pragma unroll
+      for (int q = 0; q < RQ; ++q) {
+        const double dx = sT[warp][q][m] - x;
+        r2[q] = fma(dx * dx, im, r2[q]);
+      }
+    }
+    const double aj = (j < n) ? alpha[j] : 0.0;
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+      const double kv = (j < n) ? amp * exp(-0.5 * r2[q]) : 0.0;
+      accq[q] = fma(kv, aj, accq[q]);
+      if (ks != nullptr) ks[(size_t)(q0 + q) * ldk + j] = kv;  // rows padded to a tile multiple by the host
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < RQ; ++q) {
+    double v = accq[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && q0 + q < m_rows) mu[q0 + q] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4b: predictive variance.  V = K* X^T (X = L^-1 lower, so only k <= i contributes) through
+// the tile engine; V is never stored: each CTA reduces its 128x128 tile to per-row sums of
+// squares, rowss[itile][q].   var[q] = amp - sum_itile rowss[itile][q]
+// (george: var = k(t,t) - sum(Kxs^T * K^-1 Kxs^T) = amp - |L^-1 k*|^2).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) var_gemm_kernel(const TileTask* __restrict__ tasks, const double* Ks, int ldk,
+                                                        const double* X, int ld, double* __restrict__ rowss,
+                                                        int ld_rowss) {
+  extern __shared__ __align__(16) double gsm[];
+  using Cfg = Cfg128;
+  using E = Engine<Cfg, KCONTIG, KCONTIG>;
+  const TileTask tk = tasks[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM;
+  double acc[Cfg::MI][Cfg::NI][2];
+#pragma unroll
+  for (int mi = 0; mi < Cfg::MI; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < Cfg::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  E::mainloop(acc, Ks + (size_t)tk.a_row * ldk + tk.a_col, ldk, X + (size_t)tk.b_row * ld + tk.b_col, ld, tk.nk, gsm,
+              true);
+  double* sRow = gsm;  // [4 warps_n][128 rows]
+  const int g = lane >> 2, t = lane & 3;
+  const int wn = warp % Cfg::WARPS_N;
+#pragma unroll
+  for (int mi = 0; mi < Cfg::MI; ++mi) {
+    double v = 0.0;
+#pragma unroll
+    for (int ni = 0; ni < Cfg::NI; ++ni) {
+      v = fma(acc[mi][ni][0], acc[mi][ni][0], v);
+      v = fma(acc[mi][ni][1], acc[mi][ni][1], v);
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (t == 0) sRow[wn * 128 + wm0 + mi * 8 + g] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    double v = sRow[threadIdx.x] + sRow[128 + threadIdx.x] + sRow[256 + threadIdx.x] + sRow[384 + threadIdx.x];
+    rowss[(size_t)(tk.c_col / 128) * ld_rowss + tk.c_row + threadIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) var_finish_kernel(const double* __restrict__ rowss, int ld_rowss, int nitile,
+                                                          const KernelParams* __restrict__ kp, int m_rows,
+                                                          double* __restrict__ var) {
+  const int q = blockIdx.x * 256 + threadIdx.x;
+  if (q >= m_rows) return;
+  double s = 0.0;
+  for (int it = 0; it < nitile; ++it) s += rowss[(size_t)it * ld_rowss + q];
+  var[q] = kp->amp - s;
+}
+
+}  // namespace eb

@@ -1,0 +1,133 @@
+"""
+Thin object wrapper around one native GP handle (``eb200_gp``): owns the device state of
+one Gaussian process -- design matrix, K/L/L^-1 matrix, alpha -- and exposes the C ABI calls.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_void_p
+
+import numpy as np
+
+from . import _lib
+
+
+class DeviceProblem:
+    """One GP problem resident on one GPU."""
+
+    def __init__(self, x: np.ndarray, noise: np.ndarray, device: int = 0):
+        lib = _lib.require_gpu()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.ndim != 2:
+            raise ValueError("x must be [n, d]")
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        if noise.shape != (x.shape[0],):
+            raise ValueError("noise must be [n]")
+        self.n, self.d = x.shape
+        if self.d > _lib.MAX_DIM:
+            raise ValueError(f"kernel dimension {self.d} exceeds the supported maximum {_lib.MAX_DIM}")
+        self._lib = lib
+        self._h = c_void_p()
+        _lib.check(
+            lib.eb200_gp_create(ctypes.byref(self._h), device, self.n, self.d, _lib.as_double_ptr(x), _lib.as_double_ptr(noise)),
+            "eb200_gp_create",
+        )
+        self.device = device
+        self._result = np.zeros(_lib.result_len(self.d))
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.eb200_gp_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def padded_n(self) -> int:
+        return self._lib.eb200_gp_padded_n(self._h)
+
+    # -- hot path ---------------------------------------------------------------------------
+    def set_residual(self, r: np.ndarray):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        if r.shape != (self.n,):
+            raise ValueError("residual must be [n]")
+        _lib.check(self._lib.eb200_gp_set_residual_host(self._h, _lib.as_double_ptr(r)), "set_residual")
+
+    def evaluate(self, p: np.ndarray, want_grad: bool = True):
+        """Returns (lml, grad[P], info, logdet, quad) at hyperparameters p."""
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        if p.shape != (self.d + 1,):
+            raise ValueError(f"parameter vector must have {self.d + 1} entries")
+        out = self._result
+        _lib.check(
+            self._lib.eb200_gp_eval_host(self._h, _lib.as_double_ptr(p), int(bool(want_grad)), _lib.as_double_ptr(out)),
+            "eb200_gp_eval_host",
+        )
+        d = self.d
+        return float(out[0]), out[1 : d + 2].copy(), int(out[d + 2]), float(out[d + 3]), float(out[d + 4])
+
+    def predict(self, t: np.ndarray, want_var: bool = True):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        if t.ndim != 2 or t.shape[1] != self.d:
+            raise ValueError(f"query points must be [m, {self.d}]")
+        m = t.shape[0]
+        mu = np.empty(m)
+        var = np.empty(m) if want_var else None
+        _lib.check(
+            self._lib.eb200_gp_predict_host(
+                self._h, m, _lib.as_double_ptr(t), int(bool(want_var)), _lib.as_double_ptr(mu),
+                _lib.as_double_ptr(var) if want_var else None,
+            ),
+            "eb200_gp_predict_host",
+        )
+        return (mu, var) if want_var else mu
+
+    # -- device-pointer variants (inputs already in HBM; asynchronous) ----------------------------
+    def evaluate_device(self, p_ptr: int, want_grad: bool, result_ptr: int, stream: int = 0):
+        _lib.check(
+            self._lib.eb200_gp_eval_device(self._h, c_void_p(p_ptr), int(bool(want_grad)), c_void_p(result_ptr), c_void_p(stream)),
+            "eb200_gp_eval_device",
+        )
+
+    def set_residual_device(self, r_ptr: int, stream: int = 0):
+        _lib.check(self._lib.eb200_gp_set_residual_device(self._h, c_void_p(r_ptr), c_void_p(stream)), "set_residual_device")
+
+    def predict_device(self, m: int, t_ptr: int, want_var: bool, mu_ptr: int, var_ptr: int, stream: int = 0):
+        _lib.check(
+            self._lib.eb200_gp_predict_device(
+                self._h, m, c_void_p(t_ptr), int(bool(want_var)), c_void_p(mu_ptr), c_void_p(var_ptr), c_void_p(stream)
+            ),
+            "eb200_gp_predict_device",
+        )
+
+    def synchronize(self):
+        _lib.check(self._lib.eb200_gp_synchronize(self._h), "synchronize")
+
+    def launches_per_eval(self, want_grad: bool = True) -> int:
+        return self._lib.eb200_gp_eval_launches(self._h, int(bool(want_grad)))
+
+    # -- diagnostics (tests only) -------------------------------------------------------------
+    def debug_stage(self, p: np.ndarray, stage: int):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        _lib.check(self._lib.eb200_gp_debug_stage(self._h, _lib.as_double_ptr(p), stage), "debug_stage")
+
+    def debug_matrix(self, which: int = 0) -> np.ndarray:
+        npad = self.padded_n
+        out = np.empty((npad, npad))
+        _lib.check(self._lib.eb200_gp_debug_matrix(self._h, which, _lib.as_double_ptr(out)), "debug_matrix")
+        return out
+
+    def debug_alpha(self) -> np.ndarray:
+        out = np.empty(self.n)
+        _lib.check(self._lib.eb200_gp_debug_alpha(self._h, _lib.as_double_ptr(out)), "debug_alpha")
+        return out

@@ -1,0 +1,91 @@
+/*
+ * emulator_b200 -- C ABI of the B200-native Gaussian-process hot path behind swiftemulator.
+ *
+ * This is the drop-in boundary: a plain C interface (pointers and sizes, no torch or C++
+ * types) that a `george.GP`-shaped host object binds to.  Each entry point names the
+ * reference call it replaces; paths are relative to the SWIFTSIM/emulator source tree and
+ * `george` refers to the third-party package the reference delegates to (george 0.4.x,
+ * un-vendored; see DESIGN.md "Oracle").
+ *
+ * Conventions
+ *   - all floating point data is IEEE fp64, row-major, densely packed
+ *   - hyperparameter vector p has P = d + 1 entries: [log c, log M_0 .. log M_{d-1}]
+ *     (george `ConstantKernel(log_constant) * ExpSquaredKernel(metric=M, ndim=d)`,
+ *     built at swiftemulator/emulators/gaussian_process.py:181-183)
+ *   - every function returns 0 on success, non-zero on failure; eb200_last_error() gives text
+ *   - `info` follows LAPACK dpotrf: 0 = factorised, k > 0 = leading minor k not positive
+ *     definite (the host raises numpy.linalg.LinAlgError, as george/scipy do)
+ *   - *_host entry points take host buffers and include the host<->device copies;
+ *     *_device entry points take device pointers, enqueue on `stream` (a cudaStream_t cast to
+ *     void*, NULL = the handle's own stream) and do not synchronise
+ */
+#ifndef EMULATOR_B200_H
+#define EMULATOR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct eb200_gp eb200_gp;
+
+#define EB200_MAX_DIM 16
+/* length of the result vector written by the eval entry points for a handle of dimension d:
+ * [lml, grad_0 .. grad_d, info, logdet, quad]  ->  d + 5 doubles */
+#define EB200_RESULT_LEN(d) ((d) + 5)
+
+int eb200_version(void);
+const char* eb200_last_error(void);
+int eb200_device_count(void);
+
+/* Replaces george.GP.compute(x, yerr)  (swiftemulator/emulators/gaussian_process.py:203-206,
+ * gaussian_process_bins.py:239-242, gaussian_process_mcmc.py:235-238,
+ * gaussian_process_one_dim.py:202-205).  Uploads the design matrix x[n][d] and the diagonal
+ * term noise[n] (= yerr^2 + white-noise variance, formed by the host exactly as george does)
+ * once and allocates all device state (K/L/L^-1 matrix, scratch, task lists, CUDA graphs). */
+int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_host, const double* noise_host);
+int eb200_gp_destroy(eb200_gp* gp);
+int eb200_gp_n(const eb200_gp* gp);
+int eb200_gp_dim(const eb200_gp* gp);
+
+/* Residual r = y - mean(x), the vector george forms in GP.log_likelihood / _compute_alpha. */
+int eb200_gp_set_residual_host(eb200_gp* gp, const double* r_host);
+int eb200_gp_set_residual_device(eb200_gp* gp, const double* r_dev, void* stream);
+
+/* Replaces the pair gp.set_parameter_vector(p); gp.log_likelihood(y) /
+ * gp.grad_log_likelihood(y)  (gaussian_process.py:208-214 and the three sibling emulators):
+ * rebuilds K at p, factorises, and returns the log marginal likelihood and (want_grad != 0)
+ * its gradient with respect to p in one pass.  result has EB200_RESULT_LEN(d) entries. */
+int eb200_gp_eval_host(eb200_gp* gp, const double* p_host, int want_grad, double* result_host);
+int eb200_gp_eval_device(eb200_gp* gp, const double* p_dev, int want_grad, double* result_dev, void* stream);
+
+/* Replaces gp.predict(y, t, return_cov=False, return_var=bool)  (gaussian_process.py:285-287,
+ * :344-346; gaussian_process_bins.py:354-359, :452-457).  Requires a preceding eval at the
+ * hyperparameters to predict with (the factor and alpha stay resident).  mean-model values
+ * are added by the host.  t is [m][d]; mu and var are [m]; var may be NULL if !want_var. */
+int eb200_gp_predict_host(eb200_gp* gp, int m, const double* t_host, int want_var, double* mu_host,
+                          double* var_host);
+int eb200_gp_predict_device(eb200_gp* gp, int m, const double* t_dev, int want_var, double* mu_dev,
+                            double* var_dev, void* stream);
+
+int eb200_gp_synchronize(eb200_gp* gp);
+
+/* Test / diagnostics hooks (not used by the product path).
+ * stage: 1 = K built, 2 = + Cholesky (L in the lower triangle), 3 = + triangular inverse
+ * (X = L^-1), 4 = + K^-1 lower triangle stored in the scratch matrix.
+ * eb200_gp_debug_matrix copies matrix `which` (0 = main, 1 = scratch), np*np doubles. */
+int eb200_gp_debug_stage(eb200_gp* gp, const double* p_host, int stage);
+int eb200_gp_padded_n(const eb200_gp* gp);
+int eb200_gp_debug_matrix(eb200_gp* gp, int which, double* out_host);
+int eb200_gp_debug_alpha(eb200_gp* gp, double* alpha_host);
+/* number of kernel launches issued by one eval (graph nodes) */
+int eb200_gp_eval_launches(const eb200_gp* gp, int want_grad);
+
+/* Engine micro-benchmark: C[m][n] = A[m][k] * B[n][k]^T through the tile engine, device
+ * pointers, m, n multiples of 128, k multiple of 16.  Used by bench.py to report the engine's
+ * DMMA throughput next to cuBLAS DGEMM. */
+int eb200_bench_gemm_nt(int m, int n, int k, const double* a_dev, const double* b_dev, double* c_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMULATOR_B200_H */
