@@ -648,6 +648,36 @@ int eb200_gp_debug_alpha(eb200_gp* h, double* alpha_host) {
   return 0;
 }
 
+int eb200_gp_profile_stages(eb200_gp* h, const double* p_host, int reps, float* ms_out) {
+  if (!h || !p_host || !ms_out || reps < 1) return fail("profile_stages: bad argument");
+  CK(cudaSetDevice(h->device));
+  memcpy(h->h_p, p_host, (h->d + 1) * sizeof(double));
+  CK(cudaMemcpyAsync(h->p_dev, h->h_p, (h->d + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  cudaEvent_t ev[6];
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  for (int s = 0; s < 5; ++s) ms_out[s] = 0.f;
+  for (int rep = 0; rep <= reps; ++rep) {  // rep 0 is a warm-up
+    CK(cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
+    CK(cudaEventRecord(ev[0], h->stream));
+    for (int stage = 1; stage <= 5; ++stage) {
+      for (const Op& op : h->ops)
+        if (op.stage == stage) launch_op(h, op, h->stream, 1, nullptr);
+      CK(cudaEventRecord(ev[stage], h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    if (rep == 0) continue;
+    for (int s = 0; s < 5; ++s) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, ev[s], ev[s + 1]));
+      ms_out[s] += ms / reps;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  h->factor_valid = true;
+  return 0;
+}
+
 int eb200_bench_gemm_nt(int m, int n, int k, const double* a_dev, const double* b_dev, double* c_dev, void* stream) {
   if (m % 128 || n % 128 || k % KC) return fail("bench_gemm_nt: m, n must be multiples of 128 and k of 16");
   if (set_attrs()) return 1;

@@ -116,6 +116,13 @@ class DeviceProblem:
     def launches_per_eval(self, want_grad: bool = True) -> int:
         return self._lib.eb200_gp_eval_launches(self._h, int(bool(want_grad)))
 
+    def profile_stages(self, p: np.ndarray, reps: int = 3) -> np.ndarray:
+        """Device milliseconds per stage [kbuild, cholesky, inverse+alpha, kinv+traces, finalize]."""
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        out = (ctypes.c_float * 5)()
+        _lib.check(self._lib.eb200_gp_profile_stages(self._h, _lib.as_double_ptr(p), reps, out), "profile_stages")
+        return np.array(list(out), dtype=np.float64)
+
     # -- diagnostics (tests only) -------------------------------------------------------------
     def debug_stage(self, p: np.ndarray, stage: int):
         p = np.ascontiguousarray(p, dtype=np.float64)

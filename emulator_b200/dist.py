@@ -1,0 +1,125 @@
+"""
+Sharding of independent problems over the GPUs of one box.
+
+One process per GPU (`torchrun`); unit i goes to rank ``i mod world_size`` (round-robin).  No
+collective touches the data path: a single ``all_gather`` per driver call collects the
+per-unit result rows (fitted hyperparameters, leave-one-out predictions, sweep outputs) on
+every rank -- NCCL over NVLink when the process group is NCCL, gloo in the CPU tests.
+Without an initialised process group everything degenerates to one rank.
+"""
+
+from __future__ import annotations
+
+import os
+from typing import List, Sequence
+
+import numpy as np
+
+
+def _pg():
+    try:
+        import torch.distributed as td
+    except Exception:  # pragma: no cover
+        return None
+    if td.is_available() and td.is_initialized():
+        return td
+    return None
+
+
+def rank() -> int:
+    td = _pg()
+    return td.get_rank() if td else 0
+
+
+def world_size() -> int:
+    td = _pg()
+    return td.get_world_size() if td else 1
+
+
+def local_device() -> int:
+    """CUDA device index of this rank (LOCAL_RANK under torchrun)."""
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def indices_of(rank_: int, world: int, count: int) -> List[int]:
+    """Round-robin assignment: unit i -> rank i mod world."""
+    return list(range(rank_, count, world))
+
+
+def my_indices(count: int) -> List[int]:
+    return indices_of(rank(), world_size(), count)
+
+
+def contiguous_slice(count: int, rank_: int = None, world: int = None):
+    """Contiguous 1/world slice [start, stop) of `count` rows (prediction sweeps)."""
+    rank_ = rank() if rank_ is None else rank_
+    world = world_size() if world is None else world
+    base, extra = divmod(count, world)
+    start = rank_ * base + min(rank_, extra)
+    return start, start + base + (1 if rank_ < extra else 0)
+
+
+def all_gather_rows(rows: np.ndarray, mine: Sequence[int], count: int) -> np.ndarray:
+    """
+    `rows` is a [count, ...] float64 array in which this rank has filled the entries listed in
+    `mine` (its round-robin share).  Returns the array with every rank's entries filled in.
+    """
+    td = _pg()
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    if td is None or td.get_world_size() == 1:
+        return rows
+    import torch
+
+    world = td.get_world_size()
+    per_rank = (count + world - 1) // world
+    width = int(np.prod(rows.shape[1:])) if rows.ndim > 1 else 1
+    send = np.zeros((per_rank, width))
+    flat = rows.reshape(count, width)
+    for slot, i in enumerate(mine):
+        send[slot] = flat[i]
+    use_cuda = td.get_backend() == "nccl"
+    dev = torch.device("cuda", local_device()) if use_cuda else torch.device("cpu")
+    send_t = torch.from_numpy(send).to(dev)
+    recv_t = torch.empty((world * per_rank, width), dtype=torch.float64, device=dev)
+    td.all_gather_into_tensor(recv_t, send_t)
+    recv = recv_t.cpu().numpy().reshape(world, per_rank, width)
+    out = flat.copy()
+    for r in range(world):
+        for slot, i in enumerate(indices_of(r, world, count)):
+            out[i] = recv[r, slot]
+    return out.reshape(rows.shape)
+
+
+def all_gather_concat(block: np.ndarray, count: int) -> np.ndarray:
+    """
+    Contiguous-slice counterpart: every rank holds rows [start, stop) of a [count, ...] result
+    (see `contiguous_slice`); returns the concatenation on every rank.
+    """
+    td = _pg()
+    block = np.ascontiguousarray(block, dtype=np.float64)
+    if td is None or td.get_world_size() == 1:
+        return block
+    import torch
+
+    world = td.get_world_size()
+    per_rank = (count + world - 1) // world
+    width = int(np.prod(block.shape[1:])) if block.ndim > 1 else 1
+    send = np.zeros((per_rank, width))
+    send[: len(block)] = block.reshape(len(block), width)
+    use_cuda = td.get_backend() == "nccl"
+    dev = torch.device("cuda", local_device()) if use_cuda else torch.device("cpu")
+    recv_t = torch.empty((world * per_rank, width), dtype=torch.float64, device=dev)
+    td.all_gather_into_tensor(recv_t, torch.from_numpy(send).to(dev))
+    recv = recv_t.cpu().numpy().reshape(world, per_rank, width)
+    parts = []
+    for r in range(world):
+        start, stop = contiguous_slice(count, r, world)
+        parts.append(recv[r, : stop - start])
+    out = np.concatenate(parts, axis=0)
+    return out.reshape((count,) + block.shape[1:])
+
+
+def barrier():
+    td = _pg()
+    if td is not None:
+        td.barrier()

@@ -1,0 +1,135 @@
+"""
+Emulator protocol (same attributes and methods as
+/root/reference/swiftemulator/emulators/base.py:21-172) plus the shared GP fit routine that
+every GP emulator of the reference spells out inline
+(gaussian_process.py:178-226, gaussian_process_bins.py:211-260,
+gaussian_process_mcmc.py:200-256, gaussian_process_one_dim.py:177-225).
+"""
+
+from __future__ import annotations
+
+import copy
+from typing import Dict, Hashable, List, Optional
+
+import attr
+import numpy as np
+from scipy.optimize import minimize
+
+from .. import george_compat as george
+from ..backend import ModelParameters, ModelSpecification, ModelValues
+
+
+def default_kernel(ndim: int):
+    """`1**2 * ExpSquaredKernel(np.ones(ndim), ndim=ndim)` -- the reference's default."""
+    return 1**2 * george.kernels.ExpSquaredKernel(np.ones(ndim), ndim=ndim)
+
+
+def build_gp(kernel, mean_model, x, y, yerr, device: int = 0):
+    """Create the GP the way the reference does: deep copy of the kernel, frozen mean."""
+    if mean_model is not None:
+        mean_model.train(independent=x, dependent=y)
+        gp = george.GP(copy.deepcopy(kernel), fit_kernel=True, mean=mean_model.george_model, fit_mean=False, device=device)
+    else:
+        gp = george.GP(copy.deepcopy(kernel), device=device)
+    gp.compute(x=x, yerr=yerr)
+    return gp
+
+
+def optimise_gp(gp, y):
+    """
+    scipy.optimize.minimize (BFGS, default options) on the negative log likelihood with its
+    analytic gradient, from the kernel's current parameter vector; the result is used whatever
+    `success` says, exactly as the reference does (gaussian_process.py:217-224).
+    """
+
+    def negative_log_likelihood(p):
+        gp.set_parameter_vector(p)
+        return -gp.log_likelihood(y)
+
+    def grad_negative_log_likelihood(p):
+        gp.set_parameter_vector(p)
+        return -gp.grad_log_likelihood(y)
+
+    result = minimize(fun=negative_log_likelihood, x0=gp.get_parameter_vector(), jac=grad_negative_log_likelihood)
+    gp.set_parameter_vector(result.x)
+    return result
+
+
+@attr.s
+class BaseEmulator(object):
+    ordering: Optional[List[Hashable]] = None
+    parameter_order: Optional[List[str]] = None
+
+    model_specification: Optional[ModelSpecification] = None
+    model_parameters: Optional[ModelParameters] = None
+    model_values: Optional[ModelValues] = None
+
+    independent_variables: Optional[np.array] = None
+    dependent_variables: Optional[np.array] = None
+    dependent_variable_errors: Optional[np.array] = None
+
+    emulator = None
+    #: scipy OptimizeResult of the last hyperparameter fit (not in the reference; diagnostics)
+    fit_result = None
+
+    def _build_arrays(self, model_specification, model_parameters, model_values):
+        raise NotImplementedError
+
+    def fit_model(self, model_specification, model_parameters, model_values):
+        raise NotImplementedError
+
+    def predict_values(self, independent: np.array, model_parameters: Dict[str, float]):
+        raise NotImplementedError
+
+    def predict_values_no_error(self, independent: np.array, model_parameters: Dict[str, float]):
+        raise NotImplementedError
+
+    def interactive_plot(self, *args, **kwargs):
+        raise NotImplementedError("plotting (matplotlib) is outside the accelerated hot path")
+
+
+def flatten_model_values(model_specification, model_parameters, model_values, with_independent: bool):
+    """
+    Flatten {uid: {independent, dependent[, dependent_error]}} into the float32 design matrix
+    the reference builds row by row (gaussian_process.py:89-131; 1-D variant without the
+    independent column gaussian_process_one_dim.py:88-121).  Row order = dict order.
+    Returns (X, y, yerr, ordering).
+    """
+    names = model_specification.parameter_names
+    n_par = model_specification.number_of_parameters
+    total = model_values.number_of_variables
+    width = n_par + (1 if with_independent else 0)
+    x = np.empty((total, width), dtype=np.float32)
+    y = np.empty(total, dtype=np.float32)
+    yerr = np.empty(total, dtype=np.float32)
+    ordering = []
+    row = 0
+    for uid in model_values.model_values.keys():
+        ordering.append(uid)
+        theta = np.array([model_parameters.model_parameters[uid][name] for name in names])
+        relation = model_values.model_values[uid]
+        dependent = relation["dependent"]
+        count = len(relation["independent"]) if with_independent else len(dependent)
+        errors = relation.get("dependent_error", np.zeros(count))
+        if np.ndim(errors) != 1:
+            raise AttributeError("Multiple dimensional errors are not currently supported in GPE mode")
+        stop = row + count
+        if with_independent:
+            x[row:stop, 0] = relation["independent"]
+            x[row:stop, 1:] = theta
+        else:
+            x[row:stop, :] = theta
+        y[row:stop] = dependent[:count]
+        yerr[row:stop] = errors[:count]
+        row = stop
+    assert row == total
+    return x, y, yerr, ordering
+
+
+def query_matrix(independent, model_parameters: Dict[str, float], parameter_order) -> np.ndarray:
+    """float32 query rows [independent_i, theta...] (gaussian_process.py:273-283)."""
+    theta = np.array([model_parameters[name] for name in parameter_order])
+    t = np.empty((len(independent), len(theta) + 1), dtype=np.float32)
+    t[:, 0] = independent
+    t[:, 1:] = theta
+    return t

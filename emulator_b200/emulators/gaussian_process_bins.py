@@ -1,0 +1,143 @@
+"""
+One independent GP per unique `independent` value (bin), kernel over the model parameters
+only -- API and data handling of
+/root/reference/swiftemulator/emulators/gaussian_process_bins.py:24-462.  The bins are
+independent problems: they are sharded round-robin over ranks (emulator_b200.dist) and, on
+one GPU, each owns its own device handle and stream.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import attr
+import numpy as np
+
+from .. import dist
+from .base import BaseEmulator, build_gp, default_kernel, optimise_gp
+
+
+@attr.s
+class GaussianProcessEmulatorBins(BaseEmulator):
+    kernel = attr.ib(default=None)
+    mean_model = attr.ib(default=None)
+    device: int = attr.ib(default=0)
+
+    n_bins: int = None
+    bin_centers: List[float] = None
+    bin_model_values: List[Dict[str, np.array]] = None
+    bin_gaussian_process: List = None
+    bin_fit_parameters: Optional[np.ndarray] = None
+
+    def _build_arrays(self, model_specification, model_parameters, model_values):
+        self.model_specification = model_specification
+        self.model_parameters = model_parameters
+        self.model_values = model_values
+        self.parameter_order = model_specification.parameter_names
+        names = self.parameter_order
+        n_par = model_specification.number_of_parameters
+        identifiers = list(model_values.model_values.keys())
+
+        centers = np.unique([v for uid in identifiers for v in model_values.model_values[uid]["independent"]])
+        self.n_bins = len(centers)
+        self.bin_centers = centers
+
+        per_bin = []
+        for center in centers:
+            thetas, dependent, errors = [], [], []
+            for uid in identifiers:
+                relation = model_values.model_values[uid]
+                independent = relation["independent"]
+                hit = independent == center  # exact float match, as in the reference (:121)
+                if not hit.any():
+                    continue
+                dependent.append(relation["dependent"][hit][0])
+                errors.append(relation.get("dependent_error", np.zeros(len(independent)))[hit][0])
+                thetas.append([model_parameters.model_parameters[uid][name] for name in names])
+                if np.ndim(errors) != 1:
+                    raise AttributeError("Multiple dimensional errors are not currently supported in GPE mode")
+            per_bin.append(
+                {
+                    "independent": np.array(thetas).reshape((len(dependent), n_par)),  # float64 (:146-156)
+                    "dependent": np.array(dependent).flatten(),
+                    "dependent_errors": np.array(errors).flatten(),
+                }
+            )
+        self.bin_model_values = per_bin
+
+    def fit_model(self, model_specification, model_parameters, model_values):
+        if self.bin_model_values is None:
+            self._build_arrays(model_specification, model_parameters, model_values)
+        if self.kernel is None:
+            self.kernel = default_kernel(self.model_specification.number_of_parameters)
+
+        n_hyper = len(self.kernel)
+        mine = dist.my_indices(self.n_bins)
+        gps = [None] * self.n_bins
+        fitted = np.zeros((self.n_bins, n_hyper))
+        for b in mine:
+            values = self.bin_model_values[b]
+            gp = build_gp(
+                self.kernel, self.mean_model, values["independent"], values["dependent"], values["dependent_errors"],
+                device=self.device,
+            )
+            optimise_gp(gp, values["dependent"])
+            gps[b] = gp
+            fitted[b] = gp.get_parameter_vector()
+        # collect every bin's optimum on every rank; bins fitted elsewhere get a GP at that optimum
+        fitted = dist.all_gather_rows(fitted, mine, self.n_bins)
+        for b in range(self.n_bins):
+            if gps[b] is None:
+                values = self.bin_model_values[b]
+                gp = build_gp(
+                    self.kernel, self.mean_model, values["independent"], values["dependent"],
+                    values["dependent_errors"], device=self.device,
+                )
+                gp.set_parameter_vector(fitted[b])
+                gps[b] = gp
+        self.bin_fit_parameters = fitted
+        self.bin_gaussian_process = gps
+
+    def _bin_indices(self, independent):
+        if self.bin_gaussian_process is None:
+            raise AttributeError("Please train the emulator with fit_model before attempting to make predictions.")
+        centers = np.array(self.bin_centers)
+        order = []
+        for value in independent:
+            where = np.where(centers == value)[0]
+            if len(where) == 0:
+                raise AttributeError(
+                    f"Requested independent variable {independent} not valid, ",
+                    f"this instance of GPE Bins is only valid at {centers}.",
+                )
+            order.append(where[0])
+        return order
+
+    def _query(self, model_parameters):
+        theta = np.array([model_parameters[name] for name in self.parameter_order])
+        # the reference pads with 0.98 theta and 1.02 theta "so george predicts > 1 point" and
+        # keeps row 1 (:338-345, :361-363); rows are independent, so one row is enough here
+        return theta.reshape(1, -1).astype(np.float64)
+
+    def predict_values(self, independent: np.array, model_parameters: Dict[str, float]):
+        order = self._bin_indices(independent)
+        t = self._query(model_parameters)
+        means, variances = [], []
+        for b in order:
+            mu, var = self.bin_gaussian_process[b].predict(
+                y=self.bin_model_values[b]["dependent"], t=t, return_cov=False, return_var=True
+            )
+            means.append(mu[0])
+            variances.append(var[0])
+        return np.array(means), np.array(variances)
+
+    def predict_values_no_error(self, independent: np.array, model_parameters: Dict[str, float]):
+        order = self._bin_indices(independent)
+        t = self._query(model_parameters)
+        means = []
+        for b in order:
+            mu = self.bin_gaussian_process[b].predict(
+                y=self.bin_model_values[b]["dependent"], t=t, return_cov=False, return_var=False
+            )
+            means.append(mu[0])
+        return np.array(means)

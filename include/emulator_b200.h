@@ -80,6 +80,12 @@ int eb200_gp_debug_alpha(eb200_gp* gp, double* alpha_host);
 /* number of kernel launches issued by one eval (graph nodes) */
 int eb200_gp_eval_launches(const eb200_gp* gp, int want_grad);
 
+/* Per-stage device time of one LML+grad evaluation (milliseconds, averaged over `reps` after
+ * one warm-up), launched kernel by kernel outside the CUDA graph with events in between:
+ * ms_out[0] = parameter prep + kernel-matrix build, [1] = Cholesky, [2] = triangular inverse +
+ * alpha, [3] = K^-1 tiles + gradient traces, [4] = final reduction. */
+int eb200_gp_profile_stages(eb200_gp* gp, const double* p_host, int reps, float* ms_out);
+
 /* Engine micro-benchmark: C[m][n] = A[m][k] * B[n][k]^T through the tile engine, device
  * pointers, m, n multiples of 128, k multiple of 16.  Used by bench.py to report the engine's
  * DMMA throughput next to cuBLAS DGEMM. */

@@ -1,0 +1,156 @@
+"""
+Generates tests/golden/*.npz by running the REFERENCE's own emulator code
+(/root/reference/swiftemulator, imported in this container) on seeded inputs, with `george`
+replaced by the oracle-backed shim (tests/oracle_george.py) because george itself is not
+installable here.  The vectors pin (a) the reference's data flattening / float32 rounding /
+optimiser flow and (b) the oracle's numbers, and travel to the GPU box where the CUDA path is
+checked against them.
+
+    python tests/golden/make_golden.py        (needs /root/reference; CPU only)
+"""
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import oracle_george  # noqa: E402
+
+oracle_george.install_reference_import_stubs()
+
+import swiftemulator as se  # noqa: E402  (the reference)
+from swiftemulator.emulators.gaussian_process import GaussianProcessEmulator as RefGPE  # noqa: E402
+from swiftemulator.emulators.gaussian_process_bins import GaussianProcessEmulatorBins as RefBins  # noqa: E402
+from swiftemulator.emulators.gaussian_process_one_dim import GaussianProcessEmulator1D as Ref1D  # noqa: E402
+from swiftemulator.emulators.multi_gaussian_process import MultipleGaussianProcessEmulator as RefMulti  # noqa: E402
+from swiftemulator.mean_models.linear import LinearMeanModel as RefLinear  # noqa: E402
+from swiftemulator.mean_models.offset import OffsetMeanModel as RefOffset  # noqa: E402
+from swiftemulator.sensitivity.cross_check import CrossCheck as RefCrossCheck  # noqa: E402
+
+from emulator_b200 import synthetic  # noqa: E402
+from oracle import gp_oracle  # noqa: E402
+
+
+def to_reference(spec, params, values):
+    rspec = se.ModelSpecification(
+        number_of_parameters=spec.number_of_parameters, parameter_names=spec.parameter_names,
+        parameter_limits=spec.parameter_limits,
+    )
+    return rspec, se.ModelParameters(model_parameters=params.model_parameters), se.ModelValues(
+        model_values={k: dict(v) for k, v in values.model_values.items()}
+    )
+
+
+def reference_test_fixture(seed):
+    """The data shape of the reference's own smoke tests (tests/test_emulator_gpe.py:21-58),
+    seeded: 2 parameters, 3 sims, independent = arange(10), random dependents, one sim without
+    dependent_error."""
+    from emulator_b200.backend import ModelParameters, ModelSpecification, ModelValues
+
+    rng = np.random.default_rng(seed)
+    spec = ModelSpecification(number_of_parameters=2, parameter_names=["x", "y"], parameter_limits=[[0.0, 1.0], [8.0, 9.0]])
+    params = ModelParameters(model_parameters={0: {"x": 0.1, "y": 8.1}, 1: {"x": 0.5, "y": 8.7}, 2: {"x": 0.9, "y": 8.4}})
+    values = {}
+    for uid in range(3):
+        entry = {"independent": np.arange(10, dtype=np.float64), "dependent": rng.random(10)}
+        if uid != 1:
+            entry["dependent_error"] = 0.1 * rng.random(10)
+        values[uid] = entry
+    return spec, params, ModelValues(model_values=values)
+
+
+def golden_gpe(name, n_par, sims, bins, seed, mean_model=None, fixture=False):
+    if fixture:
+        spec, params, values = reference_test_fixture(seed)
+    else:
+        spec, params, values = synthetic.make_model(n_par, sims, bins, seed=seed)
+    rspec, rparams, rvalues = to_reference(spec, params, values)
+    emu = RefGPE(mean_model=mean_model)
+    emu._build_arrays(rspec, rparams, rvalues)
+    x, y, yerr = emu.independent_variables.copy(), emu.dependent_variables.copy(), emu.dependent_variable_errors.copy()
+    d = n_par + 1
+    p0 = gp_oracle.default_parameter_vector(d)
+    # likelihood + gradient at x0 and at perturbed vectors, through the oracle GP the reference drives
+    probes = synthetic.perturbed_parameter_vectors(d, count=4, seed=seed + 5, scale=0.3)
+    if mean_model is not None:
+        mm = mean_model.copy(); mm.train(x, y); mean = mm.predict
+    else:
+        mean = None
+    gp = gp_oracle.OracleGP(d, p0, mean=mean)
+    gp.compute(x, yerr)
+    lml = []; grad = []
+    for p in probes:
+        gp.set_parameter_vector(p)
+        lml.append(gp.log_likelihood(y)); grad.append(gp.grad_log_likelihood(y))
+    emu.fit_model(rspec, rparams, rvalues)
+    p_fit = emu.emulator.get_parameter_vector()
+    query_x = np.linspace(0.05, 0.95, 7) if not fixture else np.arange(10, dtype=np.float64)
+    lo = np.array(spec.parameter_limits)[:, 0]
+    theta = {nm: float(lo[i]) + 0.37 + 0.05 * i for i, nm in enumerate(spec.parameter_names)}
+    mu, var = emu.predict_values(query_x, theta)
+    mu_only = emu.predict_values_no_error(query_x, theta)
+    np.savez(
+        os.path.join(HERE, name + ".npz"), n_par=n_par, sims=sims, bins=bins, seed=seed, fixture=int(fixture),
+        x=x, y=y, yerr=yerr, probes=probes, lml=np.array(lml), grad=np.array(grad), p_fit=p_fit,
+        query_x=query_x, theta=np.array([theta[nm] for nm in spec.parameter_names]), mu=mu, var=var, mu_only=mu_only,
+    )
+    print(name, "N =", len(y), "p_fit =", np.round(p_fit, 4))
+
+
+def golden_bins(name, n_par, sims, bins, seed):
+    spec, params, values = synthetic.make_model(n_par, sims, bins, seed=seed)
+    rspec, rparams, rvalues = to_reference(spec, params, values)
+    emu = RefBins()
+    emu.fit_model(rspec, rparams, rvalues)
+    p_fit = np.array([gp.get_parameter_vector() for gp in emu.bin_gaussian_process])
+    theta = {nm: 0.41 + 0.07 * i for i, nm in enumerate(spec.parameter_names)}
+    centers = np.array(emu.bin_centers)
+    mu, var = emu.predict_values(centers, theta)
+    np.savez(
+        os.path.join(HERE, name + ".npz"), n_par=n_par, sims=sims, bins=bins, seed=seed, p_fit=p_fit, centers=centers,
+        theta=np.array([theta[nm] for nm in spec.parameter_names]), mu=mu, var=var,
+        bin0_x=emu.bin_model_values[0]["independent"], bin0_y=emu.bin_model_values[0]["dependent"],
+        bin0_err=emu.bin_model_values[0]["dependent_errors"],
+    )
+    print(name, "bins =", len(centers))
+
+
+def golden_one_dim(name, n_par, sims, seed):
+    spec, params, values = synthetic.make_model(n_par, sims, 1, seed=seed)
+    rspec, rparams, rvalues = to_reference(spec, params, values)
+    emu = Ref1D()
+    emu.fit_model(rspec, rparams, rvalues)
+    theta = {nm: 0.3 + 0.1 * i for i, nm in enumerate(spec.parameter_names)}
+    mu, var = emu.predict_values(theta)
+    np.savez(
+        os.path.join(HERE, name + ".npz"), n_par=n_par, sims=sims, seed=seed, p_fit=emu.emulator.get_parameter_vector(),
+        theta=np.array([theta[nm] for nm in spec.parameter_names]), mu=mu, var=var, x=emu.independent_variables,
+    )
+    print(name)
+
+
+def golden_cross_check(name, n_par, sims, bins, seed):
+    spec, params, values = synthetic.make_model(n_par, sims, bins, seed=seed)
+    rspec, rparams, rvalues = to_reference(spec, params, values)
+    cc = RefCrossCheck()
+    cc.build_emulators(rspec, rparams, rvalues)
+    total, per_model = cc.get_mean_squared()
+    p_fit = np.array([cc.cross_emulators[uid].emulator.get_parameter_vector() for uid in cc.leave_out_order])
+    np.savez(os.path.join(HERE, name + ".npz"), n_par=n_par, sims=sims, bins=bins, seed=seed, total=total, p_fit=p_fit,
+             per_model=np.array([per_model[uid] for uid in cc.leave_out_order]))
+    print(name, "mean squared =", total)
+
+
+if __name__ == "__main__":
+    golden_gpe("gpe_small", 2, 12, 10, seed=101)
+    golden_gpe("gpe_noerr", 2, 3, 10, seed=102, fixture=True)
+    golden_gpe("gpe_linear_mean", 3, 20, 8, seed=103, mean_model=RefLinear())
+    golden_gpe("gpe_offset_mean", 2, 10, 6, seed=104, mean_model=RefOffset())
+    golden_bins("bins_small", 2, 24, 5, seed=105)
+    golden_one_dim("one_dim_small", 3, 30, seed=106)
+    golden_cross_check("cross_check_small", 2, 8, 6, seed=107)
