@@ -8,6 +8,7 @@
 
 #include "../../include/emulator_b200.h"
 #include "kernels.cuh"
+#include "potrf_dataflow.cuh"
 
 using namespace eb;
 
@@ -55,7 +56,8 @@ int pad_dim(int d) {
 enum OpKind {
   OP_PREP,
   OP_KBUILD,
-  OP_DIAG,
+  OP_POTRF_DF,     // persistent dataflow Cholesky (K generated in-kernel)
+  OP_DIAG_INV,     // batched 64x64 triangular inverses of the diagonal tiles
   OP_GEMM64_KK,    // Cfg64, A KCONTIG, B KCONTIG
   OP_GEMM128_KK,   // Cfg128, K/K
   OP_GEMM64_KM,    // Cfg64, A KCONTIG, B MCONTIG
@@ -98,6 +100,12 @@ struct eb200_gp {
   double *h_p = nullptr, *h_out = nullptr;  // pinned
   TileTask* tasks = nullptr;
   int2* ktiles = nullptr;
+  int2* ptiles = nullptr;     // potrf task list
+  int n_ptiles = 0;
+  unsigned* counter = nullptr;
+  int* ready = nullptr;
+  int* abort_flag = nullptr;
+  int n_sms = 148;
   int n_ktiles = 0, n_lauum = 0;
   std::vector<Op> ops;
   cudaGraphExec_t g_grad = nullptr, g_lml = nullptr;
@@ -153,30 +161,14 @@ void build_program(eb200_gp* h, std::vector<TileTask>& tasks) {
     op.kind = OP_KBUILD;
     ops.push_back(op);
   }
-  // ---- Cholesky ----
-  for (int s = 0; s < nT; ++s) {
-    for (int half = 0; half < 2; ++half) {
-      const int c = 2 * s + half;
-      if (half == 1) {
-        // rank-64 update of block column c from block column c-1
-        size_t off = tasks.size();
-        for (int i = c; i < nt; ++i) tasks.push_back({i * TB, c * TB, i * TB, (c - 1) * TB, c * TB, (c - 1) * TB, TB / KC, 0});
-        push_gemm(OP_GEMM64_KK, off, BUF_A, BUF_A, BUF_A, 0, -1.0, 1.0, 2);
-      }
-      Op dop;
-      dop.kind = OP_DIAG;
-      dop.dinv_tile = c;
-      dop.stage = 2;
-      ops.push_back(dop);
-      size_t off = tasks.size();
-      for (int i = c + 1; i < nt; ++i) tasks.push_back({i * TB, c * TB, i * TB, c * TB, 0, 0, TB / KC, 0});
-      push_gemm(OP_GEMM64_KK, off, BUF_A, BUF_A, BUF_DINV, c, 1.0, 0.0, 2);
-    }
-    size_t off = tasks.size();
-    for (int J = s + 1; J < nT; ++J)
-      for (int I = J; I < nT; ++I)
-        tasks.push_back({I * 128, J * 128, I * 128, s * 128, J * 128, s * 128, 128 / KC, I == J ? 1 : 0});
-    push_gemm(OP_GEMM128_KK, off, BUF_A, BUF_A, BUF_A, 0, -1.0, 1.0, 2);
+  // ---- Cholesky: one persistent dataflow kernel + batched diagonal inverses ----
+  {
+    Op op;
+    op.stage = 2;
+    op.kind = OP_POTRF_DF;
+    ops.push_back(op);
+    op.kind = OP_DIAG_INV;
+    ops.push_back(op);
   }
   // ---- triangular inverse: X = L^-1 ----
   {
@@ -279,8 +271,19 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
     case OP_KBUILD:
       DP_SWITCH(h->dp, (kbuild_kernel<DP><<<h->n_ktiles, 256, 0, st>>>(h->ktiles, h->X, h->noise, h->kp, h->n, np, h->A)));
       return 1;
-    case OP_DIAG:
-      diag_factor_kernel<<<1, 256, DIAG_SMEM_BYTES, st>>>(h->A, np, op.dinv_tile, h->dinv, h->logdet_part, h->info);
+    case OP_POTRF_DF: {
+      cudaMemsetAsync(h->counter, 0, sizeof(unsigned), st);
+      cudaMemsetAsync(h->ready, 0, (size_t)h->nt * h->nt * sizeof(int), st);
+      PotrfArgs pa;
+      pa.A = h->A; pa.ld = np; pa.nt = h->nt; pa.n = h->n; pa.X = h->X; pa.noise = h->noise; pa.kp = h->kp;
+      pa.tiles = h->ptiles; pa.ntasks = h->n_ptiles; pa.counter = h->counter; pa.ready = h->ready;
+      pa.logdet_part = h->logdet_part; pa.info = h->info; pa.abort_flag = h->abort_flag;
+      const int grid = std::min(h->n_sms, h->n_ptiles);
+      DP_SWITCH(h->dp, (potrf_dataflow_kernel<DP><<<grid, 256, PotrfSmem<DP>::BYTES, st>>>(pa)));
+      return 1;
+    }
+    case OP_DIAG_INV:
+      diag_inverse_kernel<<<h->nt, 256, DIAG_INV_SMEM_BYTES, st>>>(h->A, np, h->dinv);
       return 1;
     case OP_PLACE_DINV:
       place_dinv_kernel<<<h->nt, 256, 0, st>>>(h->A, np, h->dinv);
@@ -318,7 +321,7 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
       return 1;
     case OP_FINALIZE:
       finalize_kernel<<<1, 256, 0, st>>>(h->logdet_part, h->nt, h->z, h->n, h->trace_partial, h->n_lauum, h->dp, h->d,
-                                         want_grad, h->info, h->out_dev);
+                                         want_grad, h->info, h->abort_flag, h->out_dev);
       return 1;
   }
   return 0;
@@ -327,6 +330,7 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
 int enqueue_eval(eb200_gp* h, cudaStream_t st, int want_grad, int max_stage, double* kinv_out, int* launches) {
   int cnt = 0;
   CK(cudaMemsetAsync(h->info, 0, sizeof(int), st));
+  CK(cudaMemsetAsync(h->abort_flag, 0, sizeof(int), st));
   for (const Op& op : h->ops) {
     if (op.stage > max_stage) continue;
     if (op.grad_only && !want_grad) continue;
@@ -359,9 +363,15 @@ int set_attrs() {
   CK((set_gemm_attr<Cfg128, KCONTIG, KCONTIG>()));
   CK((set_gemm_attr<Cfg64, KCONTIG, MCONTIG>()));
   CK((set_gemm_attr<Cfg128, KCONTIG, MCONTIG>()));
-  CK(cudaFuncSetAttribute(diag_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
   CK(cudaFuncSetAttribute(var_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(diag_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_INV_SMEM_BYTES));
+#define SET_POTRF(DPV)                                                                                       \
+  CK(cudaFuncSetAttribute(potrf_dataflow_kernel<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                          PotrfSmem<DPV>::BYTES));
+  SET_POTRF(2) SET_POTRF(3) SET_POTRF(4) SET_POTRF(5) SET_POTRF(6) SET_POTRF(8) SET_POTRF(9) SET_POTRF(10)
+  SET_POTRF(12) SET_POTRF(16)
+#undef SET_POTRF
 #define SET_LAUUM(DPV)                                                                                       \
   CK(cudaFuncSetAttribute(lauum_trace_kernel<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                           LauumSmem<DPV>::BYTES));
@@ -466,6 +476,20 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMemset(h->z, 0, np * sizeof(double)));
   CK(cudaMemset(h->alpha, 0, np * sizeof(double)));
   CK(cudaMemset(h->W, 0, mat));
+  CK(cudaMemset(h->A, 0, mat));  // strictly-upper 64-blocks of diagonal 128-tiles must stay zero
+  CK(cudaMalloc(&h->counter, sizeof(unsigned)));
+  CK(cudaMalloc(&h->ready, (size_t)h->nt * h->nt * sizeof(int)));
+  CK(cudaMalloc(&h->abort_flag, sizeof(int)));
+  CK(cudaMemset(h->abort_flag, 0, sizeof(int)));
+  CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device));
+  {
+    std::vector<int2> pt;
+    for (int j = 0; j < h->nt; ++j)
+      for (int i = j; i < h->nt; ++i) pt.push_back(make_int2(i, j));
+    h->n_ptiles = (int)pt.size();
+    CK(cudaMalloc(&h->ptiles, pt.size() * sizeof(int2)));
+    CK(cudaMemcpy(h->ptiles, pt.data(), pt.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  }
 
   // inputs, padded
   {
@@ -508,7 +532,7 @@ int eb200_gp_destroy(eb200_gp* h) {
   if (h->g_lml) cudaGraphExecDestroy(h->g_lml);
   void* dev[] = {h->A, h->W, h->X, h->noise, h->r, h->z, h->alpha, h->dinv, h->logdet_part, h->tpartial,
                  h->trace_partial, h->p_dev, h->out_dev, h->kp, h->info, h->tasks, h->ktiles, h->T_dev, h->T_in,
-                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks};
+                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ptiles, h->counter, h->ready, h->abort_flag};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (h->h_p) cudaFreeHost(h->h_p);

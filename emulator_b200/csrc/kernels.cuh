@@ -104,77 +104,6 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const int2* __restrict__ ti
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// K2a: Cholesky of one 64x64 diagonal tile plus its triangular inverse, one CTA.
-// Writes L (zero strict upper) back into A, X = L^-1 into dinv[t], sum(log L_jj) into
-// logdet_part[t]; the first non-positive pivot is recorded in *info (1-based column), as
-// LAPACK dpotrf does for george's scipy.linalg.cholesky call.
-// ---------------------------------------------------------------------------------------
-constexpr int DS = TB + 1;  // padded smem stride
-constexpr int DIAG_SMEM_BYTES = 3 * TB * DS * (int)sizeof(double);
-
-__global__ void __launch_bounds__(256) diag_factor_kernel(double* __restrict__ A, int ld, int t,
-                                                           double* __restrict__ dinv,
-                                                           double* __restrict__ logdet_part,
-                                                           int* __restrict__ info) {
-  extern __shared__ double dsm[];
-  double* S = dsm;                 // working copy
-  double* L = dsm + TB * DS;       // factor
-  double* X = dsm + 2 * TB * DS;   // inverse
-  const int tid = threadIdx.x;
-  double* At = A + (size_t)t * TB * ld + (size_t)t * TB;
-  for (int e = tid; e < TB * TB; e += 256) {
-    int r = e >> 6, c = e & 63;
-    S[r * DS + c] = (c <= r) ? At[(size_t)r * ld + c] : 0.0;
-    L[r * DS + c] = 0.0;
-    X[r * DS + c] = 0.0;
-  }
-  const int ty = tid >> 4, tx = tid & 15;
-  for (int j = 0; j < TB; ++j) {
-    __syncthreads();
-    const double d = S[j * DS + j];
-    if (!(d > 0.0)) {
-      if (tid == 0) atomicCAS(info, 0, t * TB + j + 1);
-    }
-    const double rinv = 1.0 / sqrt(d);
-    if (tid == 0) L[j * DS + j] = d * rinv;
-    // column j of L
-    for (int i = j + 1 + tid; i < TB; i += 256) L[i * DS + j] = S[i * DS + j] * rinv;
-    // rank-1 update of the trailing lower triangle with lazily scaled column values
-    for (int i = j + 1 + ty; i < TB; i += 16) {
-      const double li = S[i * DS + j] * rinv;
-      for (int k = j + 1 + tx; k <= i; k += 16) {
-        const double lk = S[k * DS + j] * rinv;
-        S[i * DS + k] = fma(-li, lk, S[i * DS + k]);
-      }
-    }
-  }
-  __syncthreads();
-  // X = L^-1, row by row; 4 lanes cooperate on one column's dot product.
-  const int c = tid >> 2, q = tid & 3;
-  for (int i = 0; i < TB; ++i) {
-    double part = 0.0;
-    for (int k = c + q; k < i; k += 4) part = fma(L[i * DS + k], X[k * DS + c], part);
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    if (q == 0 && c <= i) {
-      const double di = 1.0 / L[i * DS + i];
-      X[i * DS + c] = (c == i) ? di : -part * di;
-    }
-    __syncthreads();
-  }
-  for (int e = tid; e < TB * TB; e += 256) {
-    int r = e >> 6, cc = e & 63;
-    At[(size_t)r * ld + cc] = L[r * DS + cc];
-    dinv[(size_t)t * TB * TB + e] = X[r * DS + cc];
-  }
-  if (tid == 0) {
-    double s = 0.0;
-    for (int j = 0; j < TB; ++j) s += log(L[j * DS + j]);
-    logdet_part[t] = s;
-  }
-}
-
 // Copy the 64x64 diagonal inverses into the diagonal of A (start of the triangular inverse).
 __global__ void __launch_bounds__(256) place_dinv_kernel(double* __restrict__ A, int ld,
                                                           const double* __restrict__ dinv) {
@@ -431,6 +360,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
                                                         const double* __restrict__ z, int n,
                                                         const double* __restrict__ partial, int ntask, int dp,
                                                         int d, int want_grad, const int* __restrict__ info,
+                                                        const int* __restrict__ abort_flag,
                                                         double* __restrict__ out) {
   __shared__ double red[256];
   double s = 0.0;
@@ -447,7 +377,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
     ld *= 2.0;
     const double quad = red[0];
     out[0] = -0.5 * ((double)n * TWO_PI_LOG + ld) - 0.5 * quad;
-    out[1 + d + 1] = (double)(*info);
+    out[1 + d + 1] = (*abort_flag != 0) ? -1.0 : (double)(*info);  // -1: device watchdog fired
     out[1 + d + 2] = ld;
     out[1 + d + 3] = quad;
   }
