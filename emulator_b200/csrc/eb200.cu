@@ -105,6 +105,8 @@ struct eb200_gp {
   unsigned* counter = nullptr;
   int* ready = nullptr;
   int* abort_flag = nullptr;
+  double* rdiag = nullptr;
+  unsigned long long* trace = nullptr;  // diagnostics only
   int n_sms = 148;
   int n_ktiles = 0, n_lauum = 0;
   std::vector<Op> ops;
@@ -277,7 +279,7 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
       PotrfArgs pa;
       pa.A = h->A; pa.ld = np; pa.nt = h->nt; pa.n = h->n; pa.X = h->X; pa.noise = h->noise; pa.kp = h->kp;
       pa.tiles = h->ptiles; pa.ntasks = h->n_ptiles; pa.counter = h->counter; pa.ready = h->ready;
-      pa.logdet_part = h->logdet_part; pa.info = h->info; pa.abort_flag = h->abort_flag;
+      pa.logdet_part = h->logdet_part; pa.info = h->info; pa.abort_flag = h->abort_flag; pa.trace = h->trace; pa.rdiag = h->rdiag;
       const int grid = std::min(h->n_sms, h->n_ptiles);
       DP_SWITCH(h->dp, (potrf_dataflow_kernel<DP><<<grid, 256, PotrfSmem<DP>::BYTES, st>>>(pa)));
       return 1;
@@ -480,6 +482,7 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMalloc(&h->counter, sizeof(unsigned)));
   CK(cudaMalloc(&h->ready, (size_t)h->nt * h->nt * sizeof(int)));
   CK(cudaMalloc(&h->abort_flag, sizeof(int)));
+  CK(cudaMalloc(&h->rdiag, (size_t)np * sizeof(double)));
   CK(cudaMemset(h->abort_flag, 0, sizeof(int)));
   CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device));
   {
@@ -532,7 +535,7 @@ int eb200_gp_destroy(eb200_gp* h) {
   if (h->g_lml) cudaGraphExecDestroy(h->g_lml);
   void* dev[] = {h->A, h->W, h->X, h->noise, h->r, h->z, h->alpha, h->dinv, h->logdet_part, h->tpartial,
                  h->trace_partial, h->p_dev, h->out_dev, h->kp, h->info, h->tasks, h->ktiles, h->T_dev, h->T_in,
-                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ptiles, h->counter, h->ready, h->abort_flag};
+                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ptiles, h->counter, h->ready, h->abort_flag, h->rdiag};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (h->h_p) cudaFreeHost(h->h_p);
@@ -669,6 +672,27 @@ int eb200_gp_debug_alpha(eb200_gp* h, double* alpha_host) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaMemcpy(alpha_host, h->alpha, h->n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int eb200_gp_debug_potrf_trace(eb200_gp* h, const double* p_host, unsigned long long* out_host, int* tiles_out) {
+  if (!h || !p_host || !out_host || !tiles_out) return fail("potrf_trace: null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMalloc(&h->trace, (size_t)h->n_ptiles * 6 * sizeof(unsigned long long)));
+  CK(cudaMemset(h->trace, 0, (size_t)h->n_ptiles * 6 * sizeof(unsigned long long)));
+  memcpy(h->h_p, p_host, (h->d + 1) * sizeof(double));
+  CK(cudaMemcpyAsync(h->p_dev, h->h_p, (h->d + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  int rc = enqueue_eval(h, h->stream, 0, 2, nullptr, nullptr);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (!rc && e == cudaSuccess) {
+    e = cudaMemcpy(out_host, h->trace, (size_t)h->n_ptiles * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(tiles_out, h->ptiles, (size_t)h->n_ptiles * sizeof(int2), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(h->trace);
+  h->trace = nullptr;
+  h->factor_valid = false;
+  if (rc) return rc;
+  CK(e);
   return 0;
 }
 

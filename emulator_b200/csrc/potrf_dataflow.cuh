@@ -30,13 +30,29 @@ struct PotrfArgs {
   unsigned* counter;      // task counter (zeroed before the launch)
   int* ready;             // [nt*nt] tile flags (zeroed before the launch)
   double* logdet_part;    // [nt]
+  double* rdiag;          // [nt][64] reciprocal pivots 1 / L_jj, published with the diagonal tile
   int* info;
   int* abort_flag;        // watchdog: set when a wait exceeded its budget
+  unsigned long long* trace;  // optional [ntasks][6] globaltimer stamps (diagnostics), or nullptr
 };
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define EB_STAMP(slot)                                                            \
+  do {                                                                            \
+    if (a.trace != nullptr && tid == 0) a.trace[(size_t)task * 6 + (slot)] = gtime(); \
+  } while (0)
+
+// Flags are polled with a relaxed gpu-scope load: an acquire load would make ptxas emit
+// CCTL.IVALL (L1 invalidate + drain of every outstanding load, including the cp.async ring) on
+// every poll.  No L1 invalidation is needed because the tile data guarded by a flag is only ever
+// read through L2 (cp.async.cg / ld.global.cg); the producer fences before its release store.
+__device__ __forceinline__ int ld_flag(const int* p) {
   int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release(int* p, int v) {
@@ -48,10 +64,10 @@ __device__ __forceinline__ bool wait_ready(const int* flag, int* abort_flag) {
   bool ok = true;
   if ((threadIdx.x & 31) == 0) {
     long long spins = 0;
-    while (ld_acquire(flag) == 0) {
-      __nanosleep(40);
+    while (ld_flag(flag) == 0) {
+      __nanosleep(20);
       if ((++spins & 0x3ff) == 0) {
-        if (spins > (1ll << 24) || ld_acquire(abort_flag) != 0) {  // ~1 s
+        if (spins > (1ll << 24) || ld_flag(abort_flag) != 0) {  // ~1 s
           atomicExch(abort_flag, 1);
           ok = false;
           break;
@@ -63,12 +79,13 @@ __device__ __forceinline__ bool wait_ready(const int* flag, int* abort_flag) {
   return ok;
 }
 
+constexpr int PSTAGES = 4;  // cp.async ring depth of the dataflow kernel
 constexpr int PS = 65;  // padded stride of the 64x64 finalisation buffers
 
 template <int DP>
 struct PotrfSmem {
   using E = Engine<CfgP, KCONTIG, KCONTIG>;
-  static constexpr int PIPE = STAGES * E::STAGE_DOUBLES;
+  static constexpr int PIPE = PSTAGES * E::STAGE_DOUBLES;
   static constexpr int C_OFF = PIPE;                 // [64][65]
   static constexpr int L_OFF = C_OFF + 64 * PS;      // [64][65]
   static constexpr int XI_OFF = L_OFF + 64 * PS;     // [DP][64]
@@ -112,6 +129,7 @@ __global__ void __launch_bounds__(256, 1) potrf_dataflow_kernel(const PotrfArgs 
     const int ti = tile.x, tj = tile.y;
     const int i0 = ti * 64, j0 = tj * 64;
     bool ok = true;
+    EB_STAMP(0);
 
     // stage the training inputs of the tile's rows / columns for the K_ij generation
     for (int e = tid; e < 64 * DP; e += 256) {
@@ -120,59 +138,11 @@ __global__ void __launch_bounds__(256, 1) potrf_dataflow_kernel(const PotrfArgs 
       sXj[m * 64 + r] = a.X[(size_t)(j0 + r) * DP + m];
     }
 
-    // ---- left-looking accumulation over the finished panels: acc = sum_k L_ik L_jk^T ----
-    double acc[CfgP::MI][CfgP::NI][2];
-#pragma unroll
-    for (int mi = 0; mi < CfgP::MI; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < CfgP::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    {
-      const int nk = tj * (64 / KC);
-      const double* Ag = a.A + (size_t)i0 * ld;
-      const double* Bg = a.A + (size_t)j0 * ld;
-      const int* ready_i = a.ready + (size_t)ti * nt;
-      const int* ready_j = a.ready + (size_t)tj * nt;
-      auto issue = [&](int kt) {
-        if ((kt & 3) == 0) {
-          const int kc = kt >> 2;
-          ok = wait_ready(ready_i + kc, a.abort_flag) && ok;
-          if (ti != tj) ok = wait_ready(ready_j + kc, a.abort_flag) && ok;
-        }
-        E::load_stage(gsm + (kt % STAGES) * E::STAGE_DOUBLES, Ag, ld, Bg, ld, kt, tid);
-      };
-#pragma unroll
-      for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nk) issue(s);
-        cp_async_commit();
-      }
-      for (int kt = 0; kt < nk; ++kt) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {
-          const int nxt = kt + STAGES - 1;
-          if (nxt < nk) issue(nxt);
-          cp_async_commit();
-        }
-        const double* sA = gsm + (kt % STAGES) * E::STAGE_DOUBLES;
-        const double* sB = sA + E::SA::DOUBLES;
-#pragma unroll
-        for (int kk = 0; kk < KC; kk += 4) {
-          double af[CfgP::MI], bf[CfgP::NI];
-#pragma unroll
-          for (int mi = 0; mi < CfgP::MI; ++mi) af[mi] = sA[(wm0 + mi * 8 + g) * E::SA::STRIDE + kk + t];
-#pragma unroll
-          for (int ni = 0; ni < CfgP::NI; ++ni) bf[ni] = sB[(wn0 + ni * 8 + g) * E::SB::STRIDE + kk + t];
-#pragma unroll
-          for (int mi = 0; mi < CfgP::MI; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
-        }
-      }
-      cp_async_wait<0>();
-    }
-    __syncthreads();  // sXi / sXj staged (also when nk == 0)
+    __syncthreads();  // sXi / sXj staged
 
-    // ---- C = K_ij - acc, generated in the accumulator layout and parked in shared memory ----
+    // ---- acc = -K_ij, generated straight into the accumulator layout (before any panel wait,
+    //      so the exp() work overlaps the wait for the producers) ----
+    double acc[CfgP::MI][CfgP::NI][2];
     {
       const double amp = a.kp->amp;
       double r2[CfgP::MI][CfgP::NI * 2];
@@ -198,10 +168,10 @@ __global__ void __launch_bounds__(256, 1) potrf_dataflow_kernel(const PotrfArgs 
       }
 #pragma unroll
       for (int mi = 0; mi < CfgP::MI; ++mi) {
-        const int lr = wm0 + mi * 8 + g, gi = i0 + lr;
+        const int gi = i0 + wm0 + mi * 8 + g;
 #pragma unroll
         for (int c = 0; c < CfgP::NI * 2; ++c) {
-          const int lc = wn0 + (c >> 1) * 8 + 2 * t + (c & 1), gj = j0 + lc;
+          const int gj = j0 + wn0 + (c >> 1) * 8 + 2 * t + (c & 1);
           double kv;
           if (gi < a.n && gj < a.n) {
             kv = amp * exp(-0.5 * r2[mi][c]);
@@ -209,106 +179,224 @@ __global__ void __launch_bounds__(256, 1) potrf_dataflow_kernel(const PotrfArgs 
           } else {
             kv = (gi == gj) ? 1.0 : 0.0;
           }
-          sC[lr * PS + lc] = kv - acc[mi][c >> 1][c & 1];
+          acc[mi][c >> 1][c & 1] = -kv;
         }
       }
     }
-    __syncthreads();
+    EB_STAMP(1);
 
-    double* At = a.A + (size_t)i0 * ld + j0;
-    if (ti == tj) {
-      // ---- diagonal tile: Cholesky, every thread keeps a 4x4 strided block in registers ----
-      const int ty = tid >> 4, tx = tid & 15;
-      double v[4][4];
-#pragma unroll
-      for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) v[aa][bb] = sC[(ty + 16 * aa) * PS + tx + 16 * bb];
-      if (tx == 0) {
-#pragma unroll
-        for (int aa = 0; aa < 4; ++aa) colbuf[ty + 16 * aa] = v[aa][0];
+    // ---- left-looking accumulation over the finished panels: acc += sum_k L_ik L_jk^T ----
+    {
+      const int nk = tj * (64 / KC);
+      const double* Ag = a.A + (size_t)i0 * ld;
+      const double* Bg = a.A + (size_t)j0 * ld;
+      const int* ready_i = a.ready + (size_t)ti * nt;
+      const int* ready_j = a.ready + (size_t)tj * nt;
+      // leading tile columns whose panels are already published (one coalesced look per warp)
+      int known = 0;
+      for (int base = 0; base < tj; base += 32) {
+        const int kc = base + lane;
+        int f = 1;
+        if (kc < tj) f = (ld_flag(ready_i + kc) != 0) && (ld_flag(ready_j + kc) != 0);
+        const unsigned missing = __ballot_sync(0xffffffffu, f == 0);
+        if (missing) {
+          known = base + __ffs(missing) - 1;
+          break;
+        }
+        known = min(base + 32, tj);
       }
-      __syncthreads();
-      for (int j = 0; j < 64; ++j) {
-        const double* col = colbuf + (j & 1) * 64;
-        const double d = col[j];
-        if (!(d > 0.0) && tid == 0) atomicCAS(a.info, 0, j0 + j + 1);
-        const double rinv = rsqrt(d);
-        double li[4], lk[4];
-#pragma unroll
-        for (int aa = 0; aa < 4; ++aa) li[aa] = col[ty + 16 * aa] * rinv;
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) lk[bb] = col[tx + 16 * bb] * rinv;
-#pragma unroll
-        for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-          for (int bb = 0; bb < 4; ++bb) {
-            const int row = ty + 16 * aa, cc = tx + 16 * bb;
-            if (cc > j && cc <= row) v[aa][bb] = fma(-li[aa], lk[bb], v[aa][bb]);
+      auto issue = [&](int kt) {
+        if ((kt & 3) == 0) {
+          const int kc = kt >> 2;
+          if (kc >= known) {
+            ok = wait_ready(ready_i + kc, a.abort_flag) && ok;
+            if (ti != tj) ok = wait_ready(ready_j + kc, a.abort_flag) && ok;
           }
-        if (tid < 64) sL[tid * PS + j] = (tid > j) ? col[tid] * rinv : ((tid == j) ? d * rinv : 0.0);
-        // owners of column j+1 publish it for the next step
-        if (j + 1 < 64 && tx == ((j + 1) & 15)) {
-          const int bb = (j + 1) >> 4;
-          double* nxt = colbuf + ((j + 1) & 1) * 64;
+        }
+        E::load_stage(gsm + (kt % PSTAGES) * E::STAGE_DOUBLES, Ag, ld, Bg, ld, kt, tid);
+      };
 #pragma unroll
-          for (int aa = 0; aa < 4; ++aa) {
-            double val = (bb == 0) ? v[aa][0] : (bb == 1) ? v[aa][1] : (bb == 2) ? v[aa][2] : v[aa][3];
-            nxt[ty + 16 * aa] = val;
+      for (int s = 0; s < PSTAGES - 1; ++s) {
+        if (s < nk) issue(s);
+        cp_async_commit();
+      }
+      for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<PSTAGES - 2>();
+        __syncthreads();
+        const double* sA = gsm + (kt % PSTAGES) * E::STAGE_DOUBLES;
+        const double* sB = sA + E::SA::DOUBLES;
+#pragma unroll
+        for (int kk = 0; kk < KC; kk += 4) {
+          double af[CfgP::MI], bf[CfgP::NI];
+#pragma unroll
+          for (int mi = 0; mi < CfgP::MI; ++mi) af[mi] = sA[(wm0 + mi * 8 + g) * E::SA::STRIDE + kk + t];
+#pragma unroll
+          for (int ni = 0; ni < CfgP::NI; ++ni) bf[ni] = sB[(wn0 + ni * 8 + g) * E::SB::STRIDE + kk + t];
+#pragma unroll
+          for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        }
+        // refill the stage consumed in the previous iteration (every warp is past the barrier
+        // above, so nobody still reads it); a flag wait here never delays math on loaded stages
+        {
+          const int nxt = kt + PSTAGES - 1;
+          if (nxt < nk) issue(nxt);
+          cp_async_commit();
+        }
+      }
+      cp_async_wait<0>();
+    }
+    // ---- C = -acc parked in shared memory ----
+#pragma unroll
+    for (int mi = 0; mi < CfgP::MI; ++mi) {
+      const int lr = wm0 + mi * 8 + g;
+#pragma unroll
+      for (int c = 0; c < CfgP::NI * 2; ++c) sC[lr * PS + wn0 + (c >> 1) * 8 + 2 * t + (c & 1)] = -acc[mi][c >> 1][c & 1];
+    }
+    __syncthreads();
+    EB_STAMP(2);
+    double* At = a.A + (size_t)i0 * ld + j0;
+    // Finalisation layout: warp w owns columns 8w..8w+7 of the tile, lane owns rows lane, lane+32.
+    double v[2][8];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[sl][c] = sC[(lane + 32 * sl) * PS + 8 * warp + c];
+    if (ti == tj) {
+      // ---- diagonal tile: right-looking Cholesky by 8-column panels; the owning warp factorises
+      //      its panel warp-synchronously (shuffles only), the warps to its right apply it ----
+      for (int p = 0; p < 8; ++p) {
+        if (warp == p) {
+          const int sj = p >> 2;            // row slot of this panel's pivot rows
+          const int ob = 8 * (p & 3);       // lane of the first pivot row
+          double dloc = sj ? v[1][0] : v[0][0];
+          double d = __shfl_sync(0xffffffffu, dloc, ob);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (!(d > 0.0) && lane == 0) atomicCAS(a.info, 0, j0 + 8 * p + c + 1);
+            const double rinv = rsqrt(d);
+            if (lane == ob + c) rdiag[8 * p + c] = rinv;
+            const double l0 = v[0][c] * rinv, l1 = v[1][c] * rinv;
+            v[0][c] = l0;
+            v[1][c] = l1;
+            const double lsel = sj ? l1 : l0;
+            if (c < 7) {
+              // next pivot, computed by its own lane (keeps the second shuffle off the chain)
+              const double nloc = fma(-lsel, lsel, sj ? v[1][c + 1] : v[0][c + 1]);
+              d = __shfl_sync(0xffffffffu, nloc, ob + c + 1);
+            }
+#pragma unroll
+            for (int c2 = c + 1; c2 < 8; ++c2) {
+              const double lk = __shfl_sync(0xffffffffu, lsel, ob + c2);
+              v[0][c2] = fma(-l0, lk, v[0][c2]);
+              v[1][c2] = fma(-l1, lk, v[1][c2]);
+            }
           }
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const int row = lane + 32 * sl, col = 8 * p + c;
+              sL[row * PS + col] = (row >= col) ? v[sl][c] : 0.0;
+            }
         }
         __syncthreads();
-      }
-      // store L_jj (zero strict upper), log-determinant share
-      for (int e = tid; e < 64 * 64; e += 256) {
-        const int r = e >> 6, c = e & 63;
-        At[(size_t)r * ld + c] = (c <= r) ? sL[r * PS + c] : 0.0;
-      }
-      if (tid == 0) {
-        double s = 0.0;
-        for (int j = 0; j < 64; ++j) s += log(sL[j * PS + j]);
-        a.logdet_part[tj] = s;
-      }
-    } else {
-      // ---- off-diagonal tile: L_ij = C L_jj^-T by forward substitution, 4 lanes per row ----
-      ok = wait_ready(a.ready + (size_t)tj * nt + tj, a.abort_flag) && ok;
-      const double* Lg = a.A + (size_t)j0 * ld + j0;
-      for (int e = tid; e < 64 * 64; e += 256) {
-        const int r = e >> 6, c = e & 63;
-        sL[r * PS + c] = __ldcg(Lg + (size_t)r * ld + c);
-      }
-      __syncthreads();
-      if (tid < 64) rdiag[tid] = 1.0 / sL[tid * PS + tid];
-      __syncthreads();
-      const int r = tid >> 2, q = tid & 3;
-      double x[16];
+        if (warp > p) {
+          double ar[2][8];
 #pragma unroll
-      for (int m = 0; m < 16; ++m) x[m] = sC[r * PS + q + 4 * m];
-      const int src_base = lane & ~3;
+          for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
-      for (int k = 0; k < 64; ++k) {
-        const int qk = k & 3, mk = k >> 2;
-        double xk = (q == qk) ? x[mk] * rdiag[k] : 0.0;
-        xk = __shfl_sync(0xffffffffu, xk, src_base + qk);
-        if (q == qk) x[mk] = xk;
+            for (int k = 0; k < 8; ++k) ar[sl][k] = sL[(lane + 32 * sl) * PS + 8 * p + k];
 #pragma unroll
-        for (int m = mk; m < 16; ++m) {
-          const int col = q + 4 * m;
-          if (col > k) x[m] = fma(-xk, sL[col * PS + k], x[m]);
+          for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const double b = sL[(8 * warp + c) * PS + 8 * p + k];
+              v[0][c] = fma(-ar[0][k], b, v[0][c]);
+              v[1][c] = fma(-ar[1][k], b, v[1][c]);
+            }
         }
       }
-#pragma unroll
-      for (int m = 0; m < 16; ++m) sC[r * PS + q + 4 * m] = x[m];
+      // store L_jj (zero strict upper) and the reciprocal pivots
+      for (int e = tid; e < 64 * 64; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        At[(size_t)r * ld + c] = sL[r * PS + c];
+      }
+      if (tid < 64) a.rdiag[(size_t)tj * 64 + tid] = rdiag[tid];
+    } else {
+      // ---- off-diagonal tile: L_ij = C L_jj^-T, forward substitution by 8-column panels ----
+      ok = wait_ready(a.ready + (size_t)tj * nt + tj, a.abort_flag) && ok;
+      EB_STAMP(3);
+      const double* Lg = a.A + (size_t)j0 * ld + j0;
+      for (int e = tid; e < 64 * 32; e += 256) {
+        const int r = e >> 5, c = (e & 31) * 2;
+        const double2 val = __ldcg(reinterpret_cast<const double2*>(Lg + (size_t)r * ld + c));
+        sL[r * PS + c] = val.x;
+        sL[r * PS + c + 1] = val.y;
+      }
+      if (tid < 64) rdiag[tid] = __ldcg(a.rdiag + (size_t)tj * 64 + tid);
       __syncthreads();
+      for (int p = 0; p < 8; ++p) {
+        if (warp == p) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const double rd = rdiag[8 * p + c];
+            const double x0 = v[0][c] * rd, x1 = v[1][c] * rd;
+            v[0][c] = x0;
+            v[1][c] = x1;
+#pragma unroll
+            for (int c2 = c + 1; c2 < 8; ++c2) {
+              const double lv = sL[(8 * p + c2) * PS + 8 * p + c];
+              v[0][c2] = fma(-x0, lv, v[0][c2]);
+              v[1][c2] = fma(-x1, lv, v[1][c2]);
+            }
+          }
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sC[(lane + 32 * sl) * PS + 8 * p + c] = v[sl][c];
+        }
+        __syncthreads();
+        if (warp > p) {
+          double ar[2][8];
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ar[sl][k] = sC[(lane + 32 * sl) * PS + 8 * p + k];
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const double b = sL[(8 * warp + c) * PS + 8 * p + k];
+              v[0][c] = fma(-ar[0][k], b, v[0][c]);
+              v[1][c] = fma(-ar[1][k], b, v[1][c]);
+            }
+        }
+      }
       for (int e = tid; e < 64 * 64; e += 256) {
         const int rr = e >> 6, c = e & 63;
         At[(size_t)rr * ld + c] = sC[rr * PS + c];
       }
     }
     // ---- publish ----
-    __threadfence();
-    const int all_ok = __syncthreads_and(ok ? 1 : 0);
-    if (tid == 0) st_release(a.ready + (size_t)ti * nt + tj, 1);
+    EB_STAMP(4);
+    const int all_ok = __syncthreads_and(ok ? 1 : 0);  // every thread's tile stores happen-before ...
+    if (tid == 0) {
+      __threadfence();                                  // ... this cumulative device-scope fence
+      st_release(a.ready + (size_t)ti * nt + tj, 1);
+    }
+    EB_STAMP(5);
+    if (ti == tj) {
+      // log-determinant share, off the critical path: sum_j log L_jj = -sum_j log(1 / L_jj)
+      if (tid < 64) colbuf[tid] = log(rdiag[tid]);
+      __syncthreads();
+      if (tid == 0) {
+        double sum = 0.0;
+        for (int j = 0; j < 64; ++j) sum += colbuf[j];
+        a.logdet_part[tj] = -sum;
+      }
+    }
     if (!all_ok) break;  // watchdog fired somewhere in this CTA: leave (host reports the abort flag)
   }
 }

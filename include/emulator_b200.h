@@ -80,6 +80,11 @@ int eb200_gp_debug_alpha(eb200_gp* gp, double* alpha_host);
 /* number of kernel launches issued by one eval (graph nodes) */
 int eb200_gp_eval_launches(const eb200_gp* gp, int want_grad);
 
+/* Per-task globaltimer stamps (ns) of the dataflow Cholesky: out[task][6] = {claimed, panels
+ * accumulated, C formed, diagonal factor visible (off-diagonal tiles), tile stored, published};
+ * tiles_out[task][2] = (tile row, tile column).  ntasks = nt (nt + 1) / 2, nt = padded_n / 64. */
+int eb200_gp_debug_potrf_trace(eb200_gp* gp, const double* p_host, unsigned long long* out_host, int* tiles_out);
+
 /* Per-stage device time of one LML+grad evaluation (milliseconds, averaged over `reps` after
  * one warm-up), launched kernel by kernel outside the CUDA graph with events in between:
  * ms_out[0] = parameter prep + kernel-matrix build, [1] = Cholesky, [2] = triangular inverse +
