@@ -8,7 +8,7 @@
 
 #include "../../include/emulator_b200.h"
 #include "kernels.cuh"
-#include "potrf_dataflow.cuh"
+#include "factor_dataflow.cuh"
 
 using namespace eb;
 
@@ -56,29 +56,19 @@ int pad_dim(int d) {
 enum OpKind {
   OP_PREP,
   OP_KBUILD,
-  OP_POTRF_DF,     // persistent dataflow Cholesky (K generated in-kernel)
-  OP_DIAG_INV,     // batched 64x64 triangular inverses of the diagonal tiles
-  OP_GEMM64_KK,    // Cfg64, A KCONTIG, B KCONTIG
-  OP_GEMM128_KK,   // Cfg128, K/K
-  OP_GEMM64_KM,    // Cfg64, A KCONTIG, B MCONTIG
-  OP_GEMM128_KM,   // Cfg128, K/M
-  OP_PLACE_DINV,
+  OP_FACTOR_DF,    // persistent dataflow Cholesky + triangular inverse (K generated in-kernel)
   OP_TRMV,
   OP_TRMV_T,
   OP_LAUUM,
   OP_FINALIZE
 };
 
-enum Buf { BUF_A = 0, BUF_W = 1, BUF_DINV = 2 };
-
 struct Op {
   OpKind kind;
   int task_off = 0, task_cnt = 0;
-  int cbuf = BUF_A, abuf = BUF_A, bbuf = BUF_A;
-  int dinv_tile = 0;  // for BUF_DINV operands / OP_DIAG
-  double alpha = 1.0, beta = 0.0;
-  int stage = 0;      // debug stage this op belongs to (1 kbuild, 2 potrf, 3 trtri, 4 lauum/trace)
+  int stage = 0;      // 1 params (+ diagnostic kbuild), 2 factorisation, 3 alpha, 4 K^-1 + traces, 5 final
   bool grad_only = false;
+  bool debug_only = false;
 };
 
 template <class Cfg, int LA, int LB>
@@ -93,17 +83,18 @@ struct eb200_gp {
   int device = 0, n = 0, d = 0, dp = 0, np = 0, nt = 0, nT = 0;
   cudaStream_t stream = nullptr;
   double *A = nullptr, *W = nullptr, *X = nullptr, *noise = nullptr, *r = nullptr, *z = nullptr, *alpha = nullptr;
-  double *dinv = nullptr, *logdet_part = nullptr, *tpartial = nullptr, *trace_partial = nullptr;
+  double *logdet_part = nullptr, *tpartial = nullptr, *trace_partial = nullptr;
   double *p_dev = nullptr, *out_dev = nullptr;
   KernelParams* kp = nullptr;
   int* info = nullptr;
   double *h_p = nullptr, *h_out = nullptr;  // pinned
   TileTask* tasks = nullptr;
   int2* ktiles = nullptr;
-  int2* ptiles = nullptr;     // potrf task list
-  int n_ptiles = 0;
+  FactorTask* ftasks = nullptr;  // dataflow task list
+  int n_ftasks = 0;
   unsigned* counter = nullptr;
   int* ready = nullptr;
+  int* xready = nullptr;
   int* abort_flag = nullptr;
   double* rdiag = nullptr;
   unsigned long long* trace = nullptr;  // diagnostics only
@@ -122,113 +113,30 @@ struct eb200_gp {
 
 namespace {
 
-double* buf_ptr(eb200_gp* h, int b, int dinv_tile) {
-  if (b == BUF_A) return h->A;
-  if (b == BUF_W) return h->W;
-  return h->dinv + (size_t)dinv_tile * TB * TB;
-}
-int buf_ld(eb200_gp* h, int b) { return b == BUF_DINV ? TB : h->np; }
-
 void sort_tasks(std::vector<TileTask>& v, size_t off) {
   std::stable_sort(v.begin() + off, v.end(), [](const TileTask& a, const TileTask& b) { return a.nk > b.nk; });
 }
 
-// Build the static launch program for one (np): Cholesky (right-looking, 128-wide outer panels
-// made of two 64-wide sub-panels), recursive blocked triangular inverse, X^T X + traces.
+// Build the static launch program for one (np): parameters, dataflow factorisation
+// (Cholesky + triangular inverse), alpha, X^T X tiles + gradient traces, final reduction.
 void build_program(eb200_gp* h, std::vector<TileTask>& tasks) {
-  const int nt = h->nt, nT = h->nT, np = h->np;
+  const int nT = h->nT, np = h->np;
   auto& ops = h->ops;
-  auto push_gemm = [&](OpKind kind, size_t off, int cb, int ab, int bb, int dt, double alpha, double beta,
-                       int stage) {
-    if (tasks.size() == off) return;
-    sort_tasks(tasks, off);
-    Op op;
-    op.kind = kind;
-    op.task_off = (int)off;
-    op.task_cnt = (int)(tasks.size() - off);
-    op.cbuf = cb;
-    op.abuf = ab;
-    op.bbuf = bb;
-    op.dinv_tile = dt;
-    op.alpha = alpha;
-    op.beta = beta;
-    op.stage = stage;
-    ops.push_back(op);
-  };
   {
     Op op;
     op.kind = OP_PREP;
     op.stage = 1;
     ops.push_back(op);
-    op.kind = OP_KBUILD;
+    op.kind = OP_KBUILD;  // diagnostics only: the product path generates K inside the factorisation
+    op.debug_only = true;
     ops.push_back(op);
   }
-  // ---- Cholesky: one persistent dataflow kernel + batched diagonal inverses ----
+  // ---- Cholesky + triangular inverse: one persistent dataflow kernel ----
   {
     Op op;
     op.stage = 2;
-    op.kind = OP_POTRF_DF;
+    op.kind = OP_FACTOR_DF;
     ops.push_back(op);
-    op.kind = OP_DIAG_INV;
-    ops.push_back(op);
-  }
-  // ---- triangular inverse: X = L^-1 ----
-  {
-    Op op;
-    op.kind = OP_PLACE_DINV;
-    op.stage = 3;
-    ops.push_back(op);
-  }
-  {
-    // level 0: inside every 128 block, X21 = -X22 (L21 X11) with 64x64 tiles
-    size_t off = tasks.size();
-    for (int b = 0; b < nT; ++b) {
-      int r0 = b * 128;
-      tasks.push_back({r0 + 64, r0, r0 + 64, r0, r0, r0, TB / KC, 0});
-    }
-    push_gemm(OP_GEMM64_KM, off, BUF_W, BUF_A, BUF_A, 0, 1.0, 0.0, 3);
-    off = tasks.size();
-    for (int b = 0; b < nT; ++b) {
-      int r0 = b * 128;
-      tasks.push_back({r0 + 64, r0, r0 + 64, r0 + 64, r0 + 64, r0, TB / KC, 0});
-    }
-    push_gemm(OP_GEMM64_KM, off, BUF_A, BUF_A, BUF_W, 0, -1.0, 0.0, 3);
-  }
-  {
-    struct Job { int r0, h1, h2; };
-    std::vector<std::vector<Job>> levels;
-    // returns level index of the node covering [b0, b0+nb) 128-blocks (0 = leaf 128 block)
-    struct Rec {
-      std::vector<std::vector<Job>>& levels;
-      int go(int b0, int nb) {
-        if (nb == 1) return 0;
-        int n1 = (nb + 1) / 2, n2 = nb - n1;
-        int l1 = go(b0, n1), l2 = go(b0 + n1, n2);
-        int lv = std::max(l1, l2) + 1;
-        if ((int)levels.size() < lv) levels.resize(lv);
-        levels[lv - 1].push_back({b0 * 128, n1 * 128, n2 * 128});
-        return lv;
-      }
-    } rec{levels};
-    rec.go(0, nT);
-    for (auto& jobs : levels) {
-      size_t off = tasks.size();
-      for (auto& j : jobs)
-        for (int I = 0; I < j.h2 / 128; ++I)
-          for (int J = 0; J < j.h1 / 128; ++J) {
-            int kb = J * 128;
-            tasks.push_back({j.r0 + j.h1 + I * 128, j.r0 + J * 128, j.r0 + j.h1 + I * 128, j.r0 + kb, j.r0 + kb,
-                             j.r0 + J * 128, (j.h1 - kb) / KC, 0});
-          }
-      push_gemm(OP_GEMM128_KM, off, BUF_W, BUF_A, BUF_A, 0, 1.0, 0.0, 3);
-      off = tasks.size();
-      for (auto& j : jobs)
-        for (int I = 0; I < j.h2 / 128; ++I)
-          for (int J = 0; J < j.h1 / 128; ++J)
-            tasks.push_back({j.r0 + j.h1 + I * 128, j.r0 + J * 128, j.r0 + j.h1 + I * 128, j.r0 + j.h1, j.r0 + j.h1,
-                             j.r0 + J * 128, (I + 1) * 128 / KC, 0});
-      push_gemm(OP_GEMM128_KM, off, BUF_A, BUF_A, BUF_W, 0, -1.0, 0.0, 3);
-    }
   }
   // ---- z = X r, alpha = X^T z ----
   {
@@ -273,53 +181,28 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
     case OP_KBUILD:
       DP_SWITCH(h->dp, (kbuild_kernel<DP><<<h->n_ktiles, 256, 0, st>>>(h->ktiles, h->X, h->noise, h->kp, h->n, np, h->A)));
       return 1;
-    case OP_POTRF_DF: {
+    case OP_FACTOR_DF: {
       cudaMemsetAsync(h->counter, 0, sizeof(unsigned), st);
-      cudaMemsetAsync(h->ready, 0, (size_t)h->nt * h->nt * sizeof(int), st);
-      PotrfArgs pa;
-      pa.A = h->A; pa.ld = np; pa.nt = h->nt; pa.n = h->n; pa.X = h->X; pa.noise = h->noise; pa.kp = h->kp;
-      pa.tiles = h->ptiles; pa.ntasks = h->n_ptiles; pa.counter = h->counter; pa.ready = h->ready;
-      pa.logdet_part = h->logdet_part; pa.info = h->info; pa.abort_flag = h->abort_flag; pa.trace = h->trace; pa.rdiag = h->rdiag;
-      const int grid = std::min(h->n_sms, h->n_ptiles);
-      DP_SWITCH(h->dp, (potrf_dataflow_kernel<DP><<<grid, 256, PotrfSmem<DP>::BYTES, st>>>(pa)));
+      cudaMemsetAsync(h->ready, 0, (size_t)2 * h->nt * h->nt * sizeof(int), st);  // ready + xready
+      FactorArgs fa;
+      fa.A = h->A; fa.W = h->W; fa.ld = np; fa.nt = h->nt; fa.n = h->n; fa.X = h->X; fa.noise = h->noise; fa.kp = h->kp;
+      fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready;
+      fa.logdet_part = h->logdet_part; fa.rdiag = h->rdiag; fa.info = h->info; fa.abort_flag = h->abort_flag;
+      fa.trace = h->trace;
+      const int grid = std::min(h->n_sms, h->n_ftasks);
+      DP_SWITCH(h->dp, (factor_dataflow_kernel<DP><<<grid, 256, FactorSmem<DP>::BYTES, st>>>(fa)));
       return 1;
     }
-    case OP_DIAG_INV:
-      diag_inverse_kernel<<<h->nt, 256, DIAG_INV_SMEM_BYTES, st>>>(h->A, np, h->dinv);
-      return 1;
-    case OP_PLACE_DINV:
-      place_dinv_kernel<<<h->nt, 256, 0, st>>>(h->A, np, h->dinv);
-      return 1;
-    case OP_GEMM64_KK:
-      tile_gemm_kernel<Cfg64, KCONTIG, KCONTIG><<<op.task_cnt, Cfg64::THREADS, Engine<Cfg64, KCONTIG, KCONTIG>::SMEM_BYTES, st>>>(
-          h->tasks + op.task_off, buf_ptr(h, op.cbuf, 0), buf_ld(h, op.cbuf), buf_ptr(h, op.abuf, 0), buf_ld(h, op.abuf),
-          buf_ptr(h, op.bbuf, op.dinv_tile), buf_ld(h, op.bbuf), op.alpha, op.beta);
-      return 1;
-    case OP_GEMM128_KK:
-      tile_gemm_kernel<Cfg128, KCONTIG, KCONTIG><<<op.task_cnt, Cfg128::THREADS, Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES, st>>>(
-          h->tasks + op.task_off, buf_ptr(h, op.cbuf, 0), buf_ld(h, op.cbuf), buf_ptr(h, op.abuf, 0), buf_ld(h, op.abuf),
-          buf_ptr(h, op.bbuf, op.dinv_tile), buf_ld(h, op.bbuf), op.alpha, op.beta);
-      return 1;
-    case OP_GEMM64_KM:
-      tile_gemm_kernel<Cfg64, KCONTIG, MCONTIG><<<op.task_cnt, Cfg64::THREADS, Engine<Cfg64, KCONTIG, MCONTIG>::SMEM_BYTES, st>>>(
-          h->tasks + op.task_off, buf_ptr(h, op.cbuf, 0), buf_ld(h, op.cbuf), buf_ptr(h, op.abuf, 0), buf_ld(h, op.abuf),
-          buf_ptr(h, op.bbuf, op.dinv_tile), buf_ld(h, op.bbuf), op.alpha, op.beta);
-      return 1;
-    case OP_GEMM128_KM:
-      tile_gemm_kernel<Cfg128, KCONTIG, MCONTIG><<<op.task_cnt, Cfg128::THREADS, Engine<Cfg128, KCONTIG, MCONTIG>::SMEM_BYTES, st>>>(
-          h->tasks + op.task_off, buf_ptr(h, op.cbuf, 0), buf_ld(h, op.cbuf), buf_ptr(h, op.abuf, 0), buf_ld(h, op.abuf),
-          buf_ptr(h, op.bbuf, op.dinv_tile), buf_ld(h, op.bbuf), op.alpha, op.beta);
-      return 1;
     case OP_TRMV:
-      trmv_lower_kernel<<<np / 8, 256, 0, st>>>(h->A, np, np, h->r, h->z);
+      trmv_lower_kernel<<<np / 8, 256, 0, st>>>(h->W, np, np, h->r, h->z);
       return 1;
     case OP_TRMV_T:
-      trmv_t_partial_kernel<<<dim3(h->nT, h->nT), 128, 0, st>>>(h->A, np, np, h->z, h->tpartial);
+      trmv_t_partial_kernel<<<dim3(h->nT, h->nT), 128, 0, st>>>(h->W, np, np, h->z, h->tpartial);
       trmv_t_reduce_kernel<<<h->nT, 128, 0, st>>>(h->tpartial, np, h->alpha);
       return 2;
     case OP_LAUUM:
       DP_SWITCH(h->dp, (lauum_trace_kernel<DP><<<op.task_cnt, 256, LauumSmem<DP>::BYTES, st>>>(
-                           h->tasks + op.task_off, h->A, np, h->X, h->alpha, h->kp, h->n, h->trace_partial, kinv_out)));
+                           h->tasks + op.task_off, h->W, np, h->X, h->alpha, h->kp, h->n, h->trace_partial, kinv_out)));
       return 1;
     case OP_FINALIZE:
       finalize_kernel<<<1, 256, 0, st>>>(h->logdet_part, h->nt, h->z, h->n, h->trace_partial, h->n_lauum, h->dp, h->d,
@@ -336,6 +219,7 @@ int enqueue_eval(eb200_gp* h, cudaStream_t st, int want_grad, int max_stage, dou
   for (const Op& op : h->ops) {
     if (op.stage > max_stage) continue;
     if (op.grad_only && !want_grad) continue;
+    if (op.debug_only && max_stage != 1) continue;
     cnt += launch_op(h, op, st, want_grad, kinv_out);
   }
   CK(cudaGetLastError());
@@ -361,16 +245,12 @@ int set_attrs() {
   CK(cudaGetDevice(&dev));
   bool& done = done_dev[dev & 63];
   if (done) return 0;
-  CK((set_gemm_attr<Cfg64, KCONTIG, KCONTIG>()));
   CK((set_gemm_attr<Cfg128, KCONTIG, KCONTIG>()));
-  CK((set_gemm_attr<Cfg64, KCONTIG, MCONTIG>()));
-  CK((set_gemm_attr<Cfg128, KCONTIG, MCONTIG>()));
   CK(cudaFuncSetAttribute(var_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(diag_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_INV_SMEM_BYTES));
 #define SET_POTRF(DPV)                                                                                       \
-  CK(cudaFuncSetAttribute(potrf_dataflow_kernel<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                          PotrfSmem<DPV>::BYTES));
+  CK(cudaFuncSetAttribute(factor_dataflow_kernel<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                          FactorSmem<DPV>::BYTES));
   SET_POTRF(2) SET_POTRF(3) SET_POTRF(4) SET_POTRF(5) SET_POTRF(6) SET_POTRF(8) SET_POTRF(9) SET_POTRF(10)
   SET_POTRF(12) SET_POTRF(16)
 #undef SET_POTRF
@@ -409,12 +289,12 @@ int ensure_var_tasks(eb200_gp* h, int mt) {
 int predict_chunk(eb200_gp* h, int mc, int want_var, double* mu_dev, double* var_dev, cudaStream_t st) {
   const int np = h->np;
   const int blocks = (mc + 31) / 32;
-  double* ks = want_var ? h->W : nullptr;
+  double* ks = want_var ? h->A : nullptr;  // L is no longer needed once X = L^-1 exists: reuse as K* scratch
   DP_SWITCH(h->dp, (predict_mean_kernel<DP><<<blocks, 256, 0, st>>>(h->T_dev, mc, h->X, h->alpha, h->kp, h->n, np, mu_dev, ks, np)));
   if (want_var) {
     const int mt = (mc + 127) / 128;
     if (ensure_var_tasks(h, mt)) return 1;
-    var_gemm_kernel<<<h->var_tasks_cnt, 256, Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES, st>>>(h->var_tasks, h->W, np, h->A, np,
+    var_gemm_kernel<<<h->var_tasks_cnt, 256, Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES, st>>>(h->var_tasks, h->A, np, h->W, np,
                                                                                                  h->rowss, np);
     var_finish_kernel<<<(mc + 255) / 256, 256, 0, st>>>(h->rowss, np, h->nT, h->kp, mc, var_dev);
   }
@@ -458,7 +338,6 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMalloc(&h->r, np * sizeof(double)));
   CK(cudaMalloc(&h->z, np * sizeof(double)));
   CK(cudaMalloc(&h->alpha, np * sizeof(double)));
-  CK(cudaMalloc(&h->dinv, (size_t)h->nt * TB * TB * sizeof(double)));
   CK(cudaMalloc(&h->logdet_part, h->nt * sizeof(double)));
   CK(cudaMalloc(&h->tpartial, (size_t)h->nT * np * sizeof(double)));
   CK(cudaMalloc(&h->p_dev, (MAXD + 1) * sizeof(double)));
@@ -480,18 +359,28 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMemset(h->W, 0, mat));
   CK(cudaMemset(h->A, 0, mat));  // strictly-upper 64-blocks of diagonal 128-tiles must stay zero
   CK(cudaMalloc(&h->counter, sizeof(unsigned)));
-  CK(cudaMalloc(&h->ready, (size_t)h->nt * h->nt * sizeof(int)));
+  CK(cudaMalloc(&h->ready, (size_t)2 * h->nt * h->nt * sizeof(int)));
+  h->xready = h->ready + (size_t)h->nt * h->nt;
   CK(cudaMalloc(&h->abort_flag, sizeof(int)));
   CK(cudaMalloc(&h->rdiag, (size_t)np * sizeof(double)));
   CK(cudaMemset(h->abort_flag, 0, sizeof(int)));
   CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device));
   {
-    std::vector<int2> pt;
-    for (int j = 0; j < h->nt; ++j)
-      for (int i = j; i < h->nt; ++i) pt.push_back(make_int2(i, j));
-    h->n_ptiles = (int)pt.size();
-    CK(cudaMalloc(&h->ptiles, pt.size() * sizeof(int2)));
-    CK(cudaMemcpy(h->ptiles, pt.data(), pt.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    // Cholesky tiles column by column; the inverse's row r follows the Cholesky column r + 1
+    // (its inputs L_r*, X_rr are then already published, so inverse tasks rarely wait).
+    std::vector<FactorTask> ft;
+    const int nt = h->nt;
+    auto trtri_row = [&](int r) {
+      for (int J = 0; J < r; ++J) ft.push_back({TASK_TRTRI, r, J, 0});
+    };
+    for (int c = 0; c < nt; ++c) {
+      for (int i = c; i < nt; ++i) ft.push_back({TASK_POTRF, i, c, 0});
+      if (c >= 1) trtri_row(c - 1);
+    }
+    trtri_row(nt - 1);
+    h->n_ftasks = (int)ft.size();
+    CK(cudaMalloc(&h->ftasks, ft.size() * sizeof(FactorTask)));
+    CK(cudaMemcpy(h->ftasks, ft.data(), ft.size() * sizeof(FactorTask), cudaMemcpyHostToDevice));
   }
 
   // inputs, padded
@@ -533,9 +422,9 @@ int eb200_gp_destroy(eb200_gp* h) {
   cudaStreamSynchronize(h->stream);
   if (h->g_grad) cudaGraphExecDestroy(h->g_grad);
   if (h->g_lml) cudaGraphExecDestroy(h->g_lml);
-  void* dev[] = {h->A, h->W, h->X, h->noise, h->r, h->z, h->alpha, h->dinv, h->logdet_part, h->tpartial,
+  void* dev[] = {h->A, h->W, h->X, h->noise, h->r, h->z, h->alpha, h->logdet_part, h->tpartial,
                  h->trace_partial, h->p_dev, h->out_dev, h->kp, h->info, h->tasks, h->ktiles, h->T_dev, h->T_in,
-                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ptiles, h->counter, h->ready, h->abort_flag, h->rdiag};
+                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ftasks, h->counter, h->ready, h->abort_flag, h->rdiag};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (h->h_p) cudaFreeHost(h->h_p);
@@ -653,7 +542,7 @@ int eb200_gp_debug_stage(eb200_gp* h, const double* p_host, int stage) {
   CK(cudaSetDevice(h->device));
   memcpy(h->h_p, p_host, (h->d + 1) * sizeof(double));
   CK(cudaMemcpyAsync(h->p_dev, h->h_p, (h->d + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  if (enqueue_eval(h, h->stream, stage >= 4, stage, stage >= 4 ? h->W : nullptr, nullptr)) return 1;
+  if (enqueue_eval(h, h->stream, stage >= 4, stage, stage >= 4 ? h->A : nullptr, nullptr)) return 1;
   CK(cudaStreamSynchronize(h->stream));
   h->factor_valid = false;
   return 0;
@@ -675,18 +564,18 @@ int eb200_gp_debug_alpha(eb200_gp* h, double* alpha_host) {
   return 0;
 }
 
-int eb200_gp_debug_potrf_trace(eb200_gp* h, const double* p_host, unsigned long long* out_host, int* tiles_out) {
-  if (!h || !p_host || !out_host || !tiles_out) return fail("potrf_trace: null argument");
+int eb200_gp_debug_factor_trace(eb200_gp* h, const double* p_host, unsigned long long* out_host, int* tasks_out) {
+  if (!h || !p_host || !out_host || !tasks_out) return fail("factor_trace: null argument");
   CK(cudaSetDevice(h->device));
-  CK(cudaMalloc(&h->trace, (size_t)h->n_ptiles * 6 * sizeof(unsigned long long)));
-  CK(cudaMemset(h->trace, 0, (size_t)h->n_ptiles * 6 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->trace, (size_t)h->n_ftasks * 6 * sizeof(unsigned long long)));
+  CK(cudaMemset(h->trace, 0, (size_t)h->n_ftasks * 6 * sizeof(unsigned long long)));
   memcpy(h->h_p, p_host, (h->d + 1) * sizeof(double));
   CK(cudaMemcpyAsync(h->p_dev, h->h_p, (h->d + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   int rc = enqueue_eval(h, h->stream, 0, 2, nullptr, nullptr);
   cudaError_t e = cudaStreamSynchronize(h->stream);
   if (!rc && e == cudaSuccess) {
-    e = cudaMemcpy(out_host, h->trace, (size_t)h->n_ptiles * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    cudaMemcpy(tiles_out, h->ptiles, (size_t)h->n_ptiles * sizeof(int2), cudaMemcpyDeviceToHost);
+    e = cudaMemcpy(out_host, h->trace, (size_t)h->n_ftasks * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(tasks_out, h->ftasks, (size_t)h->n_ftasks * sizeof(FactorTask), cudaMemcpyDeviceToHost);
   }
   cudaFree(h->trace);
   h->trace = nullptr;
@@ -695,6 +584,7 @@ int eb200_gp_debug_potrf_trace(eb200_gp* h, const double* p_host, unsigned long 
   CK(e);
   return 0;
 }
+int eb200_gp_factor_tasks(const eb200_gp* h) { return h ? h->n_ftasks : -1; }
 
 int eb200_gp_profile_stages(eb200_gp* h, const double* p_host, int reps, float* ms_out) {
   if (!h || !p_host || !ms_out || reps < 1) return fail("profile_stages: bad argument");
@@ -709,7 +599,7 @@ int eb200_gp_profile_stages(eb200_gp* h, const double* p_host, int reps, float* 
     CK(cudaEventRecord(ev[0], h->stream));
     for (int stage = 1; stage <= 5; ++stage) {
       for (const Op& op : h->ops)
-        if (op.stage == stage) launch_op(h, op, h->stream, 1, nullptr);
+        if (op.stage == stage && !op.debug_only) launch_op(h, op, h->stream, 1, nullptr);
       CK(cudaEventRecord(ev[stage], h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));

@@ -1,0 +1,529 @@
+// Persistent dataflow factorisation (sm_100a, fp64): Cholesky K = L L^T and the triangular
+// inverse X = L^-1 in ONE launch.
+//
+// The lower triangle is cut into 64x64 tiles.  A static task list (built on the host) is
+// handed out through an atomic counter, so every claimed task is owned by a CTA that is
+// already running and depends only on lower-numbered tasks: no co-residency assumption, no
+// deadlock.  Two task kinds share the list:
+//
+//   POTRF (i, j), column-major:  C = K_ij - sum_{k<j} L_ik L_jk^T   (K_ij generated in-kernel:
+//        the kernel-matrix build is fused into the factorisation), then
+//          i == j : L_jj = chol(C) (8-column panels, warp-synchronous), published; afterwards,
+//                   off the critical path, X_jj = L_jj^-1 is written to the inverse's diagonal
+//          i  > j : L_ij = C L_jj^-T (panelled forward substitution against L_jj)
+//   TRTRI (r, J), J < r, listed one block column behind the Cholesky front:
+//          X_rJ = -X_rr * sum_{K=J}^{r-1} L_rK X_KJ                  (X goes to a second matrix)
+//
+// The Cholesky has a 64-step dependency chain (diagonal tile -> tile below -> next diagonal
+// tile) that leaves most SMs idle; the inverse's tile products fill them.  Producers publish a
+// per-tile flag (CTA barrier, one cumulative device-scope fence, release store); consumers poll
+// with relaxed loads and read tile data only through L2 (cp.async.cg / ld.global.cg), so no L1
+// invalidation is ever needed.  A watchdog in the poll loop turns a lost dependency into an
+// error code instead of a hang.
+#pragma once
+#include "kernels.cuh"
+
+namespace eb {
+
+using CfgP = TileCfg<64, 64, 32, 16>;  // 256 threads: 2 x 4 warps, 16 accumulator doubles / thread
+constexpr int PSTAGES = 6;             // cp.async ring depth (5 x 16 KB in flight per CTA)
+constexpr int PSTAGE_DOUBLES = 2 * 64 * (KC + 4);
+constexpr int PS = 65;                 // stride of the 64x64 finalisation buffers
+constexpr int TS = 68;                 // stride of a parked accumulator used as a [k][n] operand
+
+enum FactorTaskType : int { TASK_POTRF = 0, TASK_TRTRI = 1 };
+struct FactorTask {
+  int type, i, j, pad;
+};
+
+struct FactorArgs {
+  double* A;   // K -> L (lower triangle)
+  double* W;   // X = L^-1 (lower triangle)
+  int ld, nt, n;
+  const double* X;        // [np][DP] padded training inputs
+  const double* noise;    // [np]
+  const KernelParams* kp;
+  const FactorTask* tasks;
+  int ntasks;
+  unsigned* counter;      // task counter (zeroed before the launch)
+  int* ready;             // [nt*nt] L tile flags (zeroed before the launch)
+  int* xready;            // [nt*nt] X tile flags (zeroed before the launch)
+  double* logdet_part;    // [nt]
+  double* rdiag;          // [nt][64] reciprocal pivots 1 / L_jj, published with the diagonal tile
+  int* info;
+  int* abort_flag;        // watchdog: set when a wait exceeded its budget
+  unsigned long long* trace;  // optional [ntasks][6] globaltimer stamps (diagnostics), or nullptr
+};
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define EB_STAMP(slot)                                                                \
+  do {                                                                                \
+    if (a.trace != nullptr && tid == 0) a.trace[(size_t)task * 6 + (slot)] = gtime(); \
+  } while (0)
+
+// Flags are polled with a relaxed gpu-scope load: an acquire load would make ptxas emit
+// CCTL.IVALL (L1 invalidate + drain of every outstanding load, including the cp.async ring) on
+// every poll.
+__device__ __forceinline__ int ld_flag(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Lane 0 of every warp polls; returns false if the watchdog fired.
+__device__ __forceinline__ bool wait_ready(const int* flag, int* abort_flag) {
+  bool ok = true;
+  if ((threadIdx.x & 31) == 0) {
+    long long spins = 0;
+    while (ld_flag(flag) == 0) {
+      __nanosleep(20);
+      if ((++spins & 0x3ff) == 0) {
+        if (spins > (1ll << 24) || ld_flag(abort_flag) != 0) {  // ~1 s
+          atomicExch(abort_flag, 1);
+          ok = false;
+          break;
+        }
+      }
+    }
+  }
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  return ok;
+}
+
+// Publish a tile: all of the CTA's stores happen-before the barrier, thread 0's cumulative
+// device-scope fence orders them before the flag.
+__device__ __forceinline__ int publish(int* flag, bool ok) {
+  const int all_ok = __syncthreads_and(ok ? 1 : 0);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    st_release(flag, 1);
+  }
+  return all_ok;
+}
+
+// acc += A(64 x nk*KC) * B(64 x nk*KC)^T, streaming the operands tile column by tile column as
+// their flags appear.  A is KCONTIG; B is KCONTIG (Cholesky) or MCONTIG (inverse).  Chunk kt
+// belongs to tile column kt / 4, guarded by fa[(kt/4) * sa] and (if fb) fb[(kt/4) * sb].
+template <int LB>
+__device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP::NI][2], const double* Ag, int lda,
+                                                   const double* Bg, int ldb, int nk, const int* fa, int sa,
+                                                   const int* fb, int sb, int* abort_flag, double* pipe, bool& ok) {
+  using E = Engine<CfgP, KCONTIG, LB>;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp / CfgP::WARPS_N) * CfgP::WM;
+  const int wn0 = (warp % CfgP::WARPS_N) * CfgP::WN;
+  const int g = lane >> 2, t = lane & 3;
+  const int ncol = nk >> 2;
+  // leading tile columns already published (one coalesced look per warp)
+  int known = 0;
+  for (int base = 0; base < ncol; base += 32) {
+    const int kc = base + lane;
+    int f = 1;
+    if (kc < ncol) f = (ld_flag(fa + (size_t)kc * sa) != 0) && (fb == nullptr || ld_flag(fb + (size_t)kc * sb) != 0);
+    const unsigned missing = __ballot_sync(0xffffffffu, f == 0);
+    if (missing) {
+      known = base + __ffs(missing) - 1;
+      break;
+    }
+    known = min(base + 32, ncol);
+  }
+  auto issue = [&](int kt) {
+    if ((kt & 3) == 0) {
+      const int kc = kt >> 2;
+      if (kc >= known) {
+        ok = wait_ready(fa + (size_t)kc * sa, abort_flag) && ok;
+        if (fb != nullptr) ok = wait_ready(fb + (size_t)kc * sb, abort_flag) && ok;
+      }
+    }
+    double* stage = pipe + (kt % PSTAGES) * PSTAGE_DOUBLES;
+    const double* ap = Ag + (size_t)kt * KC;
+    const double* bp = (LB == KCONTIG) ? Bg + (size_t)kt * KC : Bg + (size_t)kt * KC * ldb;
+    E::template load_operand<64, KCONTIG>(stage, ap, lda, tid);
+    E::template load_operand<64, LB>(stage + E::SA::DOUBLES, bp, ldb, tid);
+  };
+#pragma unroll
+  for (int s = 0; s < PSTAGES - 1; ++s) {
+    if (s < nk) issue(s);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<PSTAGES - 2>();
+    __syncthreads();
+    const double* sA = pipe + (kt % PSTAGES) * PSTAGE_DOUBLES;
+    const double* sB = sA + E::SA::DOUBLES;
+#pragma unroll
+    for (int kk = 0; kk < KC; kk += 4) {
+      double af[CfgP::MI], bf[CfgP::NI];
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi) af[mi] = sA[(wm0 + mi * 8 + g) * E::SA::STRIDE + kk + t];
+#pragma unroll
+      for (int ni = 0; ni < CfgP::NI; ++ni) {
+        const int col = wn0 + ni * 8 + g;
+        bf[ni] = (LB == KCONTIG) ? sB[col * E::SB::STRIDE + kk + t] : sB[(kk + t) * E::SB::STRIDE + col];
+      }
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+    }
+    // refill the stage consumed in the previous iteration (every warp is past the barrier above,
+    // so nobody still reads it); a flag wait here never delays math on stages already loaded
+    {
+      const int nxt = kt + PSTAGES - 1;
+      if (nxt < nk) issue(nxt);
+      cp_async_commit();
+    }
+  }
+  cp_async_wait<0>();
+}
+
+// Finalisation layout: warp w owns columns 8w..8w+7 of a 64x64 tile, lane owns rows lane, lane+32.
+//
+// Right-looking Cholesky of the tile held in v (lower triangle) by 8-column panels; the owning
+// warp factorises its panel with shuffles only, the warps to its right apply it.  L goes to sL
+// (zero strict upper), reciprocal pivots to rd.
+__device__ __forceinline__ void tile_cholesky(double (&v)[2][8], double* sL, double* rd, int* info, int col0) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int p = 0; p < 8; ++p) {
+    if (warp == p) {
+      const int sj = p >> 2;       // row slot of this panel's pivot rows
+      const int ob = 8 * (p & 3);  // lane of the first pivot row
+      double dloc = sj ? v[1][0] : v[0][0];
+      double d = __shfl_sync(0xffffffffu, dloc, ob);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, col0 + 8 * p + c + 1);
+        const double rinv = rsqrt(d);
+        if (lane == ob + c) rd[8 * p + c] = rinv;
+        const double l0 = v[0][c] * rinv, l1 = v[1][c] * rinv;
+        v[0][c] = l0;
+        v[1][c] = l1;
+        const double lsel = sj ? l1 : l0;
+        if (c < 7) {
+          // next pivot, computed by its own lane (keeps the second shuffle off the chain)
+          const double nloc = fma(-lsel, lsel, sj ? v[1][c + 1] : v[0][c + 1]);
+          d = __shfl_sync(0xffffffffu, nloc, ob + c + 1);
+        }
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; ++c2) {
+          const double lk = __shfl_sync(0xffffffffu, lsel, ob + c2);
+          v[0][c2] = fma(-l0, lk, v[0][c2]);
+          v[1][c2] = fma(-l1, lk, v[1][c2]);
+        }
+      }
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int row = lane + 32 * sl, col = 8 * p + c;
+          sL[row * PS + col] = (row >= col) ? v[sl][c] : 0.0;
+        }
+    }
+    __syncthreads();
+    if (warp > p) {
+      double ar[2][8];
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ar[sl][k] = sL[(lane + 32 * sl) * PS + 8 * p + k];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const double b = sL[(8 * warp + c) * PS + 8 * p + k];
+          v[0][c] = fma(-ar[0][k], b, v[0][c]);
+          v[1][c] = fma(-ar[1][k], b, v[1][c]);
+        }
+    }
+  }
+}
+
+// Y = V L^-T for the tile held in v (rows independent), L in sL, reciprocal pivots in rd;
+// forward substitution by 8-column panels.  Result left in sOut ([64][PS]).
+__device__ __forceinline__ void tile_trsm(double (&v)[2][8], const double* sL, const double* rd, double* sOut) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int p = 0; p < 8; ++p) {
+    if (warp == p) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const double r = rd[8 * p + c];
+        const double x0 = v[0][c] * r, x1 = v[1][c] * r;
+        v[0][c] = x0;
+        v[1][c] = x1;
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; ++c2) {
+          const double lv = sL[(8 * p + c2) * PS + 8 * p + c];
+          v[0][c2] = fma(-x0, lv, v[0][c2]);
+          v[1][c2] = fma(-x1, lv, v[1][c2]);
+        }
+      }
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) sOut[(lane + 32 * sl) * PS + 8 * p + c] = v[sl][c];
+    }
+    __syncthreads();
+    if (warp > p) {
+      double ar[2][8];
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ar[sl][k] = sOut[(lane + 32 * sl) * PS + 8 * p + k];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const double b = sL[(8 * warp + c) * PS + 8 * p + k];
+          v[0][c] = fma(-ar[0][k], b, v[0][c]);
+          v[1][c] = fma(-ar[1][k], b, v[1][c]);
+        }
+    }
+  }
+}
+
+template <int DP>
+struct FactorSmem {
+  static constexpr int PIPE = PSTAGES * PSTAGE_DOUBLES;
+  static constexpr int C_OFF = PIPE;               // [64][65]  (also the parked [64][68] accumulator, with L_OFF)
+  static constexpr int L_OFF = C_OFF + 64 * PS;    // [64][65]
+  static constexpr int XI_OFF = L_OFF + 64 * PS;   // [DP][64]
+  static constexpr int XJ_OFF = XI_OFF + DP * 64;  // [DP][64]
+  static constexpr int COL_OFF = XJ_OFF + DP * 64; // [128]
+  static constexpr int RD_OFF = COL_OFF + 128;     // [64]
+  static constexpr int DOUBLES = RD_OFF + 64 + 16;
+  static constexpr int BYTES = DOUBLES * (int)sizeof(double);
+  static_assert(64 * TS <= 2 * 64 * PS, "parked accumulator must fit the finalisation buffers");
+};
+
+template <int DP>
+__global__ void __launch_bounds__(256, 1) factor_dataflow_kernel(const FactorArgs a) {
+  extern __shared__ __align__(16) double gsm[];
+  using SM = FactorSmem<DP>;
+  __shared__ unsigned s_task;
+  double* sC = gsm + SM::C_OFF;
+  double* sL = gsm + SM::L_OFF;
+  double* sT = gsm + SM::C_OFF;  // aliases sC/sL (inverse tasks only)
+  double* sXi = gsm + SM::XI_OFF;
+  double* sXj = gsm + SM::XJ_OFF;
+  double* colbuf = gsm + SM::COL_OFF;
+  double* rdiag = gsm + SM::RD_OFF;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp / CfgP::WARPS_N) * CfgP::WM;
+  const int wn0 = (warp % CfgP::WARPS_N) * CfgP::WN;
+  const int g = lane >> 2, t = lane & 3;
+  const int ld = a.ld, nt = a.nt;
+
+  for (;;) {
+    __syncthreads();  // previous task fully retired (smem reuse, s_task reuse)
+    if (tid == 0) s_task = atomicAdd(a.counter, 1u);
+    __syncthreads();
+    const unsigned task = s_task;
+    if (task >= (unsigned)a.ntasks) break;
+    const FactorTask tk = a.tasks[task];
+    const int ti = tk.i, tj = tk.j;
+    const int i0 = ti * 64, j0 = tj * 64;
+    bool ok = true;
+    EB_STAMP(0);
+    double acc[CfgP::MI][CfgP::NI][2];
+
+    if (tk.type == TASK_TRTRI) {
+      // =====================  X_rJ = -X_rr * sum_{K=J}^{r-1} L_rK X_KJ  =====================
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < CfgP::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      accumulate_flagged<MCONTIG>(acc, a.A + (size_t)i0 * ld + j0, ld, a.W + (size_t)j0 * ld + j0, ld, (ti - tj) * 4,
+                                  a.ready + (size_t)ti * nt + tj, 1, a.xready + (size_t)tj * nt + tj, nt, a.abort_flag,
+                                  gsm, ok);
+      EB_STAMP(1);
+      __syncthreads();  // pipeline drained by every warp before it is refilled / sT written
+      // park the sum as a [k][n] operand
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < CfgP::NI; ++ni) {
+          double* pc = sT + (wm0 + mi * 8 + g) * TS + wn0 + ni * 8 + 2 * t;
+          pc[0] = acc[mi][ni][0];
+          pc[1] = acc[mi][ni][1];
+        }
+      ok = wait_ready(a.xready + (size_t)ti * nt + ti, a.abort_flag) && ok;
+      EB_STAMP(2);
+      using EK = Engine<CfgP, KCONTIG, KCONTIG>;
+      const double* Dg = a.W + (size_t)i0 * ld + i0;  // X_rr
+#pragma unroll
+      for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(gsm + c * PSTAGE_DOUBLES, Dg + c * KC, ld, tid);
+      cp_async_commit();
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < CfgP::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      cp_async_wait<0>();
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double* sA = gsm + c * PSTAGE_DOUBLES;
+#pragma unroll
+        for (int kk = 0; kk < KC; kk += 4) {
+          double af[CfgP::MI], bf[CfgP::NI];
+#pragma unroll
+          for (int mi = 0; mi < CfgP::MI; ++mi) af[mi] = sA[(wm0 + mi * 8 + g) * (KC + 4) + kk + t];
+#pragma unroll
+          for (int ni = 0; ni < CfgP::NI; ++ni) bf[ni] = sT[(c * KC + kk + t) * TS + wn0 + ni * 8 + g];
+#pragma unroll
+          for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        }
+      }
+      double* Wt = a.W + (size_t)i0 * ld + j0;
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < CfgP::NI; ++ni) {
+          double2 val;
+          val.x = -acc[mi][ni][0];
+          val.y = -acc[mi][ni][1];
+          *reinterpret_cast<double2*>(Wt + (size_t)(wm0 + mi * 8 + g) * ld + wn0 + ni * 8 + 2 * t) = val;
+        }
+      EB_STAMP(4);
+      const int all_ok = publish(a.xready + (size_t)ti * nt + tj, ok);
+      EB_STAMP(5);
+      if (!all_ok) break;
+      continue;
+    }
+
+    // ==================================  Cholesky tile (i, j)  ==================================
+    // stage the training inputs of the tile's rows / columns for the K_ij generation
+    for (int e = tid; e < 64 * DP; e += 256) {
+      int r = e / DP, m = e % DP;
+      sXi[m * 64 + r] = a.X[(size_t)(i0 + r) * DP + m];
+      sXj[m * 64 + r] = a.X[(size_t)(j0 + r) * DP + m];
+    }
+    __syncthreads();
+    // acc = -K_ij, generated straight into the accumulator layout (before any panel wait, so the
+    // exp() work overlaps the wait for the producers)
+    {
+      const double amp = a.kp->amp;
+      double r2[CfgP::MI][CfgP::NI * 2];
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+        for (int c = 0; c < CfgP::NI * 2; ++c) r2[mi][c] = 0.0;
+#pragma unroll
+      for (int m = 0; m < DP; ++m) {
+        const double im = a.kp->inv_m[m];
+        double xi[CfgP::MI], xj[CfgP::NI * 2];
+#pragma unroll
+        for (int mi = 0; mi < CfgP::MI; ++mi) xi[mi] = sXi[m * 64 + wm0 + mi * 8 + g];
+#pragma unroll
+        for (int c = 0; c < CfgP::NI * 2; ++c) xj[c] = sXj[m * 64 + wn0 + (c >> 1) * 8 + 2 * t + (c & 1)];
+#pragma unroll
+        for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+          for (int c = 0; c < CfgP::NI * 2; ++c) {
+            const double dx = xi[mi] - xj[c];
+            r2[mi][c] = fma(dx * dx, im, r2[mi][c]);
+          }
+      }
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi) {
+        const int gi = i0 + wm0 + mi * 8 + g;
+#pragma unroll
+        for (int c = 0; c < CfgP::NI * 2; ++c) {
+          const int gj = j0 + wn0 + (c >> 1) * 8 + 2 * t + (c & 1);
+          double kv;
+          if (gi < a.n && gj < a.n) {
+            kv = amp * exp(-0.5 * r2[mi][c]);
+            if (gi == gj) kv += a.noise[gi];
+          } else {
+            kv = (gi == gj) ? 1.0 : 0.0;
+          }
+          acc[mi][c >> 1][c & 1] = -kv;
+        }
+      }
+    }
+    EB_STAMP(1);
+    // left-looking accumulation over the finished panels: acc += sum_k L_ik L_jk^T
+    accumulate_flagged<KCONTIG>(acc, a.A + (size_t)i0 * ld, ld, a.A + (size_t)j0 * ld, ld, tj * 4,
+                                a.ready + (size_t)ti * nt, 1, (ti != tj) ? a.ready + (size_t)tj * nt : nullptr, 1,
+                                a.abort_flag, gsm, ok);
+    // C = -acc parked in shared memory
+#pragma unroll
+    for (int mi = 0; mi < CfgP::MI; ++mi) {
+      const int lr = wm0 + mi * 8 + g;
+#pragma unroll
+      for (int c = 0; c < CfgP::NI * 2; ++c) sC[lr * PS + wn0 + (c >> 1) * 8 + 2 * t + (c & 1)] = -acc[mi][c >> 1][c & 1];
+    }
+    __syncthreads();
+    EB_STAMP(2);
+    double* At = a.A + (size_t)i0 * ld + j0;
+    double v[2][8];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[sl][c] = sC[(lane + 32 * sl) * PS + 8 * warp + c];
+
+    if (ti == tj) {
+      tile_cholesky(v, sL, rdiag, a.info, j0);
+      for (int e = tid; e < 64 * 64; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        At[(size_t)r * ld + c] = sL[r * PS + c];
+      }
+      if (tid < 64) a.rdiag[(size_t)tj * 64 + tid] = rdiag[tid];
+      EB_STAMP(4);
+      int all_ok = publish(a.ready + (size_t)ti * nt + tj, ok);
+      EB_STAMP(5);
+      // ---- off the critical path: log-determinant share and X_jj = L_jj^-1 ----
+      if (tid < 64) colbuf[tid] = log(rdiag[tid]);
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[sl][c] = (lane + 32 * sl == 8 * warp + c) ? 1.0 : 0.0;
+      __syncthreads();
+      if (tid == 0) {
+        double sum = 0.0;
+        for (int j = 0; j < 64; ++j) sum += colbuf[j];
+        a.logdet_part[tj] = -sum;  // sum_j log L_jj = -sum_j log(1 / L_jj)
+      }
+      tile_trsm(v, sL, rdiag, sC);  // sC = I L^-T = (L^-1)^T
+      double* Wt = a.W + (size_t)i0 * ld + j0;
+      for (int e = tid; e < 64 * 64; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        Wt[(size_t)r * ld + c] = (c <= r) ? sC[c * PS + r] : 0.0;
+      }
+      all_ok &= publish(a.xready + (size_t)ti * nt + tj, ok);
+      if (!all_ok) break;
+    } else {
+      ok = wait_ready(a.ready + (size_t)tj * nt + tj, a.abort_flag) && ok;
+      EB_STAMP(3);
+      const double* Lg = a.A + (size_t)j0 * ld + j0;
+      for (int e = tid; e < 64 * 32; e += 256) {
+        const int r = e >> 5, c = (e & 31) * 2;
+        const double2 val = __ldcg(reinterpret_cast<const double2*>(Lg + (size_t)r * ld + c));
+        sL[r * PS + c] = val.x;
+        sL[r * PS + c + 1] = val.y;
+      }
+      if (tid < 64) rdiag[tid] = __ldcg(a.rdiag + (size_t)tj * 64 + tid);
+      __syncthreads();
+      tile_trsm(v, sL, rdiag, sC);
+      for (int e = tid; e < 64 * 64; e += 256) {
+        const int rr = e >> 6, c = e & 63;
+        At[(size_t)rr * ld + c] = sC[rr * PS + c];
+      }
+      EB_STAMP(4);
+      const int all_ok = publish(a.ready + (size_t)ti * nt + tj, ok);
+      EB_STAMP(5);
+      if (!all_ok) break;
+    }
+  }
+}
+
+}  // namespace eb

@@ -117,7 +117,7 @@ class DeviceProblem:
         return self._lib.eb200_gp_eval_launches(self._h, int(bool(want_grad)))
 
     def profile_stages(self, p: np.ndarray, reps: int = 3) -> np.ndarray:
-        """Device milliseconds per stage [kbuild, cholesky, inverse+alpha, kinv+traces, finalize]."""
+        """Device milliseconds per stage [params, factorisation (K + Cholesky + inverse), alpha, kinv+traces, finalize]."""
         p = np.ascontiguousarray(p, dtype=np.float64)
         out = (ctypes.c_float * 5)()
         _lib.check(self._lib.eb200_gp_profile_stages(self._h, _lib.as_double_ptr(p), reps, out), "profile_stages")

@@ -70,9 +70,10 @@ int eb200_gp_predict_device(eb200_gp* gp, int m, const double* t_dev, int want_v
 int eb200_gp_synchronize(eb200_gp* gp);
 
 /* Test / diagnostics hooks (not used by the product path).
- * stage: 1 = K built, 2 = + Cholesky (L in the lower triangle), 3 = + triangular inverse
- * (X = L^-1), 4 = + K^-1 lower triangle stored in the scratch matrix.
- * eb200_gp_debug_matrix copies matrix `which` (0 = main, 1 = scratch), np*np doubles. */
+ * stage: 1 = K built into matrix 0 (diagnostic kernel; the product path generates K inside the
+ * factorisation), 2 = Cholesky + triangular inverse (L in the lower triangle of matrix 0,
+ * X = L^-1 in matrix 1), 3 = + alpha, 4 = + K^-1 lower triangle stored into matrix 0.
+ * eb200_gp_debug_matrix copies matrix `which` (0 or 1), np*np doubles. */
 int eb200_gp_debug_stage(eb200_gp* gp, const double* p_host, int stage);
 int eb200_gp_padded_n(const eb200_gp* gp);
 int eb200_gp_debug_matrix(eb200_gp* gp, int which, double* out_host);
@@ -80,15 +81,17 @@ int eb200_gp_debug_alpha(eb200_gp* gp, double* alpha_host);
 /* number of kernel launches issued by one eval (graph nodes) */
 int eb200_gp_eval_launches(const eb200_gp* gp, int want_grad);
 
-/* Per-task globaltimer stamps (ns) of the dataflow Cholesky: out[task][6] = {claimed, panels
- * accumulated, C formed, diagonal factor visible (off-diagonal tiles), tile stored, published};
- * tiles_out[task][2] = (tile row, tile column).  ntasks = nt (nt + 1) / 2, nt = padded_n / 64. */
-int eb200_gp_debug_potrf_trace(eb200_gp* gp, const double* p_host, unsigned long long* out_host, int* tiles_out);
+/* Per-task globaltimer stamps (ns) of the dataflow factorisation kernel: out[task][6] =
+ * {claimed, K generated / panels accumulated, C formed / diagonal inverse visible, diagonal
+ * factor visible, tile stored, published}; tasks_out[task][4] = (type 0 Cholesky / 1 inverse,
+ * tile row, tile column, 0).  The number of tasks is eb200_gp_factor_tasks(). */
+int eb200_gp_debug_factor_trace(eb200_gp* gp, const double* p_host, unsigned long long* out_host, int* tasks_out);
+int eb200_gp_factor_tasks(const eb200_gp* gp);
 
 /* Per-stage device time of one LML+grad evaluation (milliseconds, averaged over `reps` after
  * one warm-up), launched kernel by kernel outside the CUDA graph with events in between:
- * ms_out[0] = parameter prep + kernel-matrix build, [1] = Cholesky, [2] = triangular inverse +
- * alpha, [3] = K^-1 tiles + gradient traces, [4] = final reduction. */
+ * ms_out[0] = parameter prep, [1] = dataflow factorisation (kernel-matrix build + Cholesky +
+ * triangular inverse), [2] = alpha, [3] = K^-1 tiles + gradient traces, [4] = final reduction. */
 int eb200_gp_profile_stages(eb200_gp* gp, const double* p_host, int reps, float* ms_out);
 
 /* Engine micro-benchmark: C[m][n] = A[m][k] * B[n][k]^T through the tile engine, device

@@ -112,14 +112,14 @@ def test_intermediate_matrices_match_numpy():
     a = gp.debug_matrix(0)
     assert relmax(np.tril(a[:n, :n]), lo) <= 1e-10
     xi = solve_triangular(lo, np.eye(n), lower=True)
+    w = gp.debug_matrix(1)  # the same launch also produced X = L^-1 in the second matrix
+    assert relmax(np.tril(w[:n, :n]), xi) <= 1e-8
+    assert np.all(w[np.triu_indices(npad, 1)] == 0.0)  # strict upper triangle of L^-1 is exactly zero
     gp.debug_stage(p, 3)
-    a = gp.debug_matrix(0)
-    assert relmax(np.tril(a[:n, :n]), xi) <= 1e-8
-    assert np.all(a[np.triu_indices(npad, 1)] == 0.0)  # strict upper triangle of L^-1 is exactly zero
     assert relmax(gp.debug_alpha(), np.linalg.solve(k, y)) <= 1e-7
     gp.debug_stage(p, 4)
-    w = gp.debug_matrix(1)
-    assert relmax(np.tril(w[:n, :n]), np.tril(xi.T @ xi)) <= 1e-8
+    a = gp.debug_matrix(0)
+    assert relmax(np.tril(a[:n, :n]), np.tril(xi.T @ xi)) <= 1e-8
     gp.close()
 
 

@@ -1,0 +1,41 @@
+"""Timeline analysis of the dataflow factorisation kernel from in-kernel globaltimer stamps (development tool)."""
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from emulator_b200 import _lib
+from emulator_b200.device import DeviceProblem
+from oracle import gp_oracle as orc
+n, d = int(sys.argv[1]), int(sys.argv[2])
+rng = np.random.default_rng(0)
+x = rng.random((n, d)).astype(np.float32).astype(np.float64)
+y = np.sin(x.sum(1) * 2.0)
+gp = DeviceProblem(x, orc.noise_diagonal(np.full(n, 0.03, dtype=np.float32))); gp.set_residual(y)
+p = orc.default_parameter_vector(d)
+gp.evaluate(p, True)
+nt = gp.padded_n // 64
+ntasks = gp._lib.eb200_gp_factor_tasks(gp.handle)
+out = np.zeros((ntasks, 6), dtype=np.uint64); tasks = np.zeros((ntasks, 4), dtype=np.int32)
+for rep in range(2):
+    _lib.check(gp._lib.eb200_gp_debug_factor_trace(gp.handle, _lib.as_double_ptr(p), out.ctypes.data_as(ctypes.POINTER(ctypes.c_ulonglong)),
+                                                    tasks.ctypes.data_as(ctypes.POINTER(ctypes.c_int))), "trace")
+t = (out.astype(np.int64) - int(out[:, 0].min())) / 1e3  # us
+print("ntasks", ntasks, "total us", t[:, 5].max())
+po = tasks[:, 0] == 0
+diag = {int(r[2]): k for k, r in enumerate(tasks) if r[0] == 0 and r[1] == r[2]}
+sub = {int(r[2]): k for k, r in enumerate(tasks) if r[0] == 0 and r[1] == r[2] + 1}
+print("j  diag: claimed kgen_done C_done stored published | sub(j+1,j): kgen_done Ljj_seen stored published")
+for j in list(range(0, min(nt, 4))) + list(range(nt // 2, nt // 2 + 3)) + list(range(max(nt - 3, 0), nt)):
+    kd = diag[j]; row = f"{j:3d} " + " ".join(f"{v:9.2f}" for v in t[kd, [0, 1, 2, 4, 5]])
+    if j in sub:
+        ks = sub[j]; row += " | " + " ".join(f"{v:9.2f}" for v in t[ks, [1, 3, 4, 5]])
+    print(row)
+pub = np.array([t[diag[j], 5] for j in range(nt)])
+print("cholesky finished at us", pub.max(), " mean diag-to-diag step us:", np.diff(pub).mean())
+dd = np.array([t[diag[j], 4] - t[diag[j], 2] for j in range(nt)]); print("diag factor+store us: mean", dd.mean())
+off = po & (tasks[:, 1] != tasks[:, 2])
+print("trsm(load Ljj+subst+store) us mean", (t[off, 4] - t[off, 3]).mean())
+tr = ~po
+if tr.any():
+    print("trtri tasks:", tr.sum(), " accumulate us mean", (t[tr, 1] - t[tr, 0]).mean(), " wait Xrr us mean", (t[tr, 2] - t[tr, 1]).mean(),
+          " finalize us mean", (t[tr, 4] - t[tr, 2]).mean(), " first start", t[tr, 0].min(), " last end", t[tr, 5].max())
+busy = (t[:, 5] - t[:, 0]).sum(); print("sum task time us", busy, "-> per-SM avg", busy / 148)

@@ -38,14 +38,14 @@ def check(n, d, seed=0, stages=True):
         out["L_err"] = rel(np.tril(A[:n, :n]), L)
         out["L_pad_ok"] = bool(np.allclose(np.tril(A[n:, :]), np.eye(npad)[n:, :]))
         Xi = solve_triangular(L, np.eye(n), lower=True)
+        Wm = gp.debug_matrix(1)
+        out["X_err"] = rel(np.tril(Wm[:n, :n]), Xi)
+        out["X_upper_zero"] = bool(np.all(Wm[np.triu_indices(npad, 1)] == 0))
         gp.debug_stage(p, 3)
-        A = gp.debug_matrix(0)
-        out["X_err"] = rel(np.tril(A[:n, :n]), Xi)
-        out["X_upper_zero"] = bool(np.all(np.triu(A, 1)[::, :] [np.triu_indices(npad, 1)] == 0) if npad <= 512 else True)
         al = gp.debug_alpha()
         out["alpha_err"] = rel(al, np.linalg.solve(K, y))
         gp.debug_stage(p, 4)
-        Wm = gp.debug_matrix(1)
+        Wm = gp.debug_matrix(0)
         Kinv = Xi.T @ Xi
         out["Kinv_err"] = rel(np.tril(Wm[:n, :n]), np.tril(Kinv))
     lml, grad, info, logdet, quad = gp.evaluate(p, True)
