@@ -148,35 +148,40 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
     E::template load_operand<64, KCONTIG>(stage, ap, lda, tid);
     E::template load_operand<64, LB>(stage + E::SA::DOUBLES, bp, ldb, tid);
   };
+  // Two chunks per barrier: nk is a multiple of 4, so pairs never straddle the end.  Ring slots
+  // refilled after the math of pair (kt, kt+1) are the ones consumed by the previous pair, which
+  // every warp has left behind at this iteration's barrier.
 #pragma unroll
-  for (int s = 0; s < PSTAGES - 1; ++s) {
+  for (int s = 0; s < PSTAGES - 2; ++s) {
     if (s < nk) issue(s);
     cp_async_commit();
   }
-  for (int kt = 0; kt < nk; ++kt) {
-    cp_async_wait<PSTAGES - 2>();
+  for (int kt = 0; kt < nk; kt += 2) {
+    cp_async_wait<PSTAGES - 4>();
     __syncthreads();
-    const double* sA = pipe + (kt % PSTAGES) * PSTAGE_DOUBLES;
-    const double* sB = sA + E::SA::DOUBLES;
 #pragma unroll
-    for (int kk = 0; kk < KC; kk += 4) {
-      double af[CfgP::MI], bf[CfgP::NI];
+    for (int h = 0; h < 2; ++h) {
+      const double* sA = pipe + ((kt + h) % PSTAGES) * PSTAGE_DOUBLES;
+      const double* sB = sA + E::SA::DOUBLES;
 #pragma unroll
-      for (int mi = 0; mi < CfgP::MI; ++mi) af[mi] = sA[(wm0 + mi * 8 + g) * E::SA::STRIDE + kk + t];
+      for (int kk = 0; kk < KC; kk += 4) {
+        double af[CfgP::MI], bf[CfgP::NI];
 #pragma unroll
-      for (int ni = 0; ni < CfgP::NI; ++ni) {
-        const int col = wn0 + ni * 8 + g;
-        bf[ni] = (LB == KCONTIG) ? sB[col * E::SB::STRIDE + kk + t] : sB[(kk + t) * E::SB::STRIDE + col];
+        for (int mi = 0; mi < CfgP::MI; ++mi) af[mi] = sA[(wm0 + mi * 8 + g) * E::SA::STRIDE + kk + t];
+#pragma unroll
+        for (int ni = 0; ni < CfgP::NI; ++ni) {
+          const int col = wn0 + ni * 8 + g;
+          bf[ni] = (LB == KCONTIG) ? sB[col * E::SB::STRIDE + kk + t] : sB[(kk + t) * E::SB::STRIDE + col];
+        }
+#pragma unroll
+        for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
       }
-#pragma unroll
-      for (int mi = 0; mi < CfgP::MI; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
     }
-    // refill the stage consumed in the previous iteration (every warp is past the barrier above,
-    // so nobody still reads it); a flag wait here never delays math on stages already loaded
-    {
-      const int nxt = kt + PSTAGES - 1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int nxt = kt + PSTAGES - 2 + h;
       if (nxt < nk) issue(nxt);
       cp_async_commit();
     }
