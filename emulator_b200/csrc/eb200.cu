@@ -90,8 +90,8 @@ struct eb200_gp {
   double *h_p = nullptr, *h_out = nullptr;  // pinned
   TileTask* tasks = nullptr;
   int2* ktiles = nullptr;
-  FactorTask* ftasks = nullptr;  // dataflow task list
-  int n_ftasks = 0;
+  FactorTask* ftasks = nullptr;  // dataflow task list: Cholesky tasks, then inverse tasks
+  int n_ftasks = 0, n_potrf_tasks = 0;
   unsigned* counter = nullptr;
   int* ready = nullptr;
   int* xready = nullptr;
@@ -182,14 +182,16 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
       DP_SWITCH(h->dp, (kbuild_kernel<DP><<<h->n_ktiles, 256, 0, st>>>(h->ktiles, h->X, h->noise, h->kp, h->n, np, h->A)));
       return 1;
     case OP_FACTOR_DF: {
-      cudaMemsetAsync(h->counter, 0, sizeof(unsigned), st);
-      cudaMemsetAsync(h->ready, 0, (size_t)2 * h->nt * h->nt * sizeof(int), st);  // ready + xready
+      cudaMemsetAsync(h->counter, 0, 2 * sizeof(unsigned), st);
+      cudaMemsetAsync(h->ready, 0, ((size_t)2 * h->nt * h->nt + 256) * sizeof(int), st);  // ready + xready + sm_chain
       FactorArgs fa;
       fa.A = h->A; fa.W = h->W; fa.ld = np; fa.nt = h->nt; fa.n = h->n; fa.X = h->X; fa.noise = h->noise; fa.kp = h->kp;
-      fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready;
+      fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; fa.n_potrf = h->n_potrf_tasks; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready; fa.sm_chain = h->xready + (size_t)h->nt * h->nt;
       fa.logdet_part = h->logdet_part; fa.rdiag = h->rdiag; fa.info = h->info; fa.abort_flag = h->abort_flag;
       fa.trace = h->trace;
-      const int grid = std::min(h->n_sms, h->n_ftasks);
+      // two CTAs per SM: the first wave (one per SM) serves the Cholesky queue, the second the inverse
+      const int grid = std::min(2 * h->n_sms, h->n_ftasks);
+      fa.n_potrf_ctas = std::min(h->n_sms, std::max(1, grid / 2));
       DP_SWITCH(h->dp, (factor_dataflow_kernel<DP><<<grid, 256, FactorSmem<DP>::BYTES, st>>>(fa)));
       return 1;
     }
@@ -358,26 +360,22 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMemset(h->alpha, 0, np * sizeof(double)));
   CK(cudaMemset(h->W, 0, mat));
   CK(cudaMemset(h->A, 0, mat));  // strictly-upper 64-blocks of diagonal 128-tiles must stay zero
-  CK(cudaMalloc(&h->counter, sizeof(unsigned)));
-  CK(cudaMalloc(&h->ready, (size_t)2 * h->nt * h->nt * sizeof(int)));
+  CK(cudaMalloc(&h->counter, 2 * sizeof(unsigned)));
+  CK(cudaMalloc(&h->ready, ((size_t)2 * h->nt * h->nt + 256) * sizeof(int)));
   h->xready = h->ready + (size_t)h->nt * h->nt;
   CK(cudaMalloc(&h->abort_flag, sizeof(int)));
   CK(cudaMalloc(&h->rdiag, (size_t)np * sizeof(double)));
   CK(cudaMemset(h->abort_flag, 0, sizeof(int)));
   CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device));
   {
-    // Cholesky tiles column by column; the inverse's row r follows the Cholesky column r + 1
-    // (its inputs L_r*, X_rr are then already published, so inverse tasks rarely wait).
+    // Cholesky tiles column by column (queue 0), then the inverse's tiles row by row (queue 1).
     std::vector<FactorTask> ft;
     const int nt = h->nt;
-    auto trtri_row = [&](int r) {
-      for (int J = 0; J < r; ++J) ft.push_back({TASK_TRTRI, r, J, 0});
-    };
-    for (int c = 0; c < nt; ++c) {
+    for (int c = 0; c < nt; ++c)
       for (int i = c; i < nt; ++i) ft.push_back({TASK_POTRF, i, c, 0});
-      if (c >= 1) trtri_row(c - 1);
-    }
-    trtri_row(nt - 1);
+    h->n_potrf_tasks = (int)ft.size();
+    for (int r = 1; r < nt; ++r)
+      for (int J = 0; J < r; ++J) ft.push_back({TASK_TRTRI, r, J, 0});
     h->n_ftasks = (int)ft.size();
     CK(cudaMalloc(&h->ftasks, ft.size() * sizeof(FactorTask)));
     CK(cudaMemcpy(h->ftasks, ft.data(), ft.size() * sizeof(FactorTask), cudaMemcpyHostToDevice));

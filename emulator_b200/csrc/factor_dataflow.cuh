@@ -26,7 +26,7 @@
 namespace eb {
 
 using CfgP = TileCfg<64, 64, 32, 16>;  // 256 threads: 2 x 4 warps, 16 accumulator doubles / thread
-constexpr int PSTAGES = 6;             // cp.async ring depth (5 x 16 KB in flight per CTA)
+constexpr int PSTAGES = 4;             // cp.async ring depth (two CTAs per SM share 227 KB)
 constexpr int PSTAGE_DOUBLES = 2 * 64 * (KC + 4);
 constexpr int PS = 65;                 // stride of the 64x64 finalisation buffers
 constexpr int TS = 68;                 // stride of a parked accumulator used as a [k][n] operand
@@ -43,11 +43,14 @@ struct FactorArgs {
   const double* X;        // [np][DP] padded training inputs
   const double* noise;    // [np]
   const KernelParams* kp;
-  const FactorTask* tasks;
+  const FactorTask* tasks;  // [n_potrf Cholesky tasks, column-major][n_trtri inverse tasks, row-major]
   int ntasks;
-  unsigned* counter;      // task counter (zeroed before the launch)
+  int n_potrf;              // tasks [0, n_potrf) are Cholesky tiles, the rest inverse tiles
+  int n_potrf_ctas;         // CTAs [0, n_potrf_ctas) serve the Cholesky list, the others the inverse list
+  unsigned* counter;        // two task counters (zeroed before the launch)
   int* ready;             // [nt*nt] L tile flags (zeroed before the launch)
   int* xready;            // [nt*nt] X tile flags (zeroed before the launch)
+  int* sm_chain;          // [256] per-SM count of resident CTAs working on a chain tile (zeroed before the launch)
   double* logdet_part;    // [nt]
   double* rdiag;          // [nt][64] reciprocal pivots 1 / L_jj, published with the diagonal tile
   int* info;
@@ -71,6 +74,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 __device__ __forceinline__ int ld_flag(const int* p) {
   int v;
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned v;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
   return v;
 }
 __device__ __forceinline__ void st_release(int* p, int v) {
@@ -114,7 +122,8 @@ __device__ __forceinline__ int publish(int* flag, bool ok) {
 template <int LB>
 __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP::NI][2], const double* Ag, int lda,
                                                    const double* Bg, int ldb, int nk, const int* fa, int sa,
-                                                   const int* fb, int sb, int* abort_flag, double* pipe, bool& ok) {
+                                                   const int* fb, int sb, int* abort_flag, double* pipe, bool& ok,
+                                                   const int* yield_to) {
   using E = Engine<CfgP, KCONTIG, LB>;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm0 = (warp / CfgP::WARPS_N) * CfgP::WM;
@@ -157,6 +166,12 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
     cp_async_commit();
   }
   for (int kt = 0; kt < nk; kt += 2) {
+    // Priority for the Cholesky chain: while a co-resident CTA on this SM works on a chain tile
+    // (diagonal / first sub-diagonal), background tasks stand aside so it has the FP64 pipe alone.
+    if (yield_to != nullptr && lane == 0) {
+      int spins = 0;
+      while (ld_flag(yield_to) != 0 && ++spins < (1 << 16)) __nanosleep(200);
+    }
     cp_async_wait<PSTAGES - 4>();
     __syncthreads();
 #pragma unroll
@@ -293,28 +308,35 @@ __device__ __forceinline__ void tile_trsm(double (&v)[2][8], const double* sL, c
   }
 }
 
+// Shared memory of one CTA (two CTAs per SM).  The finalisation buffers alias the cp.async
+// ring: they are only touched after the accumulation loop has drained it.
 template <int DP>
 struct FactorSmem {
   static constexpr int PIPE = PSTAGES * PSTAGE_DOUBLES;
-  static constexpr int C_OFF = PIPE;               // [64][65]  (also the parked [64][68] accumulator, with L_OFF)
-  static constexpr int L_OFF = C_OFF + 64 * PS;    // [64][65]
-  static constexpr int XI_OFF = L_OFF + 64 * PS;   // [DP][64]
-  static constexpr int XJ_OFF = XI_OFF + DP * 64;  // [DP][64]
-  static constexpr int COL_OFF = XJ_OFF + DP * 64; // [128]
-  static constexpr int RD_OFF = COL_OFF + 128;     // [64]
+  static constexpr int C_OFF = 0;                   // [64][65]   C tile / substitution output
+  static constexpr int L_OFF = C_OFF + 64 * PS;     // [64][65]   L_jj
+  static constexpr int T_OFF = 0;                   // [64][68]   parked accumulator (inverse tasks)
+  static constexpr int DINV_OFF = T_OFF + 64 * TS;  // 4 x [64][KC+4] slabs of X_rr (inverse tasks)
+  static constexpr int XI_OFF = PIPE;               // [DP][64]
+  static constexpr int XJ_OFF = XI_OFF + DP * 64;   // [DP][64]
+  static constexpr int COL_OFF = XJ_OFF + DP * 64;  // [128]
+  static constexpr int RD_OFF = COL_OFF + 128;      // [64]
   static constexpr int DOUBLES = RD_OFF + 64 + 16;
   static constexpr int BYTES = DOUBLES * (int)sizeof(double);
-  static_assert(64 * TS <= 2 * 64 * PS, "parked accumulator must fit the finalisation buffers");
+  static_assert(2 * 64 * PS <= PIPE, "finalisation buffers must fit the ring");
+  static_assert(DINV_OFF + 4 * 64 * (KC + 4) <= PIPE, "inverse finalisation must fit the ring");
+  static_assert(2 * BYTES + 2048 <= 227 * 1024, "two CTAs per SM");
 };
 
 template <int DP>
-__global__ void __launch_bounds__(256, 1) factor_dataflow_kernel(const FactorArgs a) {
+__global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArgs a) {
   extern __shared__ __align__(16) double gsm[];
   using SM = FactorSmem<DP>;
   __shared__ unsigned s_task;
   double* sC = gsm + SM::C_OFF;
   double* sL = gsm + SM::L_OFF;
-  double* sT = gsm + SM::C_OFF;  // aliases sC/sL (inverse tasks only)
+  double* sT = gsm + SM::T_OFF;
+  double* sD = gsm + SM::DINV_OFF;
   double* sXi = gsm + SM::XI_OFF;
   double* sXj = gsm + SM::XJ_OFF;
   double* colbuf = gsm + SM::COL_OFF;
@@ -328,10 +350,30 @@ __global__ void __launch_bounds__(256, 1) factor_dataflow_kernel(const FactorArg
 
   for (;;) {
     __syncthreads();  // previous task fully retired (smem reuse, s_task reuse)
-    if (tid == 0) s_task = atomicAdd(a.counter, 1u);
+    // Two queues: Cholesky CTAs run ahead along the dependency chain exactly as if the inverse
+    // were not there; inverse CTAs (co-resident on the same SMs) use the cycles the chain leaves
+    // idle.  A CTA whose own queue is empty helps with the other one.
+    if (tid == 0) {
+      const bool chol = blockIdx.x < (unsigned)a.n_potrf_ctas;
+      const unsigned n0 = chol ? (unsigned)a.n_potrf : (unsigned)(a.ntasks - a.n_potrf);
+      const unsigned n1 = chol ? (unsigned)(a.ntasks - a.n_potrf) : (unsigned)a.n_potrf;
+      const unsigned base0 = chol ? 0u : (unsigned)a.n_potrf, base1 = chol ? (unsigned)a.n_potrf : 0u;
+      unsigned* c0 = a.counter + (chol ? 0 : 1);
+      unsigned* c1 = a.counter + (chol ? 1 : 0);
+      unsigned tk0 = 0xffffffffu;
+      if (ld_flag(reinterpret_cast<const int*>(c0)) < (int)n0) {
+        const unsigned k = atomicAdd(c0, 1u);
+        if (k < n0) tk0 = base0 + k;
+      }
+      if (tk0 == 0xffffffffu) {
+        const unsigned k = atomicAdd(c1, 1u);
+        if (k < n1) tk0 = base1 + k;
+      }
+      s_task = tk0;
+    }
     __syncthreads();
     const unsigned task = s_task;
-    if (task >= (unsigned)a.ntasks) break;
+    if (task == 0xffffffffu) break;
     const FactorTask tk = a.tasks[task];
     const int ti = tk.i, tj = tk.j;
     const int i0 = ti * 64, j0 = tj * 64;
@@ -347,9 +389,9 @@ __global__ void __launch_bounds__(256, 1) factor_dataflow_kernel(const FactorArg
         for (int ni = 0; ni < CfgP::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
       accumulate_flagged<MCONTIG>(acc, a.A + (size_t)i0 * ld + j0, ld, a.W + (size_t)j0 * ld + j0, ld, (ti - tj) * 4,
                                   a.ready + (size_t)ti * nt + tj, 1, a.xready + (size_t)tj * nt + tj, nt, a.abort_flag,
-                                  gsm, ok);
+                                  gsm, ok, a.sm_chain + smid());
       EB_STAMP(1);
-      __syncthreads();  // pipeline drained by every warp before it is refilled / sT written
+      __syncthreads();  // ring drained by every warp before the finalisation buffers overwrite it
       // park the sum as a [k][n] operand
 #pragma unroll
       for (int mi = 0; mi < CfgP::MI; ++mi)
@@ -364,7 +406,7 @@ __global__ void __launch_bounds__(256, 1) factor_dataflow_kernel(const FactorArg
       using EK = Engine<CfgP, KCONTIG, KCONTIG>;
       const double* Dg = a.W + (size_t)i0 * ld + i0;  // X_rr
 #pragma unroll
-      for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(gsm + c * PSTAGE_DOUBLES, Dg + c * KC, ld, tid);
+      for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(sD + c * 64 * (KC + 4), Dg + c * KC, ld, tid);
       cp_async_commit();
 #pragma unroll
       for (int mi = 0; mi < CfgP::MI; ++mi)
@@ -374,7 +416,7 @@ __global__ void __launch_bounds__(256, 1) factor_dataflow_kernel(const FactorArg
       __syncthreads();
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const double* sA = gsm + c * PSTAGE_DOUBLES;
+        const double* sA = sD + c * 64 * (KC + 4);
 #pragma unroll
         for (int kk = 0; kk < KC; kk += 4) {
           double af[CfgP::MI], bf[CfgP::NI];
@@ -406,6 +448,9 @@ __global__ void __launch_bounds__(256, 1) factor_dataflow_kernel(const FactorArg
     }
 
     // ==================================  Cholesky tile (i, j)  ==================================
+    const bool chain_tile = (ti - tj) <= 1;
+    int* my_sm = a.sm_chain + smid();
+    if (chain_tile && tid == 0) atomicAdd(my_sm, 1);
     // stage the training inputs of the tile's rows / columns for the K_ij generation
     for (int e = tid; e < 64 * DP; e += 256) {
       int r = e / DP, m = e % DP;
@@ -459,7 +504,8 @@ __global__ void __launch_bounds__(256, 1) factor_dataflow_kernel(const FactorArg
     // left-looking accumulation over the finished panels: acc += sum_k L_ik L_jk^T
     accumulate_flagged<KCONTIG>(acc, a.A + (size_t)i0 * ld, ld, a.A + (size_t)j0 * ld, ld, tj * 4,
                                 a.ready + (size_t)ti * nt, 1, (ti != tj) ? a.ready + (size_t)tj * nt : nullptr, 1,
-                                a.abort_flag, gsm, ok);
+                                a.abort_flag, gsm, ok, nullptr);
+    __syncthreads();  // ring drained by every warp before the finalisation buffers overwrite it
     // C = -acc parked in shared memory
 #pragma unroll
     for (int mi = 0; mi < CfgP::MI; ++mi) {
@@ -485,6 +531,7 @@ __global__ void __launch_bounds__(256, 1) factor_dataflow_kernel(const FactorArg
       if (tid < 64) a.rdiag[(size_t)tj * 64 + tid] = rdiag[tid];
       EB_STAMP(4);
       int all_ok = publish(a.ready + (size_t)ti * nt + tj, ok);
+      if (tid == 0) atomicSub(my_sm, 1);
       EB_STAMP(5);
       // ---- off the critical path: log-determinant share and X_jj = L_jj^-1 ----
       if (tid < 64) colbuf[tid] = log(rdiag[tid]);
@@ -525,6 +572,7 @@ __global__ void __launch_bounds__(256, 1) factor_dataflow_kernel(const FactorArg
       }
       EB_STAMP(4);
       const int all_ok = publish(a.ready + (size_t)ti * nt + tj, ok);
+      if (chain_tile && tid == 0) atomicSub(my_sm, 1);
       EB_STAMP(5);
       if (!all_ok) break;
     }
