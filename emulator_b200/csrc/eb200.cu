@@ -99,7 +99,7 @@ struct eb200_gp {
   double* rdiag = nullptr;
   unsigned long long* trace = nullptr;  // diagnostics only
   int n_sms = 148;
-  int n_ktiles = 0, n_lauum = 0;
+  int n_ktiles = 0, n_lauum = 0, lauum_full_off = 0, lauum_full_cnt = 0;
   std::vector<Op> ops;
   cudaGraphExec_t g_grad = nullptr, g_lml = nullptr;
   int launches_grad = 0, launches_lml = 0;
@@ -148,11 +148,24 @@ void build_program(eb200_gp* h, std::vector<TileTask>& tasks) {
     ops.push_back(op);
   }
   // ---- K^-1 tiles + gradient traces ----
+  // Tile (I, J) contracts over k >= I*128.  A contraction can be cut into K-slices (the trace is
+  // linear in K^-1; exactly one slice per tile carries the alpha alpha^T term); measured on B200 at
+  // N=4096 slicing at 1024 rows costs more in repeated epilogues (0.99 ms) than it gains in balance
+  // (0.91 ms unsliced), so slicing is off.  The unsplit list also serves the diagnostics path that
+  // stores K^-1.
   {
+    const int LAUUM_SLICE = 1 << 20;  // contraction rows / KC per slice (effectively: no slicing)
     size_t off = tasks.size();
     for (int J = 0; J < nT; ++J)
-      for (int I = J; I < nT; ++I)
-        tasks.push_back({I * 128, J * 128, I * 128, I * 128, I * 128, J * 128, (np - I * 128) / KC, I == J ? 1 : 0});
+      for (int I = J; I < nT; ++I) {
+        const int total = (np - I * 128) / KC;
+        const int nslice = (total + LAUUM_SLICE - 1) / LAUUM_SLICE;
+        for (int sidx = 0; sidx < nslice; ++sidx) {
+          const int c0 = (int)((long long)total * sidx / nslice), c1 = (int)((long long)total * (sidx + 1) / nslice);
+          const int k0 = I * 128 + c0 * KC;
+          tasks.push_back({I * 128, J * 128, k0, I * 128, k0, J * 128, c1 - c0, (I == J ? 1 : 0) | (sidx == 0 ? 2 : 0)});
+        }
+      }
     sort_tasks(tasks, off);
     Op op;
     op.kind = OP_LAUUM;
@@ -162,6 +175,13 @@ void build_program(eb200_gp* h, std::vector<TileTask>& tasks) {
     op.grad_only = true;
     ops.push_back(op);
     h->n_lauum = op.task_cnt;
+    // unsplit list (diagnostics)
+    off = tasks.size();
+    for (int J = 0; J < nT; ++J)
+      for (int I = J; I < nT; ++I)
+        tasks.push_back({I * 128, J * 128, I * 128, I * 128, I * 128, J * 128, (np - I * 128) / KC, (I == J ? 1 : 0) | 2});
+    h->lauum_full_off = (int)off;
+    h->lauum_full_cnt = (int)(tasks.size() - off);
   }
   {
     Op op;
@@ -202,10 +222,15 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
       trmv_t_partial_kernel<<<dim3(h->nT, h->nT), 128, 0, st>>>(h->W, np, np, h->z, h->tpartial);
       trmv_t_reduce_kernel<<<h->nT, 128, 0, st>>>(h->tpartial, np, h->alpha);
       return 2;
-    case OP_LAUUM:
-      DP_SWITCH(h->dp, (lauum_trace_kernel<DP><<<op.task_cnt, 256, LauumSmem<DP>::BYTES, st>>>(
-                           h->tasks + op.task_off, h->W, np, h->X, h->alpha, h->kp, h->n, h->trace_partial, kinv_out)));
+    case OP_LAUUM: {
+      // the diagnostics path (K^-1 stored) needs whole tiles; it has no more tasks than the sliced list
+      const int toff = kinv_out ? h->lauum_full_off : op.task_off;
+      const int tcnt = kinv_out ? h->lauum_full_cnt : op.task_cnt;
+      if (kinv_out) cudaMemsetAsync(h->trace_partial, 0, (size_t)h->n_lauum * (h->dp + 1) * sizeof(double), st);
+      DP_SWITCH(h->dp, (lauum_trace_kernel<DP><<<tcnt, 256, LauumSmem<DP>::BYTES, st>>>(
+                           h->tasks + toff, h->W, np, h->X, h->alpha, h->kp, h->n, h->trace_partial, kinv_out)));
       return 1;
+    }
     case OP_FINALIZE:
       finalize_kernel<<<1, 256, 0, st>>>(h->logdet_part, h->nt, h->z, h->n, h->trace_partial, h->n_lauum, h->dp, h->d,
                                          want_grad, h->info, h->abort_flag, h->out_dev);

@@ -168,10 +168,9 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
   for (int kt = 0; kt < nk; kt += 2) {
     // Priority for the Cholesky chain: while a co-resident CTA on this SM works on a chain tile
     // (diagonal / first sub-diagonal), background tasks stand aside so it has the FP64 pipe alone.
-    if (yield_to != nullptr && lane == 0) {
-      int spins = 0;
-      while (ld_flag(yield_to) != 0 && ++spins < (1 << 16)) __nanosleep(200);
-    }
+    // (the flag is fetched here and only looked at after the math, so its L2 round trip is hidden)
+    int busy = 0;
+    if (yield_to != nullptr && lane == 0) busy = ld_flag(yield_to);
     cp_async_wait<PSTAGES - 4>();
     __syncthreads();
 #pragma unroll
@@ -199,6 +198,10 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
       const int nxt = kt + PSTAGES - 2 + h;
       if (nxt < nk) issue(nxt);
       cp_async_commit();
+    }
+    if (busy != 0) {  // lane 0 only; the other lanes wait for it at the next barrier
+      int spins = 0;
+      while (ld_flag(yield_to) != 0 && ++spins < (1 << 16)) __nanosleep(200);
     }
   }
   cp_async_wait<0>();

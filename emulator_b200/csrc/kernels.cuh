@@ -247,6 +247,9 @@ __global__ void __launch_bounds__(256) lauum_trace_kernel(const TileTask* __rest
   const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM;
   const int wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
   const bool diag = tk.flags & 1;
+  // bit 1: this K-slice carries the alpha_i alpha_j term (the trace is linear in K^-1, so a tile's
+  // contraction may be split into several K-slices, each traced on its own)
+  const double alpha_on = (tk.flags & 2) ? 1.0 : 0.0;
   const bool active = !(diag && (wm0 + Cfg::WM <= 64) && (wn0 >= 64));
   double acc[Cfg::MI][Cfg::NI][2];
 #pragma unroll
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(256) lauum_trace_kernel(const TileTask* __rest
         const double kinv = sC[li * LAUUM_CS + lj];
         if (kinv_out != nullptr) kinv_out[(size_t)gi * ld + gj] = kinv;
         const double w = (gi == gj) ? 1.0 : 2.0;
-        wa[cb] = w * (ai * aj[cb] - kinv) * (amp * exp(-0.5 * r2[cb]));
+        wa[cb] = w * (alpha_on * ai * aj[cb] - kinv) * (amp * exp(-0.5 * r2[cb]));
       }
       s[0] += wa[cb];
     }
