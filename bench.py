@@ -240,10 +240,22 @@ def run_ours(args):
         eval_ms = dev_ms / (args.steps * BATCH)
         achieved_eval = n3 / eval_ms / 1e9
         achieved_stage = stage_flops[dominant] / stage_ms[dominant] / 1e9 if stage_ms[dominant] > 0 else 0.0
+        traffic = None
+        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+            import csv
+            with open(os.path.join(ROOT, "profiles", "r01_top_kernels_ncu.csv")) as fh:
+                rows = list(csv.DictReader(fh))
+            key = "factor_dataflow" if dominant == 1 else "lauum_trace"
+            for row in rows[1:]:
+                if key in row["Kernel Name"]:
+                    traffic = (float(row["dram__bytes_read.sum"]) + float(row["dram__bytes_write.sum"])) * 1e6
+        except Exception:
+            traffic = None
+        kernel_names = {1: "factor_dataflow_kernel (K build + Cholesky + triangular inverse)", 3: "lauum_trace_kernel (K^-1 tiles + traces)"}
         roofline = {
-            "bound": "tensor", "kernel": f"stage '{names[dominant]}' of the eval graph (DMMA.8x8x4 tile engine)",
+            "bound": "tensor", "kernel": kernel_names.get(dominant, names[dominant]) + " -- DMMA.8x8x4 tile engine, one launch per eval",
             "achieved": achieved_stage, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_stage / peak_tflops,
-            "traffic": None,
+            "traffic": traffic, "traffic_source": "profiles/r01_top_kernels_ncu.csv (ncu --set full, bytes per launch)",
             "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; MEASURED_PEAKS.json has no fp64 entry",
             "whole_eval": {"flops": n3, "ms": eval_ms, "achieved": achieved_eval, "frac": achieved_eval / peak_tflops},
             "stage_ms": {k: float(v) for k, v in zip(names, stage_ms)},
