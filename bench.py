@@ -134,7 +134,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -261,12 +261,14 @@ def run_ours(args):
             "stage_ms": {k: float(v) for k, v in zip(names, stage_ms)},
         }
         # ---- CPU baseline on this box's host cores (bounded sample) ----
-        cores = blas_threads()
-        rate, ctimes = cpu_reference_evals(x, y, noise, ps, evals=2, warm=1)
-        cpu_baseline = {
-            "value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
-            "sample": f"2 LML+grad evals (after 1 warm-up) of the george-faithful oracle at N=4096, d=9; {np.mean(ctimes):.2f} s each",
-        }
+        cpu_baseline = None
+        if world == 1:  # reported at N=1 only (torchrun pins OMP_NUM_THREADS=1 on multi-rank launches)
+            cores = blas_threads()
+            rate, ctimes = cpu_reference_evals(x, y, noise, ps, evals=2, warm=1)
+            cpu_baseline = {
+                "value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
+                "sample": f"2 LML+grad evals (after 1 warm-up) of the george-faithful oracle at N=4096, d=9; {np.mean(ctimes):.2f} s each",
+            }
         launches = gp.launches_per_eval(True)
         line = {
             "metric": METRIC, "value": evals / (dev_ms / 1e3), "unit": "evals/s", "n_gpus": world, "steps": args.steps,
@@ -279,14 +281,28 @@ def run_ours(args):
             "gpu_launches": launches * args.steps * BATCH, "launches_per_eval": launches,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     gp.close()
     if world > 1:
         td.barrier()
         td.destroy_process_group()
 
 
+def emit(line: dict):
+    """Write the one JSON line to the real stdout (fd saved before anything could print to it)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    # Libraries (NCCL prints its version banner at communicator creation) write to fd 1; keep the
+    # contract of exactly one JSON line on stdout by pointing fd 1 at stderr for the run.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
