@@ -203,10 +203,10 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
       return 1;
     case OP_FACTOR_DF: {
       cudaMemsetAsync(h->counter, 0, 2 * sizeof(unsigned), st);
-      cudaMemsetAsync(h->ready, 0, ((size_t)2 * h->nt * h->nt + 256) * sizeof(int), st);  // ready + xready + sm_chain
+      cudaMemsetAsync(h->ready, 0, ((size_t)3 * h->nt * h->nt + 256) * sizeof(int), st);  // ready + xready + pready + sm_chain
       FactorArgs fa;
       fa.A = h->A; fa.W = h->W; fa.ld = np; fa.nt = h->nt; fa.n = h->n; fa.X = h->X; fa.noise = h->noise; fa.kp = h->kp;
-      fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; fa.n_potrf = h->n_potrf_tasks; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready; fa.sm_chain = h->xready + (size_t)h->nt * h->nt;
+      fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; fa.n_potrf = h->n_potrf_tasks; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready; fa.pready = h->xready + (size_t)h->nt * h->nt; fa.sm_chain = fa.pready + (size_t)h->nt * h->nt;
       fa.logdet_part = h->logdet_part; fa.rdiag = h->rdiag; fa.info = h->info; fa.abort_flag = h->abort_flag;
       fa.trace = h->trace;
       // two CTAs per SM: the first wave (one per SM) serves the Cholesky queue, the second the inverse
@@ -386,7 +386,7 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMemset(h->W, 0, mat));
   CK(cudaMemset(h->A, 0, mat));  // strictly-upper 64-blocks of diagonal 128-tiles must stay zero
   CK(cudaMalloc(&h->counter, 2 * sizeof(unsigned)));
-  CK(cudaMalloc(&h->ready, ((size_t)2 * h->nt * h->nt + 256) * sizeof(int)));
+  CK(cudaMalloc(&h->ready, ((size_t)3 * h->nt * h->nt + 256) * sizeof(int)));
   h->xready = h->ready + (size_t)h->nt * h->nt;
   CK(cudaMalloc(&h->abort_flag, sizeof(int)));
   CK(cudaMalloc(&h->rdiag, (size_t)np * sizeof(double)));
@@ -399,8 +399,20 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
     for (int c = 0; c < nt; ++c)
       for (int i = c; i < nt; ++i) ft.push_back({TASK_POTRF, i, c, 0});
     h->n_potrf_tasks = (int)ft.size();
+    // Inverse tiles row by row.  A tile with more than MAIN_K + MIN_PART tile products is split: a
+    // helper task (listed as soon as its inputs exist, i.e. after row k-1) pre-accumulates tile
+    // columns [J, k), the tile's own task adds the last MAIN_K and finalises.  This moves most of
+    // the work of the last rows -- the tail of the launch -- into the time the Cholesky chain
+    // leaves SMs idle.
+    const int MAIN_K = 12, MIN_PART = 8;
+    std::vector<std::vector<FactorTask>> after_row(nt);
     for (int r = 1; r < nt; ++r)
-      for (int J = 0; J < r; ++J) ft.push_back({TASK_TRTRI, r, J, 0});
+      for (int J = 0; J < r; ++J)
+        if (r - J > MAIN_K + MIN_PART) after_row[r - MAIN_K - 1].push_back({TASK_TRTRI_PART, r, J, r - MAIN_K});
+    for (int r = 1; r < nt; ++r) {
+      for (int J = 0; J < r; ++J) ft.push_back({TASK_TRTRI, r, J, (r - J > MAIN_K + MIN_PART) ? r - MAIN_K : J});
+      for (auto& tk : after_row[r]) ft.push_back(tk);
+    }
     h->n_ftasks = (int)ft.size();
     CK(cudaMalloc(&h->ftasks, ft.size() * sizeof(FactorTask)));
     CK(cudaMemcpy(h->ftasks, ft.data(), ft.size() * sizeof(FactorTask), cudaMemcpyHostToDevice));

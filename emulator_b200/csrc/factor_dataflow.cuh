@@ -31,9 +31,12 @@ constexpr int PSTAGE_DOUBLES = 2 * 64 * (KC + 4);
 constexpr int PS = 65;                 // stride of the 64x64 finalisation buffers
 constexpr int TS = 68;                 // stride of a parked accumulator used as a [k][n] operand
 
-enum FactorTaskType : int { TASK_POTRF = 0, TASK_TRTRI = 1 };
+// TASK_TRTRI_PART (r, J, k): helper that pre-accumulates sum_{K=J}^{k-1} L_rK X_KJ of a long inverse
+// tile into the (unused) mirrored upper tile of X, so that the tile's own task (k = first tile column
+// it still has to add) is short when the last rows of the inverse form the tail of the launch.
+enum FactorTaskType : int { TASK_POTRF = 0, TASK_TRTRI = 1, TASK_TRTRI_PART = 2 };
 struct FactorTask {
-  int type, i, j, pad;
+  int type, i, j, k;
 };
 
 struct FactorArgs {
@@ -50,6 +53,7 @@ struct FactorArgs {
   unsigned* counter;        // two task counters (zeroed before the launch)
   int* ready;             // [nt*nt] L tile flags (zeroed before the launch)
   int* xready;            // [nt*nt] X tile flags (zeroed before the launch)
+  int* pready;            // [nt*nt] partial-sum flags of long inverse tiles (zeroed before the launch)
   int* sm_chain;          // [256] per-SM count of resident CTAs working on a chain tile (zeroed before the launch)
   double* logdet_part;    // [nt]
   double* rdiag;          // [nt][64] reciprocal pivots 1 / L_jj, published with the diagonal tile
@@ -384,15 +388,49 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     EB_STAMP(0);
     double acc[CfgP::MI][CfgP::NI][2];
 
-    if (tk.type == TASK_TRTRI) {
+    if (tk.type != TASK_POTRF) {
       // =====================  X_rJ = -X_rr * sum_{K=J}^{r-1} L_rK X_KJ  =====================
+      const bool part = tk.type == TASK_TRTRI_PART;
+      const int kbeg = part ? tj : tk.k;   // first tile column this task adds
+      const int kend = part ? tk.k : ti;   // one past the last
+      double* scratch = a.W + (size_t)j0 * ld + i0;  // mirrored upper tile (J, r): never read as X
+      if (!part && kbeg > tj) {
+        ok = wait_ready(a.pready + (size_t)ti * nt + tj, a.abort_flag) && ok;
 #pragma unroll
-      for (int mi = 0; mi < CfgP::MI; ++mi)
+        for (int mi = 0; mi < CfgP::MI; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < CfgP::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-      accumulate_flagged<MCONTIG>(acc, a.A + (size_t)i0 * ld + j0, ld, a.W + (size_t)j0 * ld + j0, ld, (ti - tj) * 4,
-                                  a.ready + (size_t)ti * nt + tj, 1, a.xready + (size_t)tj * nt + tj, nt, a.abort_flag,
-                                  gsm, ok, a.sm_chain + smid());
+          for (int ni = 0; ni < CfgP::NI; ++ni) {
+            const double2 val =
+                __ldcg(reinterpret_cast<const double2*>(scratch + (size_t)(wm0 + mi * 8 + g) * ld + wn0 + ni * 8 + 2 * t));
+            acc[mi][ni][0] = val.x;
+            acc[mi][ni][1] = val.y;
+          }
+      } else {
+#pragma unroll
+        for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < CfgP::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      }
+      accumulate_flagged<MCONTIG>(acc, a.A + (size_t)i0 * ld + (size_t)kbeg * 64, ld,
+                                  a.W + (size_t)kbeg * 64 * ld + j0, ld, (kend - kbeg) * 4,
+                                  a.ready + (size_t)ti * nt + kbeg, 1, a.xready + (size_t)kbeg * nt + tj, nt,
+                                  a.abort_flag, gsm, ok, a.sm_chain + smid());
+      if (part) {
+#pragma unroll
+        for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < CfgP::NI; ++ni) {
+            double2 val;
+            val.x = acc[mi][ni][0];
+            val.y = acc[mi][ni][1];
+            *reinterpret_cast<double2*>(scratch + (size_t)(wm0 + mi * 8 + g) * ld + wn0 + ni * 8 + 2 * t) = val;
+          }
+        EB_STAMP(4);
+        const int part_ok = publish(a.pready + (size_t)ti * nt + tj, ok);
+        EB_STAMP(5);
+        if (!part_ok) break;
+        continue;
+      }
       EB_STAMP(1);
       __syncthreads();  // ring drained by every warp before the finalisation buffers overwrite it
       // park the sum as a [k][n] operand
