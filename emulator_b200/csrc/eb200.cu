@@ -97,6 +97,7 @@ struct eb200_gp {
   int* xready = nullptr;
   int* abort_flag = nullptr;
   double* rdiag = nullptr;
+  double* chain_scratch = nullptr;
   unsigned long long* trace = nullptr;  // diagnostics only
   int n_sms = 148;
   int n_ktiles = 0, n_lauum = 0, lauum_full_off = 0, lauum_full_cnt = 0;
@@ -203,10 +204,10 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
       return 1;
     case OP_FACTOR_DF: {
       cudaMemsetAsync(h->counter, 0, 2 * sizeof(unsigned), st);
-      cudaMemsetAsync(h->ready, 0, ((size_t)3 * h->nt * h->nt + 256) * sizeof(int), st);  // ready + xready + pready + sm_chain
+      cudaMemsetAsync(h->ready, 0, ((size_t)3 * h->nt * h->nt + 2 * h->nt + 256) * sizeof(int), st);  // ready, xready, pready, cready, sm_chain
       FactorArgs fa;
       fa.A = h->A; fa.W = h->W; fa.ld = np; fa.nt = h->nt; fa.n = h->n; fa.X = h->X; fa.noise = h->noise; fa.kp = h->kp;
-      fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; fa.n_potrf = h->n_potrf_tasks; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready; fa.pready = h->xready + (size_t)h->nt * h->nt; fa.sm_chain = fa.pready + (size_t)h->nt * h->nt;
+      fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; fa.n_potrf = h->n_potrf_tasks; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready; fa.pready = h->xready + (size_t)h->nt * h->nt; fa.cready = fa.pready + (size_t)h->nt * h->nt; fa.sm_chain = fa.cready + 2 * h->nt; fa.chain_scratch = h->chain_scratch;
       fa.logdet_part = h->logdet_part; fa.rdiag = h->rdiag; fa.info = h->info; fa.abort_flag = h->abort_flag;
       fa.trace = h->trace;
       // two CTAs per SM: the first wave (one per SM) serves the Cholesky queue, the second the inverse
@@ -386,7 +387,8 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMemset(h->W, 0, mat));
   CK(cudaMemset(h->A, 0, mat));  // strictly-upper 64-blocks of diagonal 128-tiles must stay zero
   CK(cudaMalloc(&h->counter, 2 * sizeof(unsigned)));
-  CK(cudaMalloc(&h->ready, ((size_t)3 * h->nt * h->nt + 256) * sizeof(int)));
+  CK(cudaMalloc(&h->ready, ((size_t)3 * h->nt * h->nt + 2 * h->nt + 256) * sizeof(int)));
+  CK(cudaMalloc(&h->chain_scratch, (size_t)2 * h->nt * 4096 * sizeof(double)));
   h->xready = h->ready + (size_t)h->nt * h->nt;
   CK(cudaMalloc(&h->abort_flag, sizeof(int)));
   CK(cudaMalloc(&h->rdiag, (size_t)np * sizeof(double)));
@@ -396,8 +398,17 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
     // Cholesky tiles column by column (queue 0), then the inverse's tiles row by row (queue 1).
     std::vector<FactorTask> ft;
     const int nt = h->nt;
-    for (int c = 0; c < nt; ++c)
-      for (int i = c; i < nt; ++i) ft.push_back({TASK_POTRF, i, c, 0});
+    // Chain tiles (diagonal, first sub-diagonal) of column c get everything up to column c - CHAIN_LA
+    // pre-accumulated by a background task listed right after column c - CHAIN_LA - 1.
+    const int CHAIN_LA = 6;
+    for (int c = 0; c < nt; ++c) {
+      for (int i = c; i < nt; ++i) ft.push_back({TASK_POTRF, i, c, (i - c <= 1 && c > CHAIN_LA + 2) ? c - CHAIN_LA : 0});
+      const int cc = c + CHAIN_LA + 1;  // column whose chain tiles can now be pre-accumulated up to column c
+      if (cc < nt && cc > CHAIN_LA + 2) {
+        ft.push_back({TASK_POTRF_PART, cc, cc, cc - CHAIN_LA});
+        if (cc + 1 < nt) ft.push_back({TASK_POTRF_PART, cc + 1, cc, cc - CHAIN_LA});
+      }
+    }
     h->n_potrf_tasks = (int)ft.size();
     // Inverse tiles row by row.  A tile with more than MAIN_K + MIN_PART tile products is split: a
     // helper task (listed as soon as its inputs exist, i.e. after row k-1) pre-accumulates tile
@@ -459,7 +470,7 @@ int eb200_gp_destroy(eb200_gp* h) {
   if (h->g_lml) cudaGraphExecDestroy(h->g_lml);
   void* dev[] = {h->A, h->W, h->X, h->noise, h->r, h->z, h->alpha, h->logdet_part, h->tpartial,
                  h->trace_partial, h->p_dev, h->out_dev, h->kp, h->info, h->tasks, h->ktiles, h->T_dev, h->T_in,
-                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ftasks, h->counter, h->ready, h->abort_flag, h->rdiag};
+                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ftasks, h->counter, h->ready, h->abort_flag, h->rdiag, h->chain_scratch};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (h->h_p) cudaFreeHost(h->h_p);
@@ -648,6 +659,28 @@ int eb200_gp_profile_stages(eb200_gp* h, const double* p_host, int reps, float* 
   }
   for (auto& e : ev) cudaEventDestroy(e);
   h->factor_valid = true;
+  return 0;
+}
+
+int eb200_bench_accumulate(int m, int n, int k, int b_mcontig, int grid, const double* a_dev, const double* b_dev,
+                           double* c_dev, void* stream) {
+  if (m % 64 || n % 64 || k % 64) return fail("bench_accumulate: m, n, k must be multiples of 64");
+  static int* ones = nullptr;
+  if (!ones) {
+    CK(cudaMalloc(&ones, 2 * sizeof(int)));
+    int h[2] = {1, 0};
+    CK(cudaMemcpy(ones, h, sizeof(h), cudaMemcpyHostToDevice));
+    CK(cudaFuncSetAttribute(accumulate_bench_kernel<KCONTIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, FactorSmem<2>::BYTES));
+    CK(cudaFuncSetAttribute(accumulate_bench_kernel<MCONTIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, FactorSmem<2>::BYTES));
+  }
+  const int ntiles = (m / 64) * (n / 64);
+  if (b_mcontig)
+    accumulate_bench_kernel<MCONTIG><<<grid, 256, FactorSmem<2>::BYTES, (cudaStream_t)stream>>>(a_dev, k, b_dev, n, c_dev, n, k / KC, n / 64,
+                                                                                                ntiles, ones, ones + 1);
+  else
+    accumulate_bench_kernel<KCONTIG><<<grid, 256, FactorSmem<2>::BYTES, (cudaStream_t)stream>>>(a_dev, k, b_dev, k, c_dev, n, k / KC, n / 64,
+                                                                                                ntiles, ones, ones + 1);
+  CK(cudaGetLastError());
   return 0;
 }
 

@@ -34,7 +34,10 @@ constexpr int TS = 68;                 // stride of a parked accumulator used as
 // TASK_TRTRI_PART (r, J, k): helper that pre-accumulates sum_{K=J}^{k-1} L_rK X_KJ of a long inverse
 // tile into the (unused) mirrored upper tile of X, so that the tile's own task (k = first tile column
 // it still has to add) is short when the last rows of the inverse form the tail of the launch.
-enum FactorTaskType : int { TASK_POTRF = 0, TASK_TRTRI = 1, TASK_TRTRI_PART = 2 };
+// TASK_POTRF_PART (i, j, k), i - j <= 1: the same idea for the Cholesky's chain tiles (diagonal and
+// first sub-diagonal): sum_{c<k} L_ic L_jc^T is pre-accumulated by a background task several block
+// columns ahead, so the chain task's own work is bounded however late it is claimed.
+enum FactorTaskType : int { TASK_POTRF = 0, TASK_TRTRI = 1, TASK_TRTRI_PART = 2, TASK_POTRF_PART = 3 };
 struct FactorTask {
   int type, i, j, k;
 };
@@ -54,6 +57,8 @@ struct FactorArgs {
   int* ready;             // [nt*nt] L tile flags (zeroed before the launch)
   int* xready;            // [nt*nt] X tile flags (zeroed before the launch)
   int* pready;            // [nt*nt] partial-sum flags of long inverse tiles (zeroed before the launch)
+  int* cready;            // [2*nt] partial-sum flags of the Cholesky chain tiles (zeroed before the launch)
+  double* chain_scratch;  // [2*nt][64*64] partial sums of the Cholesky chain tiles
   int* sm_chain;          // [256] per-SM count of resident CTAs working on a chain tile (zeroed before the launch)
   double* logdet_part;    // [nt]
   double* rdiag;          // [nt][64] reciprocal pivots 1 / L_jj, published with the diagonal tile
@@ -134,25 +139,30 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
   const int wn0 = (warp % CfgP::WARPS_N) * CfgP::WN;
   const int g = lane >> 2, t = lane & 3;
   const int ncol = nk >> 2;
-  // leading tile columns already published (one coalesced look per warp)
+  // `known`: leading tile columns whose flags have been seen set (one coalesced look per warp)
   int known = 0;
-  for (int base = 0; base < ncol; base += 32) {
-    const int kc = base + lane;
-    int f = 1;
-    if (kc < ncol) f = (ld_flag(fa + (size_t)kc * sa) != 0) && (fb == nullptr || ld_flag(fb + (size_t)kc * sb) != 0);
-    const unsigned missing = __ballot_sync(0xffffffffu, f == 0);
-    if (missing) {
-      known = base + __ffs(missing) - 1;
-      break;
+  auto rescan = [&](int from) {
+    known = from;
+    for (int base = from; base < ncol; base += 32) {
+      const int kc = base + lane;
+      int f = 1;
+      if (kc < ncol) f = (ld_flag(fa + (size_t)kc * sa) != 0) && (fb == nullptr || ld_flag(fb + (size_t)kc * sb) != 0);
+      const unsigned missing = __ballot_sync(0xffffffffu, f == 0);
+      if (missing) {
+        known = base + __ffs(missing) - 1;
+        return;
+      }
+      known = min(base + 32, ncol);
     }
-    known = min(base + 32, ncol);
-  }
+  };
+  rescan(0);
   auto issue = [&](int kt) {
     if ((kt & 3) == 0) {
       const int kc = kt >> 2;
       if (kc >= known) {
         ok = wait_ready(fa + (size_t)kc * sa, abort_flag) && ok;
         if (fb != nullptr) ok = wait_ready(fb + (size_t)kc * sb, abort_flag) && ok;
+        rescan(kc + 1);  // producers usually publish several tile columns while we wait
       }
     }
     double* stage = pipe + (kt % PSTAGES) * PSTAGE_DOUBLES;
@@ -161,22 +171,31 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
     E::template load_operand<64, KCONTIG>(stage, ap, lda, tid);
     E::template load_operand<64, LB>(stage + E::SA::DOUBLES, bp, ldb, tid);
   };
-  // Two chunks per barrier: nk is a multiple of 4, so pairs never straddle the end.  Ring slots
-  // refilled after the math of pair (kt, kt+1) are the ones consumed by the previous pair, which
-  // every warp has left behind at this iteration's barrier.
-#pragma unroll
-  for (int s = 0; s < PSTAGES - 2; ++s) {
-    if (s < nk) issue(s);
-    cp_async_commit();
+  // Ring of PSTAGES = 4 stages, two chunks (one "pair") per barrier.  While pair kt is in the math,
+  // pair kt+2 is in flight into the other two stages: it is issued right after the barrier whenever
+  // its flags are already known (the common case), and only after the math -- where a blocking flag
+  // wait cannot delay work on data that has landed -- at the dependency frontier.
+  static_assert(PSTAGES == 4, "ring logic below assumes two pairs");
+  if (nk > 0) {
+    issue(0);
+    issue(1);
   }
+  cp_async_commit();
   for (int kt = 0; kt < nk; kt += 2) {
     // Priority for the Cholesky chain: while a co-resident CTA on this SM works on a chain tile
     // (diagonal / first sub-diagonal), background tasks stand aside so it has the FP64 pipe alone.
     // (the flag is fetched here and only looked at after the math, so its L2 round trip is hidden)
     int busy = 0;
     if (yield_to != nullptr && lane == 0) busy = ld_flag(yield_to);
-    cp_async_wait<PSTAGES - 4>();
+    cp_async_wait<0>();
     __syncthreads();
+    const bool more = kt + 2 < nk;
+    const bool early = more && (((kt + 2) >> 2) < known);  // kt+2 and kt+3 share a tile column
+    if (early) {
+      issue(kt + 2);
+      issue(kt + 3);
+      cp_async_commit();
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const double* sA = pipe + ((kt + h) % PSTAGES) * PSTAGE_DOUBLES;
@@ -197,10 +216,9 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
           for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
       }
     }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int nxt = kt + PSTAGES - 2 + h;
-      if (nxt < nk) issue(nxt);
+    if (more && !early) {
+      issue(kt + 2);
+      issue(kt + 3);
       cp_async_commit();
     }
     if (busy != 0) {  // lane 0 only; the other lanes wait for it at the next barrier
@@ -388,6 +406,31 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     EB_STAMP(0);
     double acc[CfgP::MI][CfgP::NI][2];
 
+    if (tk.type == TASK_POTRF_PART) {
+      // ============  background pre-accumulation of a chain tile: sum_{c<k} L_ic L_jc^T  ============
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < CfgP::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      accumulate_flagged<KCONTIG>(acc, a.A + (size_t)i0 * ld, ld, a.A + (size_t)j0 * ld, ld, tk.k * 4,
+                                  a.ready + (size_t)ti * nt, 1, (ti != tj) ? a.ready + (size_t)tj * nt : nullptr, 1,
+                                  a.abort_flag, gsm, ok, a.sm_chain + smid());
+      double* cs = a.chain_scratch + (size_t)(2 * tj + (ti - tj)) * 4096;
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < CfgP::NI; ++ni) {
+          double2 val;
+          val.x = acc[mi][ni][0];
+          val.y = acc[mi][ni][1];
+          *reinterpret_cast<double2*>(cs + (wm0 + mi * 8 + g) * 64 + wn0 + ni * 8 + 2 * t) = val;
+        }
+      EB_STAMP(4);
+      const int part_ok = publish(a.cready + 2 * tj + (ti - tj), ok);
+      EB_STAMP(5);
+      if (!part_ok) break;
+      continue;
+    }
     if (tk.type != TASK_POTRF) {
       // =====================  X_rJ = -X_rr * sum_{K=J}^{r-1} L_rK X_KJ  =====================
       const bool part = tk.type == TASK_TRTRI_PART;
@@ -489,9 +532,10 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     }
 
     // ==================================  Cholesky tile (i, j)  ==================================
+    // Chain tiles raise their SM's priority flag only for the latency-bound finalisation (never
+    // while they wait for a producer: a background task on the same SM may be that producer).
     const bool chain_tile = (ti - tj) <= 1;
     int* my_sm = a.sm_chain + smid();
-    if (chain_tile && tid == 0) atomicAdd(my_sm, 1);
     // stage the training inputs of the tile's rows / columns for the K_ij generation
     for (int e = tid; e < 64 * DP; e += 256) {
       int r = e / DP, m = e % DP;
@@ -542,10 +586,23 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       }
     }
     EB_STAMP(1);
+    const int kbeg = tk.k;  // > 0: tile columns [0, kbeg) were pre-accumulated by a TASK_POTRF_PART
+    if (kbeg > 0) {
+      ok = wait_ready(a.cready + 2 * tj + (ti - tj), a.abort_flag) && ok;
+      const double* cs = a.chain_scratch + (size_t)(2 * tj + (ti - tj)) * 4096;
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < CfgP::NI; ++ni) {
+          const double2 val = __ldcg(reinterpret_cast<const double2*>(cs + (wm0 + mi * 8 + g) * 64 + wn0 + ni * 8 + 2 * t));
+          acc[mi][ni][0] += val.x;
+          acc[mi][ni][1] += val.y;
+        }
+    }
     // left-looking accumulation over the finished panels: acc += sum_k L_ik L_jk^T
-    accumulate_flagged<KCONTIG>(acc, a.A + (size_t)i0 * ld, ld, a.A + (size_t)j0 * ld, ld, tj * 4,
-                                a.ready + (size_t)ti * nt, 1, (ti != tj) ? a.ready + (size_t)tj * nt : nullptr, 1,
-                                a.abort_flag, gsm, ok, nullptr);
+    accumulate_flagged<KCONTIG>(acc, a.A + (size_t)i0 * ld + (size_t)kbeg * 64, ld, a.A + (size_t)j0 * ld + (size_t)kbeg * 64, ld,
+                                (tj - kbeg) * 4, a.ready + (size_t)ti * nt + kbeg, 1,
+                                (ti != tj) ? a.ready + (size_t)tj * nt + kbeg : nullptr, 1, a.abort_flag, gsm, ok, nullptr);
     __syncthreads();  // ring drained by every warp before the finalisation buffers overwrite it
     // C = -acc parked in shared memory
 #pragma unroll
@@ -564,6 +621,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       for (int c = 0; c < 8; ++c) v[sl][c] = sC[(lane + 32 * sl) * PS + 8 * warp + c];
 
     if (ti == tj) {
+      if (tid == 0) atomicAdd(my_sm, 1);
       tile_cholesky(v, sL, rdiag, a.info, j0);
       for (int e = tid; e < 64 * 64; e += 256) {
         const int r = e >> 6, c = e & 63;
@@ -596,6 +654,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       if (!all_ok) break;
     } else {
       ok = wait_ready(a.ready + (size_t)tj * nt + tj, a.abort_flag) && ok;
+      if (chain_tile && tid == 0) atomicAdd(my_sm, 1);
       EB_STAMP(3);
       const double* Lg = a.A + (size_t)j0 * ld + j0;
       for (int e = tid; e < 64 * 32; e += 256) {
@@ -617,6 +676,41 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       EB_STAMP(5);
       if (!all_ok) break;
     }
+  }
+}
+
+
+// Micro-benchmark of the dataflow main loop in isolation (all flags preset): C (64x64 tiles) =
+// A * B^T with B KCONTIG, or A * B with B MCONTIG; used to tune the loop without the chain.
+template <int LB>
+__global__ void __launch_bounds__(256, 2) accumulate_bench_kernel(const double* A, int lda, const double* B, int ldb,
+                                                                  double* C, int ldc, int nk, int tiles_n, int ntiles,
+                                                                  const int* ones, int* abort_flag) {
+  extern __shared__ __align__(16) double gsm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp / CfgP::WARPS_N) * CfgP::WM;
+  const int wn0 = (warp % CfgP::WARPS_N) * CfgP::WN;
+  const int g = lane >> 2, t = lane & 3;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int i0 = (tile / tiles_n) * 64, j0 = (tile % tiles_n) * 64;
+    double acc[CfgP::MI][CfgP::NI][2];
+#pragma unroll
+    for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < CfgP::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    bool ok = true;
+    __syncthreads();
+    accumulate_flagged<LB>(acc, A + (size_t)i0 * lda, lda, (LB == KCONTIG) ? B + (size_t)j0 * ldb : B + j0, ldb, nk, ones, 0,
+                           nullptr, 0, abort_flag, gsm, ok, nullptr);
+#pragma unroll
+    for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < CfgP::NI; ++ni) {
+        double2 val;
+        val.x = acc[mi][ni][0];
+        val.y = acc[mi][ni][1];
+        *reinterpret_cast<double2*>(C + (size_t)(i0 + wm0 + mi * 8 + g) * ldc + j0 + wn0 + ni * 8 + 2 * t) = val;
+      }
   }
 }
 

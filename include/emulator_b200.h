@@ -94,6 +94,11 @@ int eb200_gp_factor_tasks(const eb200_gp* gp);
  * triangular inverse), [2] = alpha, [3] = K^-1 tiles + gradient traces, [4] = final reduction. */
 int eb200_gp_profile_stages(eb200_gp* gp, const double* p_host, int reps, float* ms_out);
 
+/* Micro-benchmark of the dataflow kernel's 64x64 main loop in isolation: C[m][n] = A[m][k] * B[n][k]^T
+ * (b_mcontig = 0) or A[m][k] * B[k][n] (b_mcontig = 1) with `grid` persistent CTAs. */
+int eb200_bench_accumulate(int m, int n, int k, int b_mcontig, int grid, const double* a_dev, const double* b_dev,
+                           double* c_dev, void* stream);
+
 /* Engine micro-benchmark: C[m][n] = A[m][k] * B[n][k]^T through the tile engine, device
  * pointers, m, n multiples of 128, k multiple of 16.  Used by bench.py to report the engine's
  * DMMA throughput next to cuBLAS DGEMM. */
