@@ -97,7 +97,6 @@ struct eb200_gp {
   int* xready = nullptr;
   int* abort_flag = nullptr;
   double* rdiag = nullptr;
-  double* chain_scratch = nullptr;
   unsigned long long* trace = nullptr;  // diagnostics only
   int n_sms = 148;
   int n_ktiles = 0, n_lauum = 0, lauum_full_off = 0, lauum_full_cnt = 0;
@@ -204,10 +203,10 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
       return 1;
     case OP_FACTOR_DF: {
       cudaMemsetAsync(h->counter, 0, 2 * sizeof(unsigned), st);
-      cudaMemsetAsync(h->ready, 0, ((size_t)3 * h->nt * h->nt + 2 * h->nt + 256) * sizeof(int), st);  // ready, xready, pready, cready, sm_chain
+      cudaMemsetAsync(h->ready, 0, ((size_t)4 * h->nt * h->nt + 256) * sizeof(int), st);  // ready, xready, pready, cready, sm_chain
       FactorArgs fa;
       fa.A = h->A; fa.W = h->W; fa.ld = np; fa.nt = h->nt; fa.n = h->n; fa.X = h->X; fa.noise = h->noise; fa.kp = h->kp;
-      fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; fa.n_potrf = h->n_potrf_tasks; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready; fa.pready = h->xready + (size_t)h->nt * h->nt; fa.cready = fa.pready + (size_t)h->nt * h->nt; fa.sm_chain = fa.cready + 2 * h->nt; fa.chain_scratch = h->chain_scratch;
+      fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; fa.n_potrf = h->n_potrf_tasks; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready; fa.pready = h->xready + (size_t)h->nt * h->nt; fa.cready = fa.pready + (size_t)h->nt * h->nt; fa.sm_chain = fa.cready + (size_t)h->nt * h->nt;
       fa.logdet_part = h->logdet_part; fa.rdiag = h->rdiag; fa.info = h->info; fa.abort_flag = h->abort_flag;
       fa.trace = h->trace;
       // two CTAs per SM: the first wave (one per SM) serves the Cholesky queue, the second the inverse
@@ -387,8 +386,7 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMemset(h->W, 0, mat));
   CK(cudaMemset(h->A, 0, mat));  // strictly-upper 64-blocks of diagonal 128-tiles must stay zero
   CK(cudaMalloc(&h->counter, 2 * sizeof(unsigned)));
-  CK(cudaMalloc(&h->ready, ((size_t)3 * h->nt * h->nt + 2 * h->nt + 256) * sizeof(int)));
-  CK(cudaMalloc(&h->chain_scratch, (size_t)2 * h->nt * 4096 * sizeof(double)));
+  CK(cudaMalloc(&h->ready, ((size_t)4 * h->nt * h->nt + 256) * sizeof(int)));
   h->xready = h->ready + (size_t)h->nt * h->nt;
   CK(cudaMalloc(&h->abort_flag, sizeof(int)));
   CK(cudaMalloc(&h->rdiag, (size_t)np * sizeof(double)));
@@ -398,16 +396,18 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
     // Cholesky tiles column by column (queue 0), then the inverse's tiles row by row (queue 1).
     std::vector<FactorTask> ft;
     const int nt = h->nt;
-    // Chain tiles (diagonal, first sub-diagonal) of column c get everything up to column c - CHAIN_LA
-    // pre-accumulated by a background task listed right after column c - CHAIN_LA - 1.
-    const int CHAIN_LA = 6;
+    // A tile (i, c) with more than POTRF_LA + POTRF_MINP tile products is split: a background task
+    // listed right after column c - POTRF_LA - 1 (when its inputs exist) pre-accumulates tile columns
+    // [0, c - POTRF_LA); the tile's own task adds the last POTRF_LA and finalises.  Near the diagonal
+    // those own tasks sit on (or a few steps off) the dependency chain, so bounding their work keeps
+    // the chain from stalling on a late-claimed tile.
+    const int POTRF_LA = 8, POTRF_MINP = 4;
+    auto split = [&](int c) { return c > POTRF_LA + POTRF_MINP; };
     for (int c = 0; c < nt; ++c) {
-      for (int i = c; i < nt; ++i) ft.push_back({TASK_POTRF, i, c, (i - c <= 1 && c > CHAIN_LA + 2) ? c - CHAIN_LA : 0});
-      const int cc = c + CHAIN_LA + 1;  // column whose chain tiles can now be pre-accumulated up to column c
-      if (cc < nt && cc > CHAIN_LA + 2) {
-        ft.push_back({TASK_POTRF_PART, cc, cc, cc - CHAIN_LA});
-        if (cc + 1 < nt) ft.push_back({TASK_POTRF_PART, cc + 1, cc, cc - CHAIN_LA});
-      }
+      for (int i = c; i < nt; ++i) ft.push_back({TASK_POTRF, i, c, split(c) ? c - POTRF_LA : 0});
+      const int cc = c + POTRF_LA + 1;  // column whose tiles can now be pre-accumulated up to column c
+      if (cc < nt && split(cc))
+        for (int i = cc; i < nt; ++i) ft.push_back({TASK_POTRF_PART, i, cc, cc - POTRF_LA});
     }
     h->n_potrf_tasks = (int)ft.size();
     // Inverse tiles row by row.  A tile with more than MAIN_K + MIN_PART tile products is split: a
@@ -470,7 +470,7 @@ int eb200_gp_destroy(eb200_gp* h) {
   if (h->g_lml) cudaGraphExecDestroy(h->g_lml);
   void* dev[] = {h->A, h->W, h->X, h->noise, h->r, h->z, h->alpha, h->logdet_part, h->tpartial,
                  h->trace_partial, h->p_dev, h->out_dev, h->kp, h->info, h->tasks, h->ktiles, h->T_dev, h->T_in,
-                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ftasks, h->counter, h->ready, h->abort_flag, h->rdiag, h->chain_scratch};
+                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ftasks, h->counter, h->ready, h->abort_flag, h->rdiag};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (h->h_p) cudaFreeHost(h->h_p);

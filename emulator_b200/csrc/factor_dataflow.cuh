@@ -34,9 +34,10 @@ constexpr int TS = 68;                 // stride of a parked accumulator used as
 // TASK_TRTRI_PART (r, J, k): helper that pre-accumulates sum_{K=J}^{k-1} L_rK X_KJ of a long inverse
 // tile into the (unused) mirrored upper tile of X, so that the tile's own task (k = first tile column
 // it still has to add) is short when the last rows of the inverse form the tail of the launch.
-// TASK_POTRF_PART (i, j, k), i - j <= 1: the same idea for the Cholesky's chain tiles (diagonal and
-// first sub-diagonal): sum_{c<k} L_ic L_jc^T is pre-accumulated by a background task several block
-// columns ahead, so the chain task's own work is bounded however late it is claimed.
+// TASK_POTRF_PART (i, j, k): the same idea for the Cholesky: sum_{c<k} L_ic L_jc^T of tile (i, j) is
+// pre-accumulated by a background task listed several block columns ahead and parked in the tile's
+// own (not yet published) storage, so that the tile's task -- which near the diagonal sits on or
+// next to the dependency chain -- has a bounded amount of work however late it is claimed.
 enum FactorTaskType : int { TASK_POTRF = 0, TASK_TRTRI = 1, TASK_TRTRI_PART = 2, TASK_POTRF_PART = 3 };
 struct FactorTask {
   int type, i, j, k;
@@ -57,8 +58,7 @@ struct FactorArgs {
   int* ready;             // [nt*nt] L tile flags (zeroed before the launch)
   int* xready;            // [nt*nt] X tile flags (zeroed before the launch)
   int* pready;            // [nt*nt] partial-sum flags of long inverse tiles (zeroed before the launch)
-  int* cready;            // [2*nt] partial-sum flags of the Cholesky chain tiles (zeroed before the launch)
-  double* chain_scratch;  // [2*nt][64*64] partial sums of the Cholesky chain tiles
+  int* cready;            // [nt*nt] partial-sum flags of the Cholesky tiles (zeroed before the launch)
   int* sm_chain;          // [256] per-SM count of resident CTAs working on a chain tile (zeroed before the launch)
   double* logdet_part;    // [nt]
   double* rdiag;          // [nt][64] reciprocal pivots 1 / L_jj, published with the diagonal tile
@@ -112,6 +112,15 @@ __device__ __forceinline__ bool wait_ready(const int* flag, int* abort_flag) {
   }
   ok = __shfl_sync(0xffffffffu, ok, 0);
   return ok;
+}
+
+// Background work stands aside while a chain tile is being finalised on this SM.
+__device__ __forceinline__ void yield_to_chain(const int* sm_flag) {
+  if ((threadIdx.x & 31) == 0) {
+    int spins = 0;
+    while (ld_flag(sm_flag) != 0 && ++spins < (1 << 14)) __nanosleep(200);
+  }
+  __syncwarp();
 }
 
 // Publish a tile: all of the CTA's stores happen-before the barrier, thread 0's cumulative
@@ -415,7 +424,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       accumulate_flagged<KCONTIG>(acc, a.A + (size_t)i0 * ld, ld, a.A + (size_t)j0 * ld, ld, tk.k * 4,
                                   a.ready + (size_t)ti * nt, 1, (ti != tj) ? a.ready + (size_t)tj * nt : nullptr, 1,
                                   a.abort_flag, gsm, ok, a.sm_chain + smid());
-      double* cs = a.chain_scratch + (size_t)(2 * tj + (ti - tj)) * 4096;
+      double* cs = a.A + (size_t)i0 * ld + j0;  // the tile's own storage (nobody reads it before L_ij is published)
 #pragma unroll
       for (int mi = 0; mi < CfgP::MI; ++mi)
 #pragma unroll
@@ -423,10 +432,10 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
           double2 val;
           val.x = acc[mi][ni][0];
           val.y = acc[mi][ni][1];
-          *reinterpret_cast<double2*>(cs + (wm0 + mi * 8 + g) * 64 + wn0 + ni * 8 + 2 * t) = val;
+          *reinterpret_cast<double2*>(cs + (size_t)(wm0 + mi * 8 + g) * ld + wn0 + ni * 8 + 2 * t) = val;
         }
       EB_STAMP(4);
-      const int part_ok = publish(a.cready + 2 * tj + (ti - tj), ok);
+      const int part_ok = publish(a.cready + (size_t)ti * nt + tj, ok);
       EB_STAMP(5);
       if (!part_ok) break;
       continue;
@@ -486,6 +495,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
           pc[1] = acc[mi][ni][1];
         }
       ok = wait_ready(a.xready + (size_t)ti * nt + ti, a.abort_flag) && ok;
+      yield_to_chain(a.sm_chain + smid());
       EB_STAMP(2);
       using EK = Engine<CfgP, KCONTIG, KCONTIG>;
       const double* Dg = a.W + (size_t)i0 * ld + i0;  // X_rr
@@ -536,6 +546,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     // while they wait for a producer: a background task on the same SM may be that producer).
     const bool chain_tile = (ti - tj) <= 1;
     int* my_sm = a.sm_chain + smid();
+    if (!chain_tile) yield_to_chain(my_sm);  // the exp()-heavy K generation competes for the FP64 pipe
     // stage the training inputs of the tile's rows / columns for the K_ij generation
     for (int e = tid; e < 64 * DP; e += 256) {
       int r = e / DP, m = e % DP;
@@ -588,13 +599,14 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     EB_STAMP(1);
     const int kbeg = tk.k;  // > 0: tile columns [0, kbeg) were pre-accumulated by a TASK_POTRF_PART
     if (kbeg > 0) {
-      ok = wait_ready(a.cready + 2 * tj + (ti - tj), a.abort_flag) && ok;
-      const double* cs = a.chain_scratch + (size_t)(2 * tj + (ti - tj)) * 4096;
+      ok = wait_ready(a.cready + (size_t)ti * nt + tj, a.abort_flag) && ok;
+      const double* cs = a.A + (size_t)i0 * ld + j0;
 #pragma unroll
       for (int mi = 0; mi < CfgP::MI; ++mi)
 #pragma unroll
         for (int ni = 0; ni < CfgP::NI; ++ni) {
-          const double2 val = __ldcg(reinterpret_cast<const double2*>(cs + (wm0 + mi * 8 + g) * 64 + wn0 + ni * 8 + 2 * t));
+          const double2 val =
+              __ldcg(reinterpret_cast<const double2*>(cs + (size_t)(wm0 + mi * 8 + g) * ld + wn0 + ni * 8 + 2 * t));
           acc[mi][ni][0] += val.x;
           acc[mi][ni][1] += val.y;
         }
@@ -602,7 +614,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     // left-looking accumulation over the finished panels: acc += sum_k L_ik L_jk^T
     accumulate_flagged<KCONTIG>(acc, a.A + (size_t)i0 * ld + (size_t)kbeg * 64, ld, a.A + (size_t)j0 * ld + (size_t)kbeg * 64, ld,
                                 (tj - kbeg) * 4, a.ready + (size_t)ti * nt + kbeg, 1,
-                                (ti != tj) ? a.ready + (size_t)tj * nt + kbeg : nullptr, 1, a.abort_flag, gsm, ok, nullptr);
+                                (ti != tj) ? a.ready + (size_t)tj * nt + kbeg : nullptr, 1, a.abort_flag, gsm, ok, my_sm);
     __syncthreads();  // ring drained by every warp before the finalisation buffers overwrite it
     // C = -acc parked in shared memory
 #pragma unroll
@@ -654,6 +666,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       if (!all_ok) break;
     } else {
       ok = wait_ready(a.ready + (size_t)tj * nt + tj, a.abort_flag) && ok;
+      if (!chain_tile) yield_to_chain(my_sm);
       if (chain_tile && tid == 0) atomicAdd(my_sm, 1);
       EB_STAMP(3);
       const double* Lg = a.A + (size_t)j0 * ld + j0;

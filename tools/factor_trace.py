@@ -23,13 +23,22 @@ print("ntasks", ntasks, "total us", t[:, 5].max())
 po = tasks[:, 0] == 0
 diag = {int(r[2]): k for k, r in enumerate(tasks) if r[0] == 0 and r[1] == r[2]}
 sub = {int(r[2]): k for k, r in enumerate(tasks) if r[0] == 0 and r[1] == r[2] + 1}
-print("j  diag: claimed kgen_done C_done stored published | sub(j+1,j): kgen_done Ljj_seen stored published")
-for j in list(range(0, min(nt, 4))) + list(range(nt // 2, nt // 2 + 3)) + list(range(max(nt - 3, 0), nt)):
+print("j  diag: claimed kgen_done C_done stored published | sub(j+1,j): claimed C_done Ljj_seen stored published")
+for j in list(range(0, min(nt, 3))) + list(range(nt // 2, min(nt, nt // 2 + 12))) + list(range(max(nt - 3, 0), nt)):
     kd = diag[j]; row = f"{j:3d} " + " ".join(f"{v:9.2f}" for v in t[kd, [0, 1, 2, 4, 5]])
     if j in sub:
-        ks = sub[j]; row += " | " + " ".join(f"{v:9.2f}" for v in t[ks, [1, 3, 4, 5]])
+        ks = sub[j]; row += " | " + " ".join(f"{v:9.2f}" for v in t[ks, [0, 2, 3, 4, 5]])
     print(row)
 pub = np.array([t[diag[j], 5] for j in range(nt)])
+steps = np.diff(pub)
+print("step us percentiles 10/50/90/max:", np.percentile(steps, [10, 50, 90, 100]))
+# what the diagonal task of step j+1 waited for: its C_done minus the sub-diagonal publish of step j
+lag_d = np.array([t[diag[j + 1], 2] - t[sub[j], 5] for j in range(nt - 1)])
+lag_s = np.array([t[sub[j], 3] - t[diag[j], 5] for j in range(nt - 1) if j in sub])
+print("diag C_done - prev sub published (last-panel latency) 10/50/90/max:", np.percentile(lag_d, [10, 50, 90, 100]))
+print("sub Ljj_seen - diag published 10/50/90/max:", np.percentile(lag_s, [10, 50, 90, 100]))
+late_s = np.array([t[sub[j], 2] - t[diag[j], 5] for j in range(nt - 1) if j in sub])
+print("sub C_done - diag published (positive = sub tile's own accumulation finished late) 10/50/90/max:", np.percentile(late_s, [10, 50, 90, 100]))
 print("cholesky finished at us", pub.max(), " mean diag-to-diag step us:", np.diff(pub).mean())
 dd = np.array([t[diag[j], 4] - t[diag[j], 2] for j in range(nt)]); print("diag factor+store us: mean", dd.mean())
 off = po & (tasks[:, 1] != tasks[:, 2])
