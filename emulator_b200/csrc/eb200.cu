@@ -91,7 +91,7 @@ struct eb200_gp {
   TileTask* tasks = nullptr;
   int2* ktiles = nullptr;
   FactorTask* ftasks = nullptr;  // dataflow task list: Cholesky tasks, then inverse tasks
-  int n_ftasks = 0, n_potrf_tasks = 0;
+  int n_ftasks = 0, qbase[4] = {0, 0, 0, 0};
   unsigned* counter = nullptr;
   int* ready = nullptr;
   int* xready = nullptr;
@@ -202,16 +202,18 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
       DP_SWITCH(h->dp, (kbuild_kernel<DP><<<h->n_ktiles, 256, 0, st>>>(h->ktiles, h->X, h->noise, h->kp, h->n, np, h->A)));
       return 1;
     case OP_FACTOR_DF: {
-      cudaMemsetAsync(h->counter, 0, 2 * sizeof(unsigned), st);
+      cudaMemsetAsync(h->counter, 0, 4 * sizeof(unsigned), st);
       cudaMemsetAsync(h->ready, 0, ((size_t)4 * h->nt * h->nt + 256) * sizeof(int), st);  // ready, xready, pready, cready, sm_chain
       FactorArgs fa;
       fa.A = h->A; fa.W = h->W; fa.ld = np; fa.nt = h->nt; fa.n = h->n; fa.X = h->X; fa.noise = h->noise; fa.kp = h->kp;
-      fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; fa.n_potrf = h->n_potrf_tasks; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready; fa.pready = h->xready + (size_t)h->nt * h->nt; fa.cready = fa.pready + (size_t)h->nt * h->nt; fa.sm_chain = fa.cready + (size_t)h->nt * h->nt;
+      fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; for (int q = 0; q < 4; ++q) fa.qbase[q] = h->qbase[q]; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready; fa.pready = h->xready + (size_t)h->nt * h->nt; fa.cready = fa.pready + (size_t)h->nt * h->nt; fa.sm_chain = fa.cready + (size_t)h->nt * h->nt;
       fa.logdet_part = h->logdet_part; fa.rdiag = h->rdiag; fa.info = h->info; fa.abort_flag = h->abort_flag;
       fa.trace = h->trace;
       // two CTAs per SM: the first wave (one per SM) serves the Cholesky queue, the second the inverse
       const int grid = std::min(2 * h->n_sms, h->n_ftasks);
-      fa.n_potrf_ctas = std::min(h->n_sms, std::max(1, grid / 2));
+      fa.n_sms = h->n_sms;
+      // at least one CTA always serves the chain queue, never so many that the other queues starve
+      fa.n_chain_sms = std::max(1, std::min({6, h->nt / 8, grid / 4}));
       DP_SWITCH(h->dp, (factor_dataflow_kernel<DP><<<grid, 256, FactorSmem<DP>::BYTES, st>>>(fa)));
       return 1;
     }
@@ -385,7 +387,7 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMemset(h->alpha, 0, np * sizeof(double)));
   CK(cudaMemset(h->W, 0, mat));
   CK(cudaMemset(h->A, 0, mat));  // strictly-upper 64-blocks of diagonal 128-tiles must stay zero
-  CK(cudaMalloc(&h->counter, 2 * sizeof(unsigned)));
+  CK(cudaMalloc(&h->counter, 4 * sizeof(unsigned)));
   CK(cudaMalloc(&h->ready, ((size_t)4 * h->nt * h->nt + 256) * sizeof(int)));
   h->xready = h->ready + (size_t)h->nt * h->nt;
   CK(cudaMalloc(&h->abort_flag, sizeof(int)));
@@ -393,23 +395,29 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMemset(h->abort_flag, 0, sizeof(int)));
   CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device));
   {
-    // Cholesky tiles column by column (queue 0), then the inverse's tiles row by row (queue 1).
+    // Queue 0: the Cholesky's chain tiles (diagonal, first sub-diagonal) in order.  Queue 1: the other
+    // Cholesky tiles column by column plus the background pre-accumulation tasks.  Queue 2: the
+    // inverse's tiles row by row plus their pre-accumulation tasks.
+    //
+    // A Cholesky tile (i, c) with more than POTRF_LA + POTRF_MINP tile products is split: a background
+    // task listed right after column c - POTRF_LA - 1 (when its inputs exist) pre-accumulates tile
+    // columns [0, c - POTRF_LA); the tile's own task adds the last POTRF_LA and finalises.  Near the
+    // diagonal those own tasks sit on (or a few steps off) the dependency chain, so bounding their
+    // work keeps the chain from stalling on a late-claimed tile.
     std::vector<FactorTask> ft;
     const int nt = h->nt;
-    // A tile (i, c) with more than POTRF_LA + POTRF_MINP tile products is split: a background task
-    // listed right after column c - POTRF_LA - 1 (when its inputs exist) pre-accumulates tile columns
-    // [0, c - POTRF_LA); the tile's own task adds the last POTRF_LA and finalises.  Near the diagonal
-    // those own tasks sit on (or a few steps off) the dependency chain, so bounding their work keeps
-    // the chain from stalling on a late-claimed tile.
     const int POTRF_LA = 8, POTRF_MINP = 4;
     auto split = [&](int c) { return c > POTRF_LA + POTRF_MINP; };
+    for (int c = 0; c < nt; ++c)
+      for (int i = c; i < std::min(nt, c + 2); ++i) ft.push_back({TASK_POTRF, i, c, split(c) ? c - POTRF_LA : 0});
+    h->qbase[1] = (int)ft.size();
     for (int c = 0; c < nt; ++c) {
-      for (int i = c; i < nt; ++i) ft.push_back({TASK_POTRF, i, c, split(c) ? c - POTRF_LA : 0});
+      for (int i = c + 2; i < nt; ++i) ft.push_back({TASK_POTRF, i, c, split(c) ? c - POTRF_LA : 0});
       const int cc = c + POTRF_LA + 1;  // column whose tiles can now be pre-accumulated up to column c
       if (cc < nt && split(cc))
         for (int i = cc; i < nt; ++i) ft.push_back({TASK_POTRF_PART, i, cc, cc - POTRF_LA});
     }
-    h->n_potrf_tasks = (int)ft.size();
+    h->qbase[2] = (int)ft.size();
     // Inverse tiles row by row.  A tile with more than MAIN_K + MIN_PART tile products is split: a
     // helper task (listed as soon as its inputs exist, i.e. after row k-1) pre-accumulates tile
     // columns [J, k), the tile's own task adds the last MAIN_K and finalises.  This moves most of
@@ -425,6 +433,7 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
       for (auto& tk : after_row[r]) ft.push_back(tk);
     }
     h->n_ftasks = (int)ft.size();
+    h->qbase[3] = h->n_ftasks;
     CK(cudaMalloc(&h->ftasks, ft.size() * sizeof(FactorTask)));
     CK(cudaMemcpy(h->ftasks, ft.data(), ft.size() * sizeof(FactorTask), cudaMemcpyHostToDevice));
   }

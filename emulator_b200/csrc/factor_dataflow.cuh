@@ -50,11 +50,12 @@ struct FactorArgs {
   const double* X;        // [np][DP] padded training inputs
   const double* noise;    // [np]
   const KernelParams* kp;
-  const FactorTask* tasks;  // [n_potrf Cholesky tasks, column-major][n_trtri inverse tasks, row-major]
+  const FactorTask* tasks;  // three queues back to back: chain tiles | other Cholesky tasks | inverse tasks
   int ntasks;
-  int n_potrf;              // tasks [0, n_potrf) are Cholesky tiles, the rest inverse tiles
-  int n_potrf_ctas;         // CTAs [0, n_potrf_ctas) serve the Cholesky list, the others the inverse list
-  unsigned* counter;        // two task counters (zeroed before the launch)
+  int qbase[4];             // queue q holds tasks [qbase[q], qbase[q+1])
+  int n_sms;                // CTA b runs on SM slot b % n_sms (first wave, second wave)
+  int n_chain_sms;          // SM slots [0, n_chain_sms) are reserved for the chain queue
+  unsigned* counter;        // three task counters (zeroed before the launch)
   int* ready;             // [nt*nt] L tile flags (zeroed before the launch)
   int* xready;            // [nt*nt] X tile flags (zeroed before the launch)
   int* pready;            // [nt*nt] partial-sum flags of long inverse tiles (zeroed before the launch)
@@ -384,24 +385,24 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
 
   for (;;) {
     __syncthreads();  // previous task fully retired (smem reuse, s_task reuse)
-    // Two queues: Cholesky CTAs run ahead along the dependency chain exactly as if the inverse
-    // were not there; inverse CTAs (co-resident on the same SMs) use the cycles the chain leaves
-    // idle.  A CTA whose own queue is empty helps with the other one.
+    // Three queues.  (0) the Cholesky's chain tiles (diagonal + first sub-diagonal), served by the
+    // CTAs of a few SMs reserved for them so that the latency-bound finalisations never share an FP64
+    // pipe with bulk work; (1) all other Cholesky tasks, whose CTAs run ahead along the dependency
+    // chain exactly as if the inverse were not there; (2) the inverse's tasks, whose CTAs (co-resident
+    // with the queue-1 CTAs) use the cycles the chain leaves idle.  A CTA whose queue is empty helps
+    // the others.
     if (tid == 0) {
-      const bool chol = blockIdx.x < (unsigned)a.n_potrf_ctas;
-      const unsigned n0 = chol ? (unsigned)a.n_potrf : (unsigned)(a.ntasks - a.n_potrf);
-      const unsigned n1 = chol ? (unsigned)(a.ntasks - a.n_potrf) : (unsigned)a.n_potrf;
-      const unsigned base0 = chol ? 0u : (unsigned)a.n_potrf, base1 = chol ? (unsigned)a.n_potrf : 0u;
-      unsigned* c0 = a.counter + (chol ? 0 : 1);
-      unsigned* c1 = a.counter + (chol ? 1 : 0);
+      const int sm_slot = (int)(blockIdx.x % (unsigned)a.n_sms);
+      const int role = (sm_slot < a.n_chain_sms) ? 0 : ((blockIdx.x < (unsigned)a.n_sms) ? 1 : 2);
       unsigned tk0 = 0xffffffffu;
-      if (ld_flag(reinterpret_cast<const int*>(c0)) < (int)n0) {
-        const unsigned k = atomicAdd(c0, 1u);
-        if (k < n0) tk0 = base0 + k;
-      }
-      if (tk0 == 0xffffffffu) {
-        const unsigned k = atomicAdd(c1, 1u);
-        if (k < n1) tk0 = base1 + k;
+#pragma unroll 1
+      for (int attempt = 0; attempt < 3 && tk0 == 0xffffffffu; ++attempt) {
+        const int q = (role + attempt) % 3;
+        const unsigned qn = (unsigned)(a.qbase[q + 1] - a.qbase[q]);
+        if (ld_flag(reinterpret_cast<const int*>(a.counter + q)) < (int)qn) {
+          const unsigned k = atomicAdd(a.counter + q, 1u);
+          if (k < qn) tk0 = (unsigned)a.qbase[q] + k;
+        }
       }
       s_task = tk0;
     }
