@@ -8,6 +8,7 @@ one GPU, each owns its own device handle and stream.
 
 from __future__ import annotations
 
+from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, List, Optional
 
 import attr
@@ -22,6 +23,9 @@ class GaussianProcessEmulatorBins(BaseEmulator):
     kernel = attr.ib(default=None)
     mean_model = attr.ib(default=None)
     device: int = attr.ib(default=0)
+    #: independent per-bin fits run concurrently from this many host threads; every GP owns its
+    #: device handle and stream, and the C ABI calls release the GIL (results do not depend on it)
+    workers: int = attr.ib(default=8)
 
     n_bins: int = None
     bin_centers: List[float] = None
@@ -75,13 +79,22 @@ class GaussianProcessEmulatorBins(BaseEmulator):
         mine = dist.my_indices(self.n_bins)
         gps = [None] * self.n_bins
         fitted = np.zeros((self.n_bins, n_hyper))
-        for b in mine:
+        def fit_bin(b):
             values = self.bin_model_values[b]
             gp = build_gp(
                 self.kernel, self.mean_model, values["independent"], values["dependent"], values["dependent_errors"],
                 device=self.device,
             )
             optimise_gp(gp, values["dependent"])
+            return b, gp
+
+        if self.mean_model is not None or self.workers <= 1 or len(mine) <= 1:
+            # mean_model.train mutates the shared mean-model object: keep the reference's sequential order
+            results = [fit_bin(b) for b in mine]
+        else:
+            with ThreadPoolExecutor(max_workers=self.workers) as pool:
+                results = list(pool.map(fit_bin, mine))
+        for b, gp in results:
             gps[b] = gp
             fitted[b] = gp.get_parameter_vector()
         # collect every bin's optimum on every rank; bins fitted elsewhere get a GP at that optimum

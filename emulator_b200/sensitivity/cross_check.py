@@ -12,6 +12,7 @@ the one simulation removed and the caller's container is never mutated.
 
 from __future__ import annotations
 
+from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, Hashable, List, Optional
 
 import attr
@@ -34,6 +35,10 @@ class CrossCheck(object):
     mean_model = attr.ib(default=None)
     hide_progress: bool = attr.ib(default=True)
     device: int = attr.ib(default=0)
+    #: leave-one-out refits of this rank run concurrently from this many host threads (each refit
+    #: owns its device handle and stream; the Cholesky's dependency chain of one refit leaves SMs
+    #: idle that another refit's kernels use)
+    workers: int = attr.ib(default=2)
 
     model_specification: ModelSpecification = None
     model_parameters: ModelParameters = None
@@ -54,10 +59,18 @@ class CrossCheck(object):
         mine = dist.my_indices(count)
         fitted = np.zeros((count, n_hyper))
         emulators = {}
-        for i in mine:
+        def refit(i):
             uid = self.leave_out_order[i]
             emulator = GaussianProcessEmulator(kernel=self.kernel, mean_model=self.mean_model, device=self.device)
             emulator.fit_model(model_specification, model_parameters, _without(model_values, uid))
+            return i, uid, emulator
+
+        if self.kernel is None and self.mean_model is None and self.workers > 1 and len(mine) > 1:
+            with ThreadPoolExecutor(max_workers=self.workers) as pool:
+                done = list(pool.map(refit, mine))
+        else:  # shared kernel / mean-model objects are mutated by fit_model: keep it sequential
+            done = [refit(i) for i in mine]
+        for i, uid, emulator in done:
             fitted[i] = emulator.emulator.get_parameter_vector()
             emulators[uid] = emulator
         fitted = dist.all_gather_rows(fitted, mine, count)
