@@ -203,7 +203,7 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
       return 1;
     case OP_FACTOR_DF: {
       cudaMemsetAsync(h->counter, 0, 4 * sizeof(unsigned), st);
-      cudaMemsetAsync(h->ready, 0, ((size_t)4 * h->nt * h->nt + 256) * sizeof(int), st);  // ready, xready, pready, cready, sm_chain
+      cudaMemsetAsync(h->ready, 0, ((size_t)4 * h->nt * h->nt + 512) * sizeof(int), st);  // ready, xready, pready, cready, sm_chain, sm_arrival
       FactorArgs fa;
       fa.A = h->A; fa.W = h->W; fa.ld = np; fa.nt = h->nt; fa.n = h->n; fa.X = h->X; fa.noise = h->noise; fa.kp = h->kp;
       fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; for (int q = 0; q < 4; ++q) fa.qbase[q] = h->qbase[q]; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready; fa.pready = h->xready + (size_t)h->nt * h->nt; fa.cready = fa.pready + (size_t)h->nt * h->nt; fa.sm_chain = fa.cready + (size_t)h->nt * h->nt;
@@ -211,8 +211,8 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
       fa.trace = h->trace;
       // two CTAs per SM: the first wave (one per SM) serves the Cholesky queue, the second the inverse
       const int grid = std::min(2 * h->n_sms, h->n_ftasks);
-      fa.n_sms = h->n_sms;
       // at least one CTA always serves the chain queue, never so many that the other queues starve
+      fa.n_sms = h->n_sms;
       fa.n_chain_sms = std::max(1, std::min({6, h->nt / 8, grid / 4}));
       DP_SWITCH(h->dp, (factor_dataflow_kernel<DP><<<grid, 256, FactorSmem<DP>::BYTES, st>>>(fa)));
       return 1;
@@ -388,7 +388,7 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMemset(h->W, 0, mat));
   CK(cudaMemset(h->A, 0, mat));  // strictly-upper 64-blocks of diagonal 128-tiles must stay zero
   CK(cudaMalloc(&h->counter, 4 * sizeof(unsigned)));
-  CK(cudaMalloc(&h->ready, ((size_t)4 * h->nt * h->nt + 256) * sizeof(int)));
+  CK(cudaMalloc(&h->ready, ((size_t)4 * h->nt * h->nt + 512) * sizeof(int)));
   h->xready = h->ready + (size_t)h->nt * h->nt;
   CK(cudaMalloc(&h->abort_flag, sizeof(int)));
   CK(cudaMalloc(&h->rdiag, (size_t)np * sizeof(double)));
@@ -408,11 +408,14 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
     const int nt = h->nt;
     const int POTRF_LA = 8, POTRF_MINP = 4;
     auto split = [&](int c) { return c > POTRF_LA + POTRF_MINP; };
+    // The chain queue holds the band i - c <= CHAIN_BAND: tile (c + d, c) is needed d steps after the
+    // diagonal tile of its column, so the tiles next to the diagonal have almost no slack either.
+    const int CHAIN_BAND = 1;
     for (int c = 0; c < nt; ++c)
-      for (int i = c; i < std::min(nt, c + 2); ++i) ft.push_back({TASK_POTRF, i, c, split(c) ? c - POTRF_LA : 0});
+      for (int i = c; i < std::min(nt, c + CHAIN_BAND + 1); ++i) ft.push_back({TASK_POTRF, i, c, split(c) ? c - POTRF_LA : 0});
     h->qbase[1] = (int)ft.size();
     for (int c = 0; c < nt; ++c) {
-      for (int i = c + 2; i < nt; ++i) ft.push_back({TASK_POTRF, i, c, split(c) ? c - POTRF_LA : 0});
+      for (int i = c + CHAIN_BAND + 1; i < nt; ++i) ft.push_back({TASK_POTRF, i, c, split(c) ? c - POTRF_LA : 0});
       const int cc = c + POTRF_LA + 1;  // column whose tiles can now be pre-accumulated up to column c
       if (cc < nt && split(cc))
         for (int i = cc; i < nt; ++i) ft.push_back({TASK_POTRF_PART, i, cc, cc - POTRF_LA});
@@ -622,14 +625,14 @@ int eb200_gp_debug_alpha(eb200_gp* h, double* alpha_host) {
 int eb200_gp_debug_factor_trace(eb200_gp* h, const double* p_host, unsigned long long* out_host, int* tasks_out) {
   if (!h || !p_host || !out_host || !tasks_out) return fail("factor_trace: null argument");
   CK(cudaSetDevice(h->device));
-  CK(cudaMalloc(&h->trace, (size_t)h->n_ftasks * 6 * sizeof(unsigned long long)));
-  CK(cudaMemset(h->trace, 0, (size_t)h->n_ftasks * 6 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->trace, (size_t)h->n_ftasks * 8 * sizeof(unsigned long long)));
+  CK(cudaMemset(h->trace, 0, (size_t)h->n_ftasks * 8 * sizeof(unsigned long long)));
   memcpy(h->h_p, p_host, (h->d + 1) * sizeof(double));
   CK(cudaMemcpyAsync(h->p_dev, h->h_p, (h->d + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   int rc = enqueue_eval(h, h->stream, 0, 2, nullptr, nullptr);
   cudaError_t e = cudaStreamSynchronize(h->stream);
   if (!rc && e == cudaSuccess) {
-    e = cudaMemcpy(out_host, h->trace, (size_t)h->n_ftasks * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    e = cudaMemcpy(out_host, h->trace, (size_t)h->n_ftasks * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaMemcpy(tasks_out, h->ftasks, (size_t)h->n_ftasks * sizeof(FactorTask), cudaMemcpyDeviceToHost);
   }
   cudaFree(h->trace);

@@ -22,13 +22,14 @@
 // error code instead of a hang.
 #pragma once
 #include "kernels.cuh"
+#include "tile_ops.cuh"
 
 namespace eb {
 
 using CfgP = TileCfg<64, 64, 32, 16>;  // 256 threads: 2 x 4 warps, 16 accumulator doubles / thread
 constexpr int PSTAGES = 4;             // cp.async ring depth (two CTAs per SM share 227 KB)
 constexpr int PSTAGE_DOUBLES = 2 * 64 * (KC + 4);
-constexpr int PS = 65;                 // stride of the 64x64 finalisation buffers
+constexpr int PS = TPS;                // stride of the 64x64 finalisation buffers (tile_ops.cuh)
 constexpr int TS = 68;                 // stride of a parked accumulator used as a [k][n] operand
 
 // TASK_TRTRI_PART (r, J, k): helper that pre-accumulates sum_{K=J}^{k-1} L_rK X_KJ of a long inverse
@@ -53,8 +54,8 @@ struct FactorArgs {
   const FactorTask* tasks;  // three queues back to back: chain tiles | other Cholesky tasks | inverse tasks
   int ntasks;
   int qbase[4];             // queue q holds tasks [qbase[q], qbase[q+1])
-  int n_sms;                // CTA b runs on SM slot b % n_sms (first wave, second wave)
-  int n_chain_sms;          // SM slots [0, n_chain_sms) are reserved for the chain queue
+  int n_sms;                // CTAs are numbered in two waves of n_sms
+  int n_chain_sms;          // CTAs with (blockIdx % n_sms) < n_chain_sms serve the chain queue
   unsigned* counter;        // three task counters (zeroed before the launch)
   int* ready;             // [nt*nt] L tile flags (zeroed before the launch)
   int* xready;            // [nt*nt] X tile flags (zeroed before the launch)
@@ -65,7 +66,7 @@ struct FactorArgs {
   double* rdiag;          // [nt][64] reciprocal pivots 1 / L_jj, published with the diagonal tile
   int* info;
   int* abort_flag;        // watchdog: set when a wait exceeded its budget
-  unsigned long long* trace;  // optional [ntasks][6] globaltimer stamps (diagnostics), or nullptr
+  unsigned long long* trace;  // optional [ntasks][8]: 6 globaltimer stamps, SM id, CTA id (diagnostics), or nullptr
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -75,7 +76,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define EB_STAMP(slot)                                                                \
   do {                                                                                \
-    if (a.trace != nullptr && tid == 0) a.trace[(size_t)task * 6 + (slot)] = gtime(); \
+    if (a.trace != nullptr && tid == 0) a.trace[(size_t)task * 8 + (slot)] = gtime(); \
   } while (0)
 
 // Flags are polled with a relaxed gpu-scope load: an acquire load would make ptxas emit
@@ -239,110 +240,6 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
   cp_async_wait<0>();
 }
 
-// Finalisation layout: warp w owns columns 8w..8w+7 of a 64x64 tile, lane owns rows lane, lane+32.
-//
-// Right-looking Cholesky of the tile held in v (lower triangle) by 8-column panels; the owning
-// warp factorises its panel with shuffles only, the warps to its right apply it.  L goes to sL
-// (zero strict upper), reciprocal pivots to rd.
-__device__ __forceinline__ void tile_cholesky(double (&v)[2][8], double* sL, double* rd, int* info, int col0) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int p = 0; p < 8; ++p) {
-    if (warp == p) {
-      const int sj = p >> 2;       // row slot of this panel's pivot rows
-      const int ob = 8 * (p & 3);  // lane of the first pivot row
-      double dloc = sj ? v[1][0] : v[0][0];
-      double d = __shfl_sync(0xffffffffu, dloc, ob);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, col0 + 8 * p + c + 1);
-        const double rinv = rsqrt(d);
-        if (lane == ob + c) rd[8 * p + c] = rinv;
-        const double l0 = v[0][c] * rinv, l1 = v[1][c] * rinv;
-        v[0][c] = l0;
-        v[1][c] = l1;
-        const double lsel = sj ? l1 : l0;
-        if (c < 7) {
-          // next pivot, computed by its own lane (keeps the second shuffle off the chain)
-          const double nloc = fma(-lsel, lsel, sj ? v[1][c + 1] : v[0][c + 1]);
-          d = __shfl_sync(0xffffffffu, nloc, ob + c + 1);
-        }
-#pragma unroll
-        for (int c2 = c + 1; c2 < 8; ++c2) {
-          const double lk = __shfl_sync(0xffffffffu, lsel, ob + c2);
-          v[0][c2] = fma(-l0, lk, v[0][c2]);
-          v[1][c2] = fma(-l1, lk, v[1][c2]);
-        }
-      }
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int row = lane + 32 * sl, col = 8 * p + c;
-          sL[row * PS + col] = (row >= col) ? v[sl][c] : 0.0;
-        }
-    }
-    __syncthreads();
-    if (warp > p) {
-      double ar[2][8];
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) ar[sl][k] = sL[(lane + 32 * sl) * PS + 8 * p + k];
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const double b = sL[(8 * warp + c) * PS + 8 * p + k];
-          v[0][c] = fma(-ar[0][k], b, v[0][c]);
-          v[1][c] = fma(-ar[1][k], b, v[1][c]);
-        }
-    }
-  }
-}
-
-// Y = V L^-T for the tile held in v (rows independent), L in sL, reciprocal pivots in rd;
-// forward substitution by 8-column panels.  Result left in sOut ([64][PS]).
-__device__ __forceinline__ void tile_trsm(double (&v)[2][8], const double* sL, const double* rd, double* sOut) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int p = 0; p < 8; ++p) {
-    if (warp == p) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const double r = rd[8 * p + c];
-        const double x0 = v[0][c] * r, x1 = v[1][c] * r;
-        v[0][c] = x0;
-        v[1][c] = x1;
-#pragma unroll
-        for (int c2 = c + 1; c2 < 8; ++c2) {
-          const double lv = sL[(8 * p + c2) * PS + 8 * p + c];
-          v[0][c2] = fma(-x0, lv, v[0][c2]);
-          v[1][c2] = fma(-x1, lv, v[1][c2]);
-        }
-      }
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) sOut[(lane + 32 * sl) * PS + 8 * p + c] = v[sl][c];
-    }
-    __syncthreads();
-    if (warp > p) {
-      double ar[2][8];
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) ar[sl][k] = sOut[(lane + 32 * sl) * PS + 8 * p + k];
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const double b = sL[(8 * warp + c) * PS + 8 * p + k];
-          v[0][c] = fma(-ar[0][k], b, v[0][c]);
-          v[1][c] = fma(-ar[1][k], b, v[1][c]);
-        }
-    }
-  }
-}
-
 // Shared memory of one CTA (two CTAs per SM).  The finalisation buffers alias the cp.async
 // ring: they are only touched after the accumulation loop has drained it.
 template <int DP>
@@ -368,6 +265,8 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
   extern __shared__ __align__(16) double gsm[];
   using SM = FactorSmem<DP>;
   __shared__ unsigned s_task;
+  __shared__ int s_role;
+  __shared__ int s_pflags[16];  // per-panel flags of the two tile finalisers (epoch-valued, never reset)
   double* sC = gsm + SM::C_OFF;
   double* sL = gsm + SM::L_OFF;
   double* sT = gsm + SM::T_OFF;
@@ -382,6 +281,8 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
   const int wn0 = (warp % CfgP::WARPS_N) * CfgP::WN;
   const int g = lane >> 2, t = lane & 3;
   const int ld = a.ld, nt = a.nt;
+  if (tid < 16) s_pflags[tid] = 0;
+  if (tid == 0) s_role = -1;
 
   for (;;) {
     __syncthreads();  // previous task fully retired (smem reuse, s_task reuse)
@@ -392,8 +293,15 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     // with the queue-1 CTAs) use the cycles the chain leaves idle.  A CTA whose queue is empty helps
     // the others.
     if (tid == 0) {
-      const int sm_slot = (int)(blockIdx.x % (unsigned)a.n_sms);
-      const int role = (sm_slot < a.n_chain_sms) ? 0 : ((blockIdx.x < (unsigned)a.n_sms) ? 1 : 2);
+      if (s_role < 0) {
+        // A dozen CTAs serve the chain queue, the rest of the first wave the Cholesky queue, the
+        // second wave the inverse queue.  (Measured alternatives: reserving whole SMs for the chain by
+        // %smid -- 6 or 12 SMs, band of 1 or 3 sub-diagonals -- made its tile factorisations 25 %
+        // faster but lost more in look-ahead and bulk capacity: 307-314 vs 321 evals/s at N = 4096.)
+        const int slot = (int)(blockIdx.x % (unsigned)a.n_sms);
+        s_role = (slot < a.n_chain_sms) ? 0 : ((blockIdx.x < (unsigned)a.n_sms) ? 1 : 2);
+      }
+      const int role = s_role;
       unsigned tk0 = 0xffffffffu;
 #pragma unroll 1
       for (int attempt = 0; attempt < 3 && tk0 == 0xffffffffu; ++attempt) {
@@ -414,6 +322,10 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     const int i0 = ti * 64, j0 = tj * 64;
     bool ok = true;
     EB_STAMP(0);
+    if (a.trace != nullptr && tid == 0) {
+      a.trace[(size_t)task * 8 + 6] = smid();
+      a.trace[(size_t)task * 8 + 7] = blockIdx.x;
+    }
     double acc[CfgP::MI][CfgP::NI][2];
 
     if (tk.type == TASK_POTRF_PART) {
@@ -545,7 +457,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     // ==================================  Cholesky tile (i, j)  ==================================
     // Chain tiles raise their SM's priority flag only for the latency-bound finalisation (never
     // while they wait for a producer: a background task on the same SM may be that producer).
-    const bool chain_tile = (ti - tj) <= 1;
+    const bool chain_tile = (ti - tj) <= 1;  // the band served by the chain queue (CHAIN_BAND in eb200.cu)
     int* my_sm = a.sm_chain + smid();
     if (!chain_tile) yield_to_chain(my_sm);  // the exp()-heavy K generation competes for the FP64 pipe
     // stage the training inputs of the tile's rows / columns for the K_ij generation
@@ -635,7 +547,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
 
     if (ti == tj) {
       if (tid == 0) atomicAdd(my_sm, 1);
-      tile_cholesky(v, sL, rdiag, a.info, j0);
+      tile_cholesky(v, sL, rdiag, a.info, j0, s_pflags, (int)task + 1);
       for (int e = tid; e < 64 * 64; e += 256) {
         const int r = e >> 6, c = e & 63;
         At[(size_t)r * ld + c] = sL[r * PS + c];

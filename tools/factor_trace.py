@@ -14,11 +14,12 @@ p = orc.default_parameter_vector(d)
 gp.evaluate(p, True)
 nt = gp.padded_n // 64
 ntasks = gp._lib.eb200_gp_factor_tasks(gp.handle)
-out = np.zeros((ntasks, 6), dtype=np.uint64); tasks = np.zeros((ntasks, 4), dtype=np.int32)
+out = np.zeros((ntasks, 8), dtype=np.uint64); tasks = np.zeros((ntasks, 4), dtype=np.int32)
 for rep in range(2):
     _lib.check(gp._lib.eb200_gp_debug_factor_trace(gp.handle, _lib.as_double_ptr(p), out.ctypes.data_as(ctypes.POINTER(ctypes.c_ulonglong)),
                                                     tasks.ctypes.data_as(ctypes.POINTER(ctypes.c_int))), "trace")
-t = (out.astype(np.int64) - int(out[:, 0].min())) / 1e3  # us
+sm_of = out[:, 6].astype(np.int64); cta_of = out[:, 7].astype(np.int64)
+t = (out[:, :6].astype(np.int64) - int(out[:, 0].min())) / 1e3  # us
 print("ntasks", ntasks, "total us", t[:, 5].max())
 po = tasks[:, 0] == 0
 diag = {int(r[2]): k for k, r in enumerate(tasks) if r[0] == 0 and r[1] == r[2]}
@@ -41,6 +42,13 @@ late_s = np.array([t[sub[j], 2] - t[diag[j], 5] for j in range(nt - 1) if j in s
 print("sub C_done - diag published (positive = sub tile's own accumulation finished late) 10/50/90/max:", np.percentile(late_s, [10, 50, 90, 100]))
 print("cholesky finished at us", pub.max(), " mean diag-to-diag step us:", np.diff(pub).mean())
 dd = np.array([t[diag[j], 4] - t[diag[j], 2] for j in range(nt)]); print("diag factor+store us: mean", dd.mean())
+subk = [sub[j] for j in sorted(sub)]
+print("chain sub tiles: Ljj_seen->stored (trsm) 10/50/90:", np.percentile(t[subk, 4] - t[subk, 3], [10, 50, 90]), " publish:", np.median(t[subk, 5] - t[subk, 4]))
+dk = [diag[j] for j in sorted(diag)]
+print("chain diag tiles: C_done->stored (chol) 10/50/90:", np.percentile(t[dk, 4] - t[dk, 2], [10, 50, 90]), " publish:", np.median(t[dk, 5] - t[dk, 4]))
+second = {int(r[2]): k for k, r in enumerate(tasks) if r[0] == 0 and r[1] == r[2] + 2}
+lat2 = np.array([t[second[j], 5] - t[diag[j], 5] for j in second])
+print("second sub-diagonal tile published - diag published 10/50/90/max:", np.percentile(lat2, [10, 50, 90, 100]))
 off = po & (tasks[:, 1] != tasks[:, 2])
 print("trsm(load Ljj+subst+store) us mean", (t[off, 4] - t[off, 3]).mean())
 tr = ~po
@@ -48,3 +56,10 @@ if tr.any():
     print("trtri tasks:", tr.sum(), " accumulate us mean", (t[tr, 1] - t[tr, 0]).mean(), " wait Xrr us mean", (t[tr, 2] - t[tr, 1]).mean(),
           " finalize us mean", (t[tr, 4] - t[tr, 2]).mean(), " first start", t[tr, 0].min(), " last end", t[tr, 5].max())
 busy = (t[:, 5] - t[:, 0]).sum(); print("sum task time us", busy, "-> per-SM avg", busy / 148)
+
+chain = [k for k, r in enumerate(tasks) if r[0] == 0 and r[1] - r[2] <= 1]
+print("chain tasks ran on SMs", sorted(set(sm_of[chain].tolist())), "CTAs", sorted(set(cta_of[chain].tolist())))
+pairs = {}
+for k in range(ntasks): pairs.setdefault(int(cta_of[k]), set()).add(int(sm_of[k]))
+same = sum(1 for b in range(148) if b in pairs and (b + 148) in pairs and pairs[b] == pairs[b + 148])
+print("CTA b and b+148 on the same SM for", same, "of 148 pairs; distinct SMs used", len(set(sm_of.tolist())))
