@@ -275,6 +275,7 @@ int set_attrs() {
   bool& done = done_dev[dev & 63];
   if (done) return 0;
   CK((set_gemm_attr<Cfg128, KCONTIG, KCONTIG>()));
+  CK((set_gemm_attr<Cfg128W, KCONTIG, KCONTIG>()));
   CK(cudaFuncSetAttribute(var_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES));
 #define SET_POTRF(DPV)                                                                                       \
@@ -697,7 +698,7 @@ int eb200_bench_accumulate(int m, int n, int k, int b_mcontig, int grid, const d
 }
 
 int eb200_bench_gemm_nt(int m, int n, int k, const double* a_dev, const double* b_dev, double* c_dev, void* stream) {
-  if (m % 128 || n % 128 || k % KC) return fail("bench_gemm_nt: m, n must be multiples of 128 and k of 16");
+  if (m % 128 || n % 128 || k % (2 * KC)) return fail("bench_gemm_nt: m, n must be multiples of 128 and k of 32");
   if (set_attrs()) return 1;
   static TileTask* d_tasks = nullptr;
   static int cached_m = -1, cached_n = -1, cached_k = -1;

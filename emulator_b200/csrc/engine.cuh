@@ -18,7 +18,7 @@
 namespace eb {
 
 constexpr int KC = 16;      // k extent of one pipeline stage
-constexpr int STAGES = 3;   // cp.async ring depth (4 measured: no gain)
+constexpr int STAGES = 4;   // cp.async ring depth: two pairs of chunks
 
 enum Layout : int { KCONTIG = 0, MCONTIG = 1 };
 
@@ -55,6 +55,7 @@ struct TileCfg {
 };
 using Cfg128 = TileCfg<128, 128, 64, 32>;  // 256 threads, 64 accumulator doubles / thread
 using Cfg64 = TileCfg<64, 64, 32, 32>;     // 128 threads, 32 accumulator doubles / thread
+using Cfg128W = TileCfg<128, 128, 32, 32>; // 512 threads (4 warps per scheduler), 32 accumulator doubles / thread
 
 template <class Cfg, int LA, int LB>
 struct Engine {
@@ -104,39 +105,45 @@ struct Engine {
     const int wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
     const int g = lane >> 2, t = lane & 3;
 
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-      if (s < nk) load_stage(smem + s * STAGE_DOUBLES, Ag, lda, Bg, ldb, s, tid);
-      cp_async_commit();
+    // Two chunks ("a pair") per barrier, nk even.  While pair kt is in the math, pair kt+2 is in
+    // flight into the other two stages; it is issued right after the barrier that retires pair kt-2.
+    static_assert(STAGES == 4, "ring logic assumes two pairs");
+    if (nk > 0) {
+      load_stage(smem, Ag, lda, Bg, ldb, 0, tid);
+      load_stage(smem + STAGE_DOUBLES, Ag, lda, Bg, ldb, 1, tid);
     }
-    for (int kt = 0; kt < nk; ++kt) {
-      cp_async_wait<STAGES - 2>();
+    cp_async_commit();
+    for (int kt = 0; kt < nk; kt += 2) {
+      cp_async_wait<0>();
       __syncthreads();
-      {
-        int nxt = kt + STAGES - 1;
-        if (nxt < nk) load_stage(smem + (nxt % STAGES) * STAGE_DOUBLES, Ag, lda, Bg, ldb, nxt, tid);
-        cp_async_commit();
+      if (kt + 2 < nk) {
+        load_stage(smem + ((kt + 2) % STAGES) * STAGE_DOUBLES, Ag, lda, Bg, ldb, kt + 2, tid);
+        load_stage(smem + ((kt + 3) % STAGES) * STAGE_DOUBLES, Ag, lda, Bg, ldb, kt + 3, tid);
       }
+      cp_async_commit();
       if (active) {
-        const double* sA = smem + (kt % STAGES) * STAGE_DOUBLES;
-        const double* sB = sA + SA::DOUBLES;
 #pragma unroll
-        for (int kk = 0; kk < KC; kk += 4) {
-          double af[Cfg::MI], bf[Cfg::NI];
+        for (int h = 0; h < 2; ++h) {
+          const double* sA = smem + ((kt + h) % STAGES) * STAGE_DOUBLES;
+          const double* sB = sA + SA::DOUBLES;
 #pragma unroll
-          for (int mi = 0; mi < Cfg::MI; ++mi) {
-            int row = wm0 + mi * 8 + g;
-            af[mi] = (LA == KCONTIG) ? sA[row * SA::STRIDE + kk + t] : sA[(kk + t) * SA::STRIDE + row];
+          for (int kk = 0; kk < KC; kk += 4) {
+            double af[Cfg::MI], bf[Cfg::NI];
+#pragma unroll
+            for (int mi = 0; mi < Cfg::MI; ++mi) {
+              int row = wm0 + mi * 8 + g;
+              af[mi] = (LA == KCONTIG) ? sA[row * SA::STRIDE + kk + t] : sA[(kk + t) * SA::STRIDE + row];
+            }
+#pragma unroll
+            for (int ni = 0; ni < Cfg::NI; ++ni) {
+              int col = wn0 + ni * 8 + g;
+              bf[ni] = (LB == KCONTIG) ? sB[col * SB::STRIDE + kk + t] : sB[(kk + t) * SB::STRIDE + col];
+            }
+#pragma unroll
+            for (int mi = 0; mi < Cfg::MI; ++mi)
+#pragma unroll
+              for (int ni = 0; ni < Cfg::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
           }
-#pragma unroll
-          for (int ni = 0; ni < Cfg::NI; ++ni) {
-            int col = wn0 + ni * 8 + g;
-            bf[ni] = (LB == KCONTIG) ? sB[col * SB::STRIDE + kk + t] : sB[(kk + t) * SB::STRIDE + col];
-          }
-#pragma unroll
-          for (int mi = 0; mi < Cfg::MI; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < Cfg::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
         }
       }
     }
