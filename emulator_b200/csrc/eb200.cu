@@ -203,10 +203,10 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
       return 1;
     case OP_FACTOR_DF: {
       cudaMemsetAsync(h->counter, 0, 4 * sizeof(unsigned), st);
-      cudaMemsetAsync(h->ready, 0, ((size_t)4 * h->nt * h->nt + 512) * sizeof(int), st);  // ready, xready, pready, cready, sm_chain, sm_arrival
+      cudaMemsetAsync(h->ready, 0, ((size_t)4 * h->nt * h->nt + 8 * h->nt + 512) * sizeof(int), st);  // ready, xready, pready, cready, lready, sm_chain
       FactorArgs fa;
       fa.A = h->A; fa.W = h->W; fa.ld = np; fa.nt = h->nt; fa.n = h->n; fa.X = h->X; fa.noise = h->noise; fa.kp = h->kp;
-      fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; for (int q = 0; q < 4; ++q) fa.qbase[q] = h->qbase[q]; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready; fa.pready = h->xready + (size_t)h->nt * h->nt; fa.cready = fa.pready + (size_t)h->nt * h->nt; fa.sm_chain = fa.cready + (size_t)h->nt * h->nt;
+      fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; for (int q = 0; q < 4; ++q) fa.qbase[q] = h->qbase[q]; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready; fa.pready = h->xready + (size_t)h->nt * h->nt; fa.cready = fa.pready + (size_t)h->nt * h->nt; fa.lready = fa.cready + (size_t)h->nt * h->nt; fa.sm_chain = fa.lready + 8 * h->nt;
       fa.logdet_part = h->logdet_part; fa.rdiag = h->rdiag; fa.info = h->info; fa.abort_flag = h->abort_flag;
       fa.trace = h->trace;
       // two CTAs per SM: the first wave (one per SM) serves the Cholesky queue, the second the inverse
@@ -389,7 +389,7 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMemset(h->W, 0, mat));
   CK(cudaMemset(h->A, 0, mat));  // strictly-upper 64-blocks of diagonal 128-tiles must stay zero
   CK(cudaMalloc(&h->counter, 4 * sizeof(unsigned)));
-  CK(cudaMalloc(&h->ready, ((size_t)4 * h->nt * h->nt + 512) * sizeof(int)));
+  CK(cudaMalloc(&h->ready, ((size_t)4 * h->nt * h->nt + 8 * h->nt + 512) * sizeof(int)));
   h->xready = h->ready + (size_t)h->nt * h->nt;
   CK(cudaMalloc(&h->abort_flag, sizeof(int)));
   CK(cudaMalloc(&h->rdiag, (size_t)np * sizeof(double)));

@@ -61,6 +61,7 @@ struct FactorArgs {
   int* xready;            // [nt*nt] X tile flags (zeroed before the launch)
   int* pready;            // [nt*nt] partial-sum flags of long inverse tiles (zeroed before the launch)
   int* cready;            // [nt*nt] partial-sum flags of the Cholesky tiles (zeroed before the launch)
+  int* lready;            // [nt*8] per-panel flags of the diagonal tiles (zeroed before the launch)
   int* sm_chain;          // [256] per-SM count of resident CTAs working on a chain tile (zeroed before the launch)
   double* logdet_part;    // [nt]
   double* rdiag;          // [nt][64] reciprocal pivots 1 / L_jj, published with the diagonal tile
@@ -547,12 +548,9 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
 
     if (ti == tj) {
       if (tid == 0) atomicAdd(my_sm, 1);
-      tile_cholesky(v, sL, rdiag, a.info, j0, s_pflags, (int)task + 1);
-      for (int e = tid; e < 64 * 64; e += 256) {
-        const int r = e >> 6, c = e & 63;
-        At[(size_t)r * ld + c] = sL[r * PS + c];
-      }
-      if (tid < 64) a.rdiag[(size_t)tj * 64 + tid] = rdiag[tid];
+      // (the panels of L_jj and the reciprocal pivots are streamed to global memory as they are produced)
+      tile_cholesky(v, sL, rdiag, a.info, j0, s_pflags, (int)task + 1, At, ld, a.rdiag + (size_t)tj * 64,
+                    a.lready + (size_t)tj * 8);
       EB_STAMP(4);
       int all_ok = publish(a.ready + (size_t)ti * nt + tj, ok);
       if (tid == 0) atomicSub(my_sm, 1);
@@ -578,20 +576,17 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       all_ok &= publish(a.xready + (size_t)ti * nt + tj, ok);
       if (!all_ok) break;
     } else {
-      ok = wait_ready(a.ready + (size_t)tj * nt + tj, a.abort_flag) && ok;
+      // substitution against L_jj, panel by panel as the diagonal tile's owner streams them out
       if (!chain_tile) yield_to_chain(my_sm);
       if (chain_tile && tid == 0) atomicAdd(my_sm, 1);
       EB_STAMP(3);
-      const double* Lg = a.A + (size_t)j0 * ld + j0;
-      for (int e = tid; e < 64 * 32; e += 256) {
-        const int r = e >> 5, c = (e & 31) * 2;
-        const double2 val = __ldcg(reinterpret_cast<const double2*>(Lg + (size_t)r * ld + c));
-        sL[r * PS + c] = val.x;
-        sL[r * PS + c + 1] = val.y;
+      {
+        int* abort_flag = a.abort_flag;
+        ok = tile_trsm_streamed(v, sL, rdiag, sC, a.A + (size_t)j0 * ld + j0, ld, a.rdiag + (size_t)tj * 64,
+                                a.lready + (size_t)tj * 8,
+                                [abort_flag](const int* f) { return wait_ready(f, abort_flag); }) && ok;
       }
-      if (tid < 64) rdiag[tid] = __ldcg(a.rdiag + (size_t)tj * 64 + tid);
       __syncthreads();
-      tile_trsm(v, sL, rdiag, sC);
       for (int e = tid; e < 64 * 64; e += 256) {
         const int rr = e >> 6, c = e & 63;
         At[(size_t)rr * ld + c] = sC[rr * PS + c];

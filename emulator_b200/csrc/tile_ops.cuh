@@ -83,9 +83,43 @@ __device__ __forceinline__ void stand_back() { __nanosleep(400); }
 // (zero strict upper), reciprocal pivots in rd[64].  Returns (to every thread of the panel's warp)
 // nothing; a non-positive pivot is recorded in *info as 1-based global column.  flags: 8 ints in
 // shared memory; epoch: a value unique to this call.  Ends with a CTA barrier.
+//
+// Streaming: as soon as panel p is in shared memory, a warp that has nothing else to do (warp p-1,
+// already finished; warp 7 for panel 0) copies it -- 64 rows x 8 columns of L plus 8 reciprocal
+// pivots -- to global memory (Lg, ld; rd_g) and publishes the global flag gflags[p], so that the
+// tiles below the diagonal start their substitution against panel p while the chain is still
+// factorising panel p+1 (see tile_trsm_streamed).
+__device__ __forceinline__ void stream_panel(const double* sL, const double* rd, int p, double* Lg, int ld, double* rd_g,
+                                             int* gflags, int lane) {
+#pragma unroll
+  for (int sl = 0; sl < 2; ++sl) {
+    const int row = lane + 32 * sl;
+    const double* src = sL + row * TPS + 8 * p;
+    double* dst = Lg + (size_t)row * ld + 8 * p;
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+      double2 val;
+      val.x = src[c];
+      val.y = src[c + 1];
+      *reinterpret_cast<double2*>(dst + c) = val;
+    }
+  }
+  if (lane < 8) rd_g[8 * p + lane] = rd[8 * p + lane];
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(gflags + p), "r"(1) : "memory");
+  }
+}
+
 __device__ __forceinline__ void tile_cholesky(double (&v)[2][8], double* sL, double* rd, int* info, int col0,
-                                              volatile int* flags, int epoch) {
+                                              volatile int* flags, int epoch, double* Lg, int ld, double* rd_g,
+                                              int* gflags) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 7) {  // nothing to do until panel 0 exists: stream it out first
+    panel_wait(flags + 0, epoch);
+    stream_panel(sL, rd, 0, Lg, ld, rd_g, gflags, lane);
+  }
   // panels 0 .. warp-2: apply as they appear (this warp is not yet on the critical path)
   for (int p = 0; p + 1 < warp; ++p) {
     panel_wait(flags + p, epoch);
@@ -145,6 +179,10 @@ __device__ __forceinline__ void tile_cholesky(double (&v)[2][8], double* sL, dou
       }
     panel_signal(flags + p, epoch);
     if (bad && lane == 0) atomicCAS(info, 0, col0 + 8 * p + bad_col + 1);
+    if (warp < 7) {  // done with everything of its own: stream the next panel out when it appears
+      panel_wait(flags + warp + 1, epoch);
+      stream_panel(sL, rd, warp + 1, Lg, ld, rd_g, gflags, lane);
+    }
   }
   __syncthreads();
 }
@@ -192,6 +230,64 @@ __device__ __forceinline__ void tile_trsm(double (&v)[2][8], const double* sL, c
         }
     }
   }
+}
+
+// tile_trsm against a diagonal tile that is still being factorised by another CTA: panel p of L
+// (and its reciprocal pivots) is fetched from global memory as soon as its flag is published.
+// Lg/ld/rd_g/gflags describe the diagonal tile; returns false if the watchdog of the poll fired.
+template <class WaitFn>
+__device__ __forceinline__ bool tile_trsm_streamed(double (&v)[2][8], double* sL, double* rd, double* sOut, const double* Lg,
+                                                    int ld, const double* rd_g, const int* gflags, WaitFn wait_flag) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  bool ok = true;
+  for (int p = 0; p < 8; ++p) {
+    ok = wait_flag(gflags + p) && ok;
+    {
+      // 64 rows x 8 columns: thread t loads row t/4, columns 2*(t%4), +1
+      const int row = tid >> 2, c2 = (tid & 3) * 2;
+      const double2 val = __ldcg(reinterpret_cast<const double2*>(Lg + (size_t)row * ld + 8 * p + c2));
+      sL[row * TPS + 8 * p + c2] = val.x;
+      sL[row * TPS + 8 * p + c2 + 1] = val.y;
+      if (tid < 8) rd[8 * p + tid] = __ldcg(rd_g + 8 * p + tid);
+    }
+    __syncthreads();
+    if (warp == p) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const double r = rd[8 * p + c];
+        const double x0 = v[0][c] * r, x1 = v[1][c] * r;
+        v[0][c] = x0;
+        v[1][c] = x1;
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; ++c2) {
+          const double lv = sL[(8 * p + c2) * TPS + 8 * p + c];
+          v[0][c2] = fma(-x0, lv, v[0][c2]);
+          v[1][c2] = fma(-x1, lv, v[1][c2]);
+        }
+      }
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) sOut[(lane + 32 * sl) * TPS + 8 * p + c] = v[sl][c];
+    }
+    __syncthreads();
+    if (warp > p) {
+      double ar[2][8];
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ar[sl][k] = sOut[(lane + 32 * sl) * TPS + 8 * p + k];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const double b = sL[(8 * warp + c) * TPS + 8 * p + k];
+          v[0][c] = fma(-ar[0][k], b, v[0][c]);
+          v[1][c] = fma(-ar[1][k], b, v[1][c]);
+        }
+    }
+  }
+  return ok;
 }
 
 }  // namespace eb

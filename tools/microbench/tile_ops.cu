@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256, 2) bench(const double* tile, double* out,
   double* sOut = sm + 2 * 64 * PS + 64;
   __shared__ int info;
   __shared__ int flags[16];
+  int* gfl = reinterpret_cast<int*>(cyc + 4);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int e = tid; e < 4096; e += 256) sC[(e >> 6) * PS + (e & 63)] = tile[e];
   if (tid == 0) info = 0;
@@ -29,7 +30,7 @@ __global__ void __launch_bounds__(256, 2) bench(const double* tile, double* out,
       for (int c = 0; c < 8; ++c) v[sl][c] = sC[(lane + 32 * sl) * PS + 8 * warp + c];
     __syncthreads();
     long long t0 = clock64();
-    tile_cholesky(v, sL, rd, &info, 0, flags, ++epoch);
+    tile_cholesky(v, sL, rd, &info, 0, flags, ++epoch, out, 64, out + 4096 + 4096, gfl);
     long long t1 = clock64();
     t_chol += t1 - t0;
   }
@@ -53,7 +54,7 @@ int main() {
   for (int i = 0; i < 64; ++i) for (int j = 0; j < 64; ++j) g[i * 64 + j] = std::sin(0.37 * i + 0.11 * j * j);
   for (int i = 0; i < 64; ++i) for (int j = 0; j < 64; ++j) { double s = (i == j) ? 8.0 : 0.0; for (int k = 0; k < 64; ++k) s += g[i * 64 + k] * g[j * 64 + k] / 64.0; a[i * 64 + j] = s; }
   double *d_t, *d_o; long long* d_c;
-  cudaMalloc(&d_t, 4096 * 8); cudaMalloc(&d_o, 2 * 4096 * 8); cudaMalloc(&d_c, 3 * 8);
+  cudaMalloc(&d_t, 4096 * 8); cudaMalloc(&d_o, (2 * 4096 + 64) * 8); cudaMalloc(&d_c, 16 * 8); cudaMemset(d_c, 0, 16 * 8);
   cudaMemcpy(d_t, a.data(), 4096 * 8, cudaMemcpyHostToDevice);
   const int smem = (3 * 64 * PS + 128) * 8;
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
