@@ -121,7 +121,7 @@ __device__ __forceinline__ bool wait_ready(const int* flag, int* abort_flag) {
 __device__ __forceinline__ void yield_to_chain(const int* sm_flag) {
   if ((threadIdx.x & 31) == 0) {
     int spins = 0;
-    while (ld_flag(sm_flag) != 0 && ++spins < (1 << 14)) __nanosleep(200);
+    while (ld_flag(sm_flag) != 0 && ++spins < 256) __nanosleep(200);  // a chain finalisation lasts ~10 us; never wait much longer
   }
   __syncwarp();
 }
@@ -235,7 +235,7 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
     }
     if (busy != 0) {  // lane 0 only; the other lanes wait for it at the next barrier
       int spins = 0;
-      while (ld_flag(yield_to) != 0 && ++spins < (1 << 16)) __nanosleep(200);
+      while (ld_flag(yield_to) != 0 && ++spins < 256) __nanosleep(200);
     }
   }
   cp_async_wait<0>();
@@ -577,8 +577,9 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       if (!all_ok) break;
     } else {
       // substitution against L_jj, panel by panel as the diagonal tile's owner streams them out
+      // (no priority flag here: this phase waits for panels of another CTA, and a flag held across a
+      //  wait can starve the very producer it waits for)
       if (!chain_tile) yield_to_chain(my_sm);
-      if (chain_tile && tid == 0) atomicAdd(my_sm, 1);
       EB_STAMP(3);
       {
         int* abort_flag = a.abort_flag;
@@ -593,7 +594,6 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       }
       EB_STAMP(4);
       const int all_ok = publish(a.ready + (size_t)ti * nt + tj, ok);
-      if (chain_tile && tid == 0) atomicSub(my_sm, 1);
       EB_STAMP(5);
       if (!all_ok) break;
     }
