@@ -275,7 +275,6 @@ int set_attrs() {
   bool& done = done_dev[dev & 63];
   if (done) return 0;
   CK((set_gemm_attr<Cfg128, KCONTIG, KCONTIG>()));
-  CK((set_gemm_attr<Cfg128W, KCONTIG, KCONTIG>()));
   CK(cudaFuncSetAttribute(var_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES));
 #define SET_POTRF(DPV)                                                                                       \

@@ -1,8 +1,10 @@
 // fp64 tile-GEMM engine for sm_100a: cp.async (LDGSTS) multi-stage pipeline feeding
 // DMMA.8x8x4 (mma.sync.m8n8k4.f64) -- the only FP64 tensor shape Blackwell has (tcgen05 has
-// no f64 kind).  Every dense contraction of the GP hot path (Cholesky trailing updates,
-// triangular inverse, K^-1 = X^T X, predictive variance) is expressed as tile tasks that
-// run through this one main loop.
+// no f64 kind).  The dense contractions of the GP hot path are tile tasks on this engine:
+// K^-1 = X^T X and the predictive variance through `Engine::mainloop` (128x128 tiles), the
+// Cholesky / triangular-inverse tile products through its flag-synchronised 64x64 sibling in
+// factor_dataflow.cuh.  (Measured: a 16-warp variant of the 128x128 tile and a deeper ring
+// bring nothing; two chunks per barrier do: 31.4 -> 32.2 TFLOP/s, 89 % of cuBLAS DGEMM.)
 //
 // Operand layouts (both live in row-major global matrices):
 //   KCONTIG : element (row, k) at base[row*ld + k]      ("N" for A, "T" for B)
@@ -54,8 +56,6 @@ struct TileCfg {
   static constexpr int MI = WM / 8, NI = WN / 8;
 };
 using Cfg128 = TileCfg<128, 128, 64, 32>;  // 256 threads, 64 accumulator doubles / thread
-using Cfg64 = TileCfg<64, 64, 32, 32>;     // 128 threads, 32 accumulator doubles / thread
-using Cfg128W = TileCfg<128, 128, 32, 32>; // 512 threads (4 warps per scheduler), 32 accumulator doubles / thread
 
 template <class Cfg, int LA, int LB>
 struct Engine {

@@ -1,10 +1,9 @@
 // CUDA kernels of the GP hot path (fp64, sm_100a).  See DESIGN.md for the data layout.
 //
-// Matrix storage: one row-major (Np x Np) fp64 buffer `A` per GP handle, Np = N rounded up to a
+// Matrix storage: two row-major (Np x Np) fp64 buffers per GP handle, Np = N rounded up to a
 // multiple of 128; rows/columns >= N carry the identity so every kernel works on whole tiles.
-// The lower triangle goes K -> L (Cholesky factor) -> X = L^-1 in place; a second buffer `W`
-// of the same shape is scratch (T = L21*X11 during the triangular inverse, K* during
-// prediction).
+// `A` receives the Cholesky factor L (factor_dataflow.cuh) and is reused as K* scratch by
+// prediction; `W` receives X = L^-1, which the gradient and the predictive variance consume.
 #pragma once
 #include <math.h>
 #include "engine.cuh"
@@ -102,14 +101,6 @@ __global__ void __launch_bounds__(256) kbuild_kernel(const int2* __restrict__ ti
       A[(size_t)gi * ld + gj] = v;
     }
   }
-}
-
-// Copy the 64x64 diagonal inverses into the diagonal of A (start of the triangular inverse).
-__global__ void __launch_bounds__(256) place_dinv_kernel(double* __restrict__ A, int ld,
-                                                          const double* __restrict__ dinv) {
-  const int t = blockIdx.x;
-  double* At = A + (size_t)t * TB * ld + (size_t)t * TB;
-  for (int e = threadIdx.x; e < TB * TB; e += 256) At[(size_t)(e >> 6) * ld + (e & 63)] = dinv[(size_t)t * TB * TB + e];
 }
 
 // ---------------------------------------------------------------------------------------
