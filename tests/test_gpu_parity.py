@@ -252,3 +252,49 @@ def test_device_pointer_entry_points_with_torch_memory():
     assert relmax(mu.cpu().numpy(), ref_mu) <= TOL
     assert np.max(np.abs(var.cpu().numpy() - ref_var)) <= TOL * orc.amplitude(ps[-1], d)
     gp.close()
+
+
+def test_repeated_evaluations_are_bit_identical():
+    """The dataflow kernel's task interleaving varies from launch to launch; the arithmetic must not
+    (fixed accumulation order per tile, ordered final reductions, no floating-point atomics)."""
+    for n, d, reps in ((1000, 3, 60), (4096, 9, 12)):
+        x, y, diag = problem(n, d, seed=17)
+        gp = device_problem(x, diag, y)
+        ps = synthetic.perturbed_parameter_vectors(d, count=2, seed=5, scale=0.3)
+        first = [gp.evaluate(p, True) for p in ps]
+        t = x[:64] + 0.01
+        gp.evaluate(ps[1], True)
+        mu0, var0 = gp.predict(t, True)
+        for _ in range(reps):
+            for p, ref in zip(ps, first):
+                got = gp.evaluate(p, True)
+                assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and got[2] == 0
+        gp.evaluate(ps[1], True)
+        mu1, var1 = gp.predict(t, True)
+        assert np.array_equal(mu0, mu1) and np.array_equal(var0, var1)
+        gp.close()
+
+
+def test_concurrent_handles_from_threads_agree_with_sequential():
+    """Several handles driven from host threads at once (what the per-bin and leave-one-out drivers do)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    problems = [problem(700 + 100 * i, 4, seed=30 + i) for i in range(6)]
+    p = orc.default_parameter_vector(4) + 0.1
+    sequential = []
+    for x, y, diag in problems:
+        gp = device_problem(x, diag, y)
+        sequential.append(gp.evaluate(p, True))
+        gp.close()
+
+    def work(args):
+        x, y, diag = args
+        gp = device_problem(x, diag, y)
+        out = [gp.evaluate(p, True) for _ in range(5)][-1]
+        gp.close()
+        return out
+
+    with ThreadPoolExecutor(max_workers=6) as pool:
+        threaded = list(pool.map(work, problems))
+    for a, b in zip(sequential, threaded):
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and b[2] == 0
