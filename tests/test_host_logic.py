@@ -226,3 +226,34 @@ def test_containers_validate_and_roundtrip(tmp_path):
     assert pback[0]["p0"] == pytest.approx(params[0]["p0"])
     closest, _ = params.find_closest_model(params[2], 1)
     assert closest == [2]
+
+
+def test_cross_check_bins_builds_and_scores(oracle_backend):
+    """Reference test_cross_check_bins.py only builds; the broken post-processing there
+    (cross_check_bins.py:142-148, :224-229) is implemented to its evident intent here."""
+    spec, params, values = synthetic.make_model(2, 7, 4, seed=77)
+    cc = CrossCheckBins()
+    cc.build_emulators(spec, params, values)
+    assert list(cc.cross_emulators.keys()) == list(values.keys())
+    assert all(e.n_bins == 4 for e in cc.cross_emulators.values())
+    total, per_model = cc.get_mean_squared()
+    assert np.isfinite(total) and set(per_model) == set(values.keys())
+    with pytest.raises(AttributeError):
+        CrossCheckBins().get_mean_squared()
+
+
+def test_ensemble_sampler_recovers_a_gaussian():
+    from emulator_b200.emulators.ensemble import EnsembleSampler
+
+    mean, sigma = np.array([1.0, -2.0]), np.array([0.5, 2.0])
+    sampler = EnsembleSampler(20, 2, lambda p: -0.5 * np.sum(((p - mean) / sigma) ** 2), seed=3)
+    p0 = mean + 0.1 * np.random.default_rng(0).standard_normal((20, 2))
+    p0, _, _ = sampler.run_mcmc(p0, 300)
+    sampler.run_mcmc(p0, 700)
+    chain = sampler.get_chain()
+    assert chain.shape == (1000, 20, 2)
+    flat = sampler.get_chain(flat=True, discard=300)
+    assert np.allclose(flat.mean(axis=0), mean, atol=0.25)
+    assert np.allclose(flat.std(axis=0), sigma, rtol=0.25)
+    with pytest.raises(ValueError):
+        EnsembleSampler(7, 2, lambda p: 0.0)
