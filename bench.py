@@ -91,9 +91,21 @@ class ClockSampler(threading.Thread):
         }
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
+
+
 def cpu_reference_evals(x, y, noise, ps, evals, warm=1):
     """George-faithful oracle on the host cores: returns (evals/s, seconds per eval list)."""
     from oracle import gp_oracle
+
+    use_all_host_threads()
 
     times = []
     for i in range(warm + evals):
