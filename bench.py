@@ -31,6 +31,11 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core,
+# and BLAS reads the variable when numpy is imported.
+if os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -91,21 +96,9 @@ class ClockSampler(threading.Thread):
         }
 
 
-def use_all_host_threads():
-    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
-    try:
-        from threadpoolctl import threadpool_limits
-
-        threadpool_limits(limits=os.cpu_count())
-    except Exception:
-        pass
-
-
 def cpu_reference_evals(x, y, noise, ps, evals, warm=1):
     """George-faithful oracle on the host cores: returns (evals/s, seconds per eval list)."""
     from oracle import gp_oracle
-
-    use_all_host_threads()
 
     times = []
     for i in range(warm + evals):
