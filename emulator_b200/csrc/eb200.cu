@@ -92,6 +92,9 @@ struct eb200_gp {
   int2* ktiles = nullptr;
   FactorTask* ftasks = nullptr;  // dataflow task list: Cholesky tasks, then inverse tasks
   int n_ftasks = 0, qbase[4] = {0, 0, 0, 0};
+  FactorTask* ftasks_v = nullptr;  // value-only list: Cholesky tiles + the residual row
+  int n_ftasks_v = 0;
+  int qbase_v[4] = {0, 0, 0, 0};
   unsigned* counter = nullptr;
   int* ready = nullptr;
   int* xready = nullptr;
@@ -101,8 +104,8 @@ struct eb200_gp {
   int n_sms = 148;
   int n_ktiles = 0, n_lauum = 0, lauum_full_off = 0, lauum_full_cnt = 0;
   std::vector<Op> ops;
-  cudaGraphExec_t g_grad = nullptr, g_lml = nullptr;
-  int launches_grad = 0, launches_lml = 0;
+  cudaGraphExec_t g_grad = nullptr, g_lml = nullptr, g_val = nullptr;
+  int launches_grad = 0, launches_lml = 0, launches_val = 0;
   bool factor_valid = false;
   // prediction scratch
   double *T_dev = nullptr, *mu_dev = nullptr, *var_dev = nullptr, *rowss = nullptr, *T_in = nullptr;
@@ -192,7 +195,8 @@ void build_program(eb200_gp* h, std::vector<TileTask>& tasks) {
 }
 
 // Enqueue one op.  Returns number of kernel launches issued.
-int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double* kinv_out) {
+int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int mode, double* kinv_out) {
+  const int want_grad = mode == EB200_EVAL_GRAD;
   const int np = h->np;
   switch (op.kind) {
     case OP_PREP:
@@ -202,15 +206,21 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
       DP_SWITCH(h->dp, (kbuild_kernel<DP><<<h->n_ktiles, 256, 0, st>>>(h->ktiles, h->X, h->noise, h->kp, h->n, np, h->A)));
       return 1;
     case OP_FACTOR_DF: {
+      const bool vo = mode == EB200_EVAL_VALUE_ONLY;
+      const size_t nf = (size_t)(h->nt + 1) * h->nt;  // flags per array (tile row nt: the residual row)
       cudaMemsetAsync(h->counter, 0, 4 * sizeof(unsigned), st);
-      cudaMemsetAsync(h->ready, 0, ((size_t)4 * h->nt * h->nt + 8 * h->nt + 512) * sizeof(int), st);  // ready, xready, pready, cready, lready, sm_chain
+      cudaMemsetAsync(h->ready, 0, (4 * nf + 8 * h->nt + 512) * sizeof(int), st);  // ready, xready, pready, cready, lready, sm_chain
       FactorArgs fa;
       fa.A = h->A; fa.W = h->W; fa.ld = np; fa.nt = h->nt; fa.n = h->n; fa.X = h->X; fa.noise = h->noise; fa.kp = h->kp;
-      fa.tasks = h->ftasks; fa.ntasks = h->n_ftasks; for (int q = 0; q < 4; ++q) fa.qbase[q] = h->qbase[q]; fa.counter = h->counter; fa.ready = h->ready; fa.xready = h->xready; fa.pready = h->xready + (size_t)h->nt * h->nt; fa.cready = fa.pready + (size_t)h->nt * h->nt; fa.lready = fa.cready + (size_t)h->nt * h->nt; fa.sm_chain = fa.lready + 8 * h->nt;
+      fa.value_only = vo ? 1 : 0; fa.r = h->r;
+      fa.tasks = vo ? h->ftasks_v : h->ftasks; fa.ntasks = vo ? h->n_ftasks_v : h->n_ftasks;
+      for (int q = 0; q < 4; ++q) fa.qbase[q] = vo ? h->qbase_v[q] : h->qbase[q];
+      fa.counter = h->counter; fa.ready = h->ready; fa.xready = fa.ready + nf; fa.pready = fa.xready + nf;
+      fa.cready = fa.pready + nf; fa.lready = fa.cready + nf; fa.sm_chain = fa.lready + 8 * h->nt;
       fa.logdet_part = h->logdet_part; fa.rdiag = h->rdiag; fa.info = h->info; fa.abort_flag = h->abort_flag;
       fa.trace = h->trace;
       // two CTAs per SM: the first wave (one per SM) serves the Cholesky queue, the second the inverse
-      const int grid = std::min(2 * h->n_sms, h->n_ftasks);
+      const int grid = std::min(2 * h->n_sms, fa.ntasks);
       // at least one CTA always serves the chain queue, never so many that the other queues starve
       fa.n_sms = h->n_sms;
       fa.n_chain_sms = std::max(1, std::min({6, h->nt / 8, grid / 4}));
@@ -234,32 +244,34 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int want_grad, double*
       return 1;
     }
     case OP_FINALIZE:
-      finalize_kernel<<<1, 256, 0, st>>>(h->logdet_part, h->nt, h->z, h->n, h->trace_partial, h->n_lauum, h->dp, h->d,
+      // value-only: z = L^-1 r is the residual row of the factorised matrix
+      finalize_kernel<<<1, 256, 0, st>>>(h->logdet_part, h->nt, mode == EB200_EVAL_VALUE_ONLY ? h->A + (size_t)np * np : h->z, h->n, h->trace_partial, h->n_lauum, h->dp, h->d,
                                          want_grad, h->info, h->abort_flag, h->out_dev);
       return 1;
   }
   return 0;
 }
 
-int enqueue_eval(eb200_gp* h, cudaStream_t st, int want_grad, int max_stage, double* kinv_out, int* launches) {
+int enqueue_eval(eb200_gp* h, cudaStream_t st, int mode, int max_stage, double* kinv_out, int* launches) {
   int cnt = 0;
   CK(cudaMemsetAsync(h->info, 0, sizeof(int), st));
   CK(cudaMemsetAsync(h->abort_flag, 0, sizeof(int), st));
   for (const Op& op : h->ops) {
     if (op.stage > max_stage) continue;
-    if (op.grad_only && !want_grad) continue;
+    if (op.grad_only && mode != EB200_EVAL_GRAD) continue;
     if (op.debug_only && max_stage != 1) continue;
-    cnt += launch_op(h, op, st, want_grad, kinv_out);
+    if (mode == EB200_EVAL_VALUE_ONLY && op.stage == 3) continue;  // no inverse, no alpha
+    cnt += launch_op(h, op, st, mode, kinv_out);
   }
   CK(cudaGetLastError());
   if (launches) *launches = cnt;
   return 0;
 }
 
-int capture_graph(eb200_gp* h, int want_grad, cudaGraphExec_t* exec, int* launches) {
+int capture_graph(eb200_gp* h, int mode, cudaGraphExec_t* exec, int* launches) {
   cudaGraph_t graph;
   CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-  int rc = enqueue_eval(h, h->stream, want_grad, 99, nullptr, launches);
+  int rc = enqueue_eval(h, h->stream, mode, 99, nullptr, launches);
   cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
   if (rc) return rc;
   CK(e);
@@ -360,7 +372,8 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   const int np = h->np, dp = h->dp;
   const size_t mat = (size_t)np * np * sizeof(double);
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CK(cudaMalloc(&h->A, mat));
+  const size_t mat_a = mat + (size_t)TB * np * sizeof(double);  // + the residual tile row of value-only evaluations
+  CK(cudaMalloc(&h->A, mat_a));
   CK(cudaMalloc(&h->W, mat));
   CK(cudaMalloc(&h->X, (size_t)np * dp * sizeof(double)));
   CK(cudaMalloc(&h->noise, np * sizeof(double)));
@@ -386,10 +399,9 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMemset(h->z, 0, np * sizeof(double)));
   CK(cudaMemset(h->alpha, 0, np * sizeof(double)));
   CK(cudaMemset(h->W, 0, mat));
-  CK(cudaMemset(h->A, 0, mat));  // strictly-upper 64-blocks of diagonal 128-tiles must stay zero
+  CK(cudaMemset(h->A, 0, mat_a));  // strictly-upper 64-blocks of diagonal 128-tiles must stay zero
   CK(cudaMalloc(&h->counter, 4 * sizeof(unsigned)));
-  CK(cudaMalloc(&h->ready, ((size_t)4 * h->nt * h->nt + 8 * h->nt + 512) * sizeof(int)));
-  h->xready = h->ready + (size_t)h->nt * h->nt;
+  CK(cudaMalloc(&h->ready, ((size_t)4 * (h->nt + 1) * h->nt + 8 * h->nt + 512) * sizeof(int)));
   CK(cudaMalloc(&h->abort_flag, sizeof(int)));
   CK(cudaMalloc(&h->rdiag, (size_t)np * sizeof(double)));
   CK(cudaMemset(h->abort_flag, 0, sizeof(int)));
@@ -439,6 +451,22 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
     h->qbase[3] = h->n_ftasks;
     CK(cudaMalloc(&h->ftasks, ft.size() * sizeof(FactorTask)));
     CK(cudaMemcpy(h->ftasks, ft.data(), ft.size() * sizeof(FactorTask), cudaMemcpyHostToDevice));
+    // Value-only list (likelihood without gradient, e.g. ensemble sampling): the Cholesky tasks of
+    // queues 0 and 1 with one more tile row, nt, that carries the residual (factor_dataflow.cuh), and
+    // no inverse.
+    std::vector<FactorTask> fv(ft.begin(), ft.begin() + h->qbase[1]);
+    h->qbase_v[1] = (int)fv.size();
+    for (int c = 0; c < nt; ++c) {
+      // (the residual row's tile is never a chain-queue tile, also where it falls inside the band)
+      for (int i = std::min(c + CHAIN_BAND + 1, nt); i <= nt; ++i) fv.push_back({TASK_POTRF, i, c, split(c) ? c - POTRF_LA : 0});
+      const int cc = c + POTRF_LA + 1;
+      if (cc < nt && split(cc))
+        for (int i = cc; i <= nt; ++i) fv.push_back({TASK_POTRF_PART, i, cc, cc - POTRF_LA});
+    }
+    h->n_ftasks_v = (int)fv.size();
+    h->qbase_v[2] = h->qbase_v[3] = h->n_ftasks_v;
+    CK(cudaMalloc(&h->ftasks_v, fv.size() * sizeof(FactorTask)));
+    CK(cudaMemcpy(h->ftasks_v, fv.data(), fv.size() * sizeof(FactorTask), cudaMemcpyHostToDevice));
   }
 
   // inputs, padded
@@ -468,8 +496,9 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
     CK(cudaMemcpy(h->tasks, tasks.data(), tasks.size() * sizeof(TileTask), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&h->trace_partial, (size_t)std::max(1, h->n_lauum) * (dp + 1) * sizeof(double)));
   }
-  if (capture_graph(h, 1, &h->g_grad, &h->launches_grad)) return 1;
-  if (capture_graph(h, 0, &h->g_lml, &h->launches_lml)) return 1;
+  if (capture_graph(h, EB200_EVAL_GRAD, &h->g_grad, &h->launches_grad)) return 1;
+  if (capture_graph(h, EB200_EVAL_LML, &h->g_lml, &h->launches_lml)) return 1;
+  if (capture_graph(h, EB200_EVAL_VALUE_ONLY, &h->g_val, &h->launches_val)) return 1;
   *out = h;
   return 0;
 }
@@ -480,9 +509,10 @@ int eb200_gp_destroy(eb200_gp* h) {
   cudaStreamSynchronize(h->stream);
   if (h->g_grad) cudaGraphExecDestroy(h->g_grad);
   if (h->g_lml) cudaGraphExecDestroy(h->g_lml);
+  if (h->g_val) cudaGraphExecDestroy(h->g_val);
   void* dev[] = {h->A, h->W, h->X, h->noise, h->r, h->z, h->alpha, h->logdet_part, h->tpartial,
                  h->trace_partial, h->p_dev, h->out_dev, h->kp, h->info, h->tasks, h->ktiles, h->T_dev, h->T_in,
-                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ftasks, h->counter, h->ready, h->abort_flag, h->rdiag};
+                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ftasks, h->ftasks_v, h->counter, h->ready, h->abort_flag, h->rdiag};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (h->h_p) cudaFreeHost(h->h_p);
@@ -496,8 +526,9 @@ int eb200_gp_destroy(eb200_gp* h) {
 int eb200_gp_n(const eb200_gp* h) { return h ? h->n : -1; }
 int eb200_gp_dim(const eb200_gp* h) { return h ? h->d : -1; }
 int eb200_gp_padded_n(const eb200_gp* h) { return h ? h->np : -1; }
-int eb200_gp_eval_launches(const eb200_gp* h, int want_grad) {
-  return h ? (want_grad ? h->launches_grad : h->launches_lml) : -1;
+int eb200_gp_eval_launches(const eb200_gp* h, int mode) {
+  if (!h) return -1;
+  return mode == EB200_EVAL_GRAD ? h->launches_grad : (mode == EB200_EVAL_VALUE_ONLY ? h->launches_val : h->launches_lml);
 }
 
 int eb200_gp_set_residual_host(eb200_gp* h, const double* r_host) {
@@ -520,38 +551,44 @@ int eb200_gp_set_residual_device(eb200_gp* h, const double* r_dev, void* stream)
   return 0;
 }
 
-int eb200_gp_eval_device(eb200_gp* h, const double* p_dev, int want_grad, double* result_dev, void* stream) {
+static cudaGraphExec_t eval_graph(eb200_gp* h, int mode) {
+  return mode == EB200_EVAL_GRAD ? h->g_grad : (mode == EB200_EVAL_VALUE_ONLY ? h->g_val : h->g_lml);
+}
+
+int eb200_gp_eval_device(eb200_gp* h, const double* p_dev, int mode, double* result_dev, void* stream) {
   if (!h || !p_dev) return fail("eval: null argument");
+  if (mode < 0 || mode > 2) return fail("eval: mode must be EB200_EVAL_LML, EB200_EVAL_GRAD or EB200_EVAL_VALUE_ONLY");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   CK(cudaMemcpyAsync(h->p_dev, p_dev, (h->d + 1) * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  CK(cudaGraphLaunch(want_grad ? h->g_grad : h->g_lml, st));
+  CK(cudaGraphLaunch(eval_graph(h, mode), st));
   if (result_dev)
     CK(cudaMemcpyAsync(result_dev, h->out_dev, EB200_RESULT_LEN(h->d) * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  h->factor_valid = true;
+  h->factor_valid = mode != EB200_EVAL_VALUE_ONLY;  // a value-only evaluation leaves no L^-1 / alpha behind
   return 0;
 }
 
-int eb200_gp_eval_host(eb200_gp* h, const double* p_host, int want_grad, double* result_host) {
+int eb200_gp_eval_host(eb200_gp* h, const double* p_host, int mode, double* result_host) {
   if (!h || !p_host || !result_host) return fail("eval: null argument");
+  if (mode < 0 || mode > 2) return fail("eval: mode must be EB200_EVAL_LML, EB200_EVAL_GRAD or EB200_EVAL_VALUE_ONLY");
   CK(cudaSetDevice(h->device));
   const int len = EB200_RESULT_LEN(h->d);
   memcpy(h->h_p, p_host, (h->d + 1) * sizeof(double));
   CK(cudaMemcpyAsync(h->p_dev, h->h_p, (h->d + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaGraphLaunch(want_grad ? h->g_grad : h->g_lml, h->stream));
+  CK(cudaGraphLaunch(eval_graph(h, mode), h->stream));
   CK(cudaMemcpyAsync(h->h_out, h->out_dev, len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   memcpy(result_host, h->h_out, len * sizeof(double));
-  if (!want_grad)
+  if (mode != EB200_EVAL_GRAD)
     for (int i = 0; i <= h->d; ++i) result_host[1 + i] = 0.0;
-  h->factor_valid = true;
+  h->factor_valid = mode != EB200_EVAL_VALUE_ONLY;
   return 0;
 }
 
 int eb200_gp_predict_device(eb200_gp* h, int m, const double* t_dev, int want_var, double* mu_dev, double* var_dev,
                             void* stream) {
   if (!h || !t_dev || !mu_dev || (want_var && !var_dev)) return fail("predict: null argument");
-  if (!h->factor_valid) return fail("predict: no factorisation resident (call eval first)");
+  if (!h->factor_valid) return fail("predict: no factorisation resident (evaluate with EB200_EVAL_LML or EB200_EVAL_GRAD first)");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   for (int q0 = 0; q0 < m; q0 += h->np) {
@@ -565,7 +602,7 @@ int eb200_gp_predict_device(eb200_gp* h, int m, const double* t_dev, int want_va
 
 int eb200_gp_predict_host(eb200_gp* h, int m, const double* t_host, int want_var, double* mu_host, double* var_host) {
   if (!h || !t_host || !mu_host || (want_var && !var_host)) return fail("predict: null argument");
-  if (!h->factor_valid) return fail("predict: no factorisation resident (call eval first)");
+  if (!h->factor_valid) return fail("predict: no factorisation resident (evaluate with EB200_EVAL_LML or EB200_EVAL_GRAD first)");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   const int d = h->d;

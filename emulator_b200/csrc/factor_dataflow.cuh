@@ -48,6 +48,8 @@ struct FactorArgs {
   double* A;   // K -> L (lower triangle)
   double* W;   // X = L^-1 (lower triangle)
   int ld, nt, n;
+  int value_only;         // 1: Cholesky only, plus the residual carried as tile row nt (see TASK_POTRF); no inverse
+  const double* r;        // [np] residual (value_only)
   const double* X;        // [np][DP] padded training inputs
   const double* noise;    // [np]
   const KernelParams* kp;
@@ -57,10 +59,11 @@ struct FactorArgs {
   int n_sms;                // CTAs are numbered in two waves of n_sms
   int n_chain_sms;          // CTAs with (blockIdx % n_sms) < n_chain_sms serve the chain queue
   unsigned* counter;        // three task counters (zeroed before the launch)
-  int* ready;             // [nt*nt] L tile flags (zeroed before the launch)
-  int* xready;            // [nt*nt] X tile flags (zeroed before the launch)
-  int* pready;            // [nt*nt] partial-sum flags of long inverse tiles (zeroed before the launch)
-  int* cready;            // [nt*nt] partial-sum flags of the Cholesky tiles (zeroed before the launch)
+  // flag arrays are [(nt+1)*nt], indexed tile_row * nt + tile_col (row nt: the residual row of value_only)
+  int* ready;             // L tile flags (zeroed before the launch)
+  int* xready;            // X tile flags (zeroed before the launch)
+  int* pready;            // partial-sum flags of long inverse tiles (zeroed before the launch)
+  int* cready;            // partial-sum flags of the Cholesky tiles (zeroed before the launch)
   int* lready;            // [nt*8] per-panel flags of the diagonal tiles (zeroed before the launch)
   int* sm_chain;          // [256] per-SM count of resident CTAs working on a chain tile (zeroed before the launch)
   double* logdet_part;    // [nt]
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
         // %smid -- 6 or 12 SMs, band of 1 or 3 sub-diagonals -- made its tile factorisations 25 %
         // faster but lost more in look-ahead and bulk capacity: 307-314 vs 321 evals/s at N = 4096.)
         const int slot = (int)(blockIdx.x % (unsigned)a.n_sms);
-        s_role = (slot < a.n_chain_sms) ? 0 : ((blockIdx.x < (unsigned)a.n_sms) ? 1 : 2);
+        s_role = (slot < a.n_chain_sms) ? 0 : ((blockIdx.x < (unsigned)a.n_sms || a.value_only) ? 1 : 2);
       }
       const int role = s_role;
       unsigned tk0 = 0xffffffffu;
@@ -458,9 +461,21 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     // ==================================  Cholesky tile (i, j)  ==================================
     // Chain tiles raise their SM's priority flag only for the latency-bound finalisation (never
     // while they wait for a producer: a background task on the same SM may be that producer).
-    const bool chain_tile = (ti - tj) <= 1;  // the band served by the chain queue (CHAIN_BAND in eb200.cu)
+    const bool chain_tile = (ti - tj) <= 1 && ti < nt;  // the band served by the chain queue (CHAIN_BAND in eb200.cu)
     int* my_sm = a.sm_chain + smid();
     if (!chain_tile) yield_to_chain(my_sm);  // the exp()-heavy K generation competes for the FP64 pipe
+    if (ti == nt) {
+      // Residual row (value-only evaluations): the residual rides along as row 0 of an extra tile
+      // row of the matrix being factorised, [K r; r^T .] = [L 0; z^T .][L 0; z^T .]^T, so the same tile
+      // pipeline that produces L_ij leaves z = L^-1 r in row nt*64 of A.  acc = -r_j in row 0.
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+        for (int c = 0; c < CfgP::NI * 2; ++c) {
+          const int lr = wm0 + mi * 8 + g, gj = j0 + wn0 + (c >> 1) * 8 + 2 * t + (c & 1);
+          acc[mi][c >> 1][c & 1] = (lr == 0) ? -a.r[gj] : 0.0;
+        }
+    } else {
     // stage the training inputs of the tile's rows / columns for the K_ij generation
     for (int e = tid; e < 64 * DP; e += 256) {
       int r = e / DP, m = e % DP;
@@ -509,6 +524,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
           acc[mi][c >> 1][c & 1] = -kv;
         }
       }
+    }
     }
     EB_STAMP(1);
     const int kbeg = tk.k;  // > 0: tile columns [0, kbeg) were pre-accumulated by a TASK_POTRF_PART
@@ -566,6 +582,10 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
         double sum = 0.0;
         for (int j = 0; j < 64; ++j) sum += colbuf[j];
         a.logdet_part[tj] = -sum;  // sum_j log L_jj = -sum_j log(1 / L_jj)
+      }
+      if (a.value_only) {
+        if (!all_ok) break;
+        continue;
       }
       tile_trsm(v, sL, rdiag, sC);  // sC = I L^-T = (L^-1)^T
       double* Wt = a.W + (size_t)i0 * ld + j0;

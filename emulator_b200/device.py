@@ -13,6 +13,18 @@ import numpy as np
 from . import _lib
 
 
+# evaluation modes of eb200_gp_eval_* (include/emulator_b200.h)
+EVAL_LML, EVAL_GRAD, EVAL_VALUE_ONLY = 0, 1, 2
+
+
+def _mode(want_grad, value_only) -> int:
+    if value_only:
+        if want_grad:
+            raise ValueError("a value-only evaluation has no gradient")
+        return EVAL_VALUE_ONLY
+    return EVAL_GRAD if want_grad else EVAL_LML
+
+
 class DeviceProblem:
     """One GP problem resident on one GPU."""
 
@@ -63,14 +75,17 @@ class DeviceProblem:
             raise ValueError("residual must be [n]")
         _lib.check(self._lib.eb200_gp_set_residual_host(self._h, _lib.as_double_ptr(r)), "set_residual")
 
-    def evaluate(self, p: np.ndarray, want_grad: bool = True):
-        """Returns (lml, grad[P], info, logdet, quad) at hyperparameters p."""
+    def evaluate(self, p: np.ndarray, want_grad: bool = True, value_only: bool = False):
+        """Returns (lml, grad[P], info, logdet, quad) at hyperparameters p.
+
+        ``value_only`` evaluates the likelihood through the Cholesky factor alone (a third of the
+        flops); it leaves no prediction state (L^-1, alpha) on the device."""
         p = np.ascontiguousarray(p, dtype=np.float64)
         if p.shape != (self.d + 1,):
             raise ValueError(f"parameter vector must have {self.d + 1} entries")
         out = self._result
         _lib.check(
-            self._lib.eb200_gp_eval_host(self._h, _lib.as_double_ptr(p), int(bool(want_grad)), _lib.as_double_ptr(out)),
+            self._lib.eb200_gp_eval_host(self._h, _lib.as_double_ptr(p), _mode(want_grad, value_only), _lib.as_double_ptr(out)),
             "eb200_gp_eval_host",
         )
         d = self.d
@@ -93,9 +108,9 @@ class DeviceProblem:
         return (mu, var) if want_var else mu
 
     # -- device-pointer variants (inputs already in HBM; asynchronous) ----------------------------
-    def evaluate_device(self, p_ptr: int, want_grad: bool, result_ptr: int, stream: int = 0):
+    def evaluate_device(self, p_ptr: int, want_grad: bool, result_ptr: int, stream: int = 0, value_only: bool = False):
         _lib.check(
-            self._lib.eb200_gp_eval_device(self._h, c_void_p(p_ptr), int(bool(want_grad)), c_void_p(result_ptr), c_void_p(stream)),
+            self._lib.eb200_gp_eval_device(self._h, c_void_p(p_ptr), _mode(want_grad, value_only), c_void_p(result_ptr), c_void_p(stream)),
             "eb200_gp_eval_device",
         )
 
@@ -113,8 +128,8 @@ class DeviceProblem:
     def synchronize(self):
         _lib.check(self._lib.eb200_gp_synchronize(self._h), "synchronize")
 
-    def launches_per_eval(self, want_grad: bool = True) -> int:
-        return self._lib.eb200_gp_eval_launches(self._h, int(bool(want_grad)))
+    def launches_per_eval(self, want_grad: bool = True, value_only: bool = False) -> int:
+        return self._lib.eb200_gp_eval_launches(self._h, _mode(want_grad, value_only))
 
     def profile_stages(self, p: np.ndarray, reps: int = 3) -> np.ndarray:
         """Device milliseconds per stage [params, factorisation (K + Cholesky + inverse), alpha, kinv+traces, finalize]."""

@@ -63,7 +63,8 @@ class GP:
             self.mean = ConstantModel(float(mean))
         self.device = device
         #: evaluate the gradient together with every likelihood value (what BFGS wants);
-        #: the ensemble sampler switches this off (value-only evaluations).
+        #: the ensemble sampler switches this off: its evaluations then go through the Cholesky
+        #: factor alone (EB200_EVAL_VALUE_ONLY, a third of the flops).
         self.eager_gradient = True
         self._problem = None
         self._x = None
@@ -143,14 +144,15 @@ class GP:
         r = np.ascontiguousarray(self._check_dimensions(y) - self._call_mean(self._x), dtype=np.float64)
         self._set_residual(r)
 
-    def _evaluate(self, want_grad: bool):
+    def _evaluate(self, want_grad: bool, value_only: bool = False):
         p = np.ascontiguousarray(self.get_parameter_vector(), dtype=np.float64)
         key = p.tobytes()
         if self._cache_key == key and (self._cache[1] is not None or not want_grad):
             return self._cache
-        lml, grad, info, _logdet, _quad = self._problem.evaluate(p, want_grad)
+        lml, grad, info, _logdet, _quad = self._problem.evaluate(p, want_grad, value_only=value_only)
         self.n_device_evaluations += 1
-        self._device_p = key
+        # a value-only evaluation (Cholesky factor alone) leaves no prediction state behind
+        self._device_p = None if value_only else key
         self._cache_key = key
         self._cache = (lml, grad if want_grad else None, info)
         if info != 0:
@@ -161,7 +163,7 @@ class GP:
     def log_likelihood(self, y, quiet=False):
         self._residual(y)
         try:
-            lml, _, _ = self._evaluate(want_grad=self.eager_gradient)
+            lml, _, _ = self._evaluate(want_grad=self.eager_gradient, value_only=not self.eager_gradient)
         except np.linalg.LinAlgError:
             if quiet:
                 return -np.inf

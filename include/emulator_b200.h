@@ -53,14 +53,23 @@ int eb200_gp_set_residual_device(eb200_gp* gp, const double* r_dev, void* stream
 
 /* Replaces the pair gp.set_parameter_vector(p); gp.log_likelihood(y) /
  * gp.grad_log_likelihood(y)  (gaussian_process.py:208-214 and the three sibling emulators):
- * rebuilds K at p, factorises, and returns the log marginal likelihood and (want_grad != 0)
- * its gradient with respect to p in one pass.  result has EB200_RESULT_LEN(d) entries. */
-int eb200_gp_eval_host(eb200_gp* gp, const double* p_host, int want_grad, double* result_host);
-int eb200_gp_eval_device(eb200_gp* gp, const double* p_dev, int want_grad, double* result_dev, void* stream);
+ * rebuilds K at p, factorises, and returns the log marginal likelihood and (EB200_EVAL_GRAD)
+ * its gradient with respect to p in one pass.  result has EB200_RESULT_LEN(d) entries.
+ *   EB200_EVAL_LML         value; L^-1 and alpha stay resident for eb200_gp_predict_*
+ *   EB200_EVAL_GRAD        value + gradient; L^-1 and alpha stay resident
+ *   EB200_EVAL_VALUE_ONLY  value only through the Cholesky factor alone (a third of the flops):
+ *                          the evaluation the ensemble sampler makes per walker
+ *                          (gaussian_process_mcmc.py:240-265); leaves NO prediction state */
+#define EB200_EVAL_LML 0
+#define EB200_EVAL_GRAD 1
+#define EB200_EVAL_VALUE_ONLY 2
+int eb200_gp_eval_host(eb200_gp* gp, const double* p_host, int mode, double* result_host);
+int eb200_gp_eval_device(eb200_gp* gp, const double* p_dev, int mode, double* result_dev, void* stream);
 
 /* Replaces gp.predict(y, t, return_cov=False, return_var=bool)  (gaussian_process.py:285-287,
  * :344-346; gaussian_process_bins.py:354-359, :452-457).  Requires a preceding eval at the
- * hyperparameters to predict with (the factor and alpha stay resident).  mean-model values
+ * hyperparameters to predict with in mode EB200_EVAL_LML or EB200_EVAL_GRAD (L^-1 and alpha stay
+ * resident).  mean-model values
  * are added by the host.  t is [m][d]; mu and var are [m]; var may be NULL if !want_var. */
 int eb200_gp_predict_host(eb200_gp* gp, int m, const double* t_host, int want_var, double* mu_host,
                           double* var_host);
@@ -79,7 +88,7 @@ int eb200_gp_padded_n(const eb200_gp* gp);
 int eb200_gp_debug_matrix(eb200_gp* gp, int which, double* out_host);
 int eb200_gp_debug_alpha(eb200_gp* gp, double* alpha_host);
 /* number of kernel launches issued by one eval (graph nodes) */
-int eb200_gp_eval_launches(const eb200_gp* gp, int want_grad);
+int eb200_gp_eval_launches(const eb200_gp* gp, int mode);
 
 /* Per-task globaltimer stamps (ns) of the dataflow factorisation kernel: out[task][8] =
  * {claimed, K generated / panels accumulated, C formed / diagonal inverse visible, diagonal

@@ -56,6 +56,12 @@ def test_lml_and_gradient_match_oracle(n, d):
         assert np.max(np.abs(grad - ref_grad)) <= TOL * np.max(np.abs(ref_grad))
         lml_only, _, info2, _, _ = gp.evaluate(p, False)
         assert info2 == 0 and lml_only == lml  # same kernels, deterministic
+        # value-only mode: Cholesky factor alone, the residual carried as an extra matrix row
+        lml_v, grad_v, info3, logdet_v, quad_v = gp.evaluate(p, False, value_only=True)
+        assert info3 == 0 and np.all(grad_v == 0.0)
+        assert logdet_v == logdet  # same Cholesky tiles
+        assert abs(quad_v - ref_quad) <= TOL * abs(ref_quad)
+        assert abs(lml_v - ref_lml) <= TOL * abs(ref_lml)
     gp.close()
 
 
@@ -88,6 +94,37 @@ def test_prediction_requires_factorisation_and_follows_latest_parameters():
     mu2 = gp.predict(x[:9] + 0.01, False)
     assert relmax(mu1, orc.predict(p1, x, diag, y, x[:9] + 0.01, False)) <= TOL
     assert relmax(mu2, orc.predict(p2, x, diag, y, x[:9] + 0.01, False)) <= TOL
+    gp.close()
+
+
+def test_value_only_evaluation_leaves_no_prediction_state():
+    x, y, diag = problem(200, 3)
+    gp = device_problem(x, diag, y)
+    p = orc.default_parameter_vector(3) + 0.1
+    gp.evaluate(p, True)
+    mu = gp.predict(x[:5] + 0.02, False)
+    lml_v, _, info, _, _ = gp.evaluate(p + 0.3, False, value_only=True)
+    assert info == 0 and abs(lml_v - orc.lml_and_grad(p + 0.3, x, diag, y)[0]) <= TOL * abs(lml_v)
+    with pytest.raises(RuntimeError):
+        gp.predict(x[:5] + 0.02, False)  # L^-1 / alpha were not produced at p + 0.3
+    with pytest.raises(ValueError):
+        gp.evaluate(p, True, value_only=True)
+    gp.evaluate(p, False)
+    assert np.array_equal(gp.predict(x[:5] + 0.02, False), mu)
+    assert gp.launches_per_eval(False, value_only=True) == 3  # parameters, factorisation, reduction
+    # a new residual is picked up by the residual row
+    gp.set_residual(2.0 * y)
+    _, _, _, _, quad2 = gp.evaluate(p, False, value_only=True)
+    assert abs(quad2 - 4.0 * orc.lml_and_grad(p, x, diag, y)[3]) <= 4 * TOL * abs(quad2)
+    gp.close()
+
+
+def test_value_only_not_positive_definite_reports_info():
+    x = np.zeros((40, 2))
+    x[:, 0] = np.repeat(np.arange(20), 2) * 0.05
+    gp = device_problem(x, np.zeros(40), np.ones(40))
+    _, _, info, _, _ = gp.evaluate(np.array([5.0, 3.0, 3.0]), False, value_only=True)
+    assert info > 0
     gp.close()
 
 
@@ -181,6 +218,8 @@ def test_full_size_c2_against_oracle_and_properties():
         assert info == 0
         assert abs(lml - ref[0]) <= TOL * abs(ref[0])
         assert np.max(np.abs(grad - ref[1])) <= TOL * np.max(np.abs(ref[1]))
+        value_only = gp.evaluate(p, False, value_only=True)
+        assert value_only[2] == 0 and abs(value_only[0] - ref[0]) <= TOL * abs(ref[0])
     # size-independent properties
     p = ps[0]
     base = gp.evaluate(p, True)
