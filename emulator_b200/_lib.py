@@ -52,6 +52,8 @@ SIGNATURES = {
     "eb200_gp_eval_launches": (c_int, [c_void_p, c_int]),
     "eb200_gp_debug_factor_trace": (c_int, [c_void_p, _dp, POINTER(ctypes.c_ulonglong), POINTER(c_int)]),
     "eb200_gp_factor_tasks": (c_int, [c_void_p]),
+    "eb200_gp_debug_value_trace": (c_int, [c_void_p, _dp, POINTER(ctypes.c_ulonglong), POINTER(c_int)]),
+    "eb200_gp_value_tasks": (c_int, [c_void_p]),
     "eb200_gp_profile_stages": (c_int, [c_void_p, _dp, c_int, POINTER(ctypes.c_float)]),
     "eb200_bench_accumulate": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "eb200_bench_gemm_nt": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -423,8 +423,10 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
     // The chain queue holds the band i - c <= CHAIN_BAND: tile (c + d, c) is needed d steps after the
     // diagonal tile of its column, so the tiles next to the diagonal have almost no slack either.
     const int CHAIN_BAND = 1;
-    for (int c = 0; c < nt; ++c)
+    for (int c = 0; c < nt; ++c) {
       for (int i = c; i < std::min(nt, c + CHAIN_BAND + 1); ++i) ft.push_back({TASK_POTRF, i, c, split(c) ? c - POTRF_LA : 0});
+      ft.push_back({TASK_XDIAG, c, c, 0});
+    }
     h->qbase[1] = (int)ft.size();
     for (int c = 0; c < nt; ++c) {
       for (int i = c + CHAIN_BAND + 1; i < nt; ++i) ft.push_back({TASK_POTRF, i, c, split(c) ? c - POTRF_LA : 0});
@@ -659,18 +661,20 @@ int eb200_gp_debug_alpha(eb200_gp* h, double* alpha_host) {
   return 0;
 }
 
-int eb200_gp_debug_factor_trace(eb200_gp* h, const double* p_host, unsigned long long* out_host, int* tasks_out) {
+static int factor_trace_impl(eb200_gp* h, const double* p_host, int mode, unsigned long long* out_host, int* tasks_out) {
   if (!h || !p_host || !out_host || !tasks_out) return fail("factor_trace: null argument");
   CK(cudaSetDevice(h->device));
-  CK(cudaMalloc(&h->trace, (size_t)h->n_ftasks * 8 * sizeof(unsigned long long)));
-  CK(cudaMemset(h->trace, 0, (size_t)h->n_ftasks * 8 * sizeof(unsigned long long)));
+  const bool vo = mode == EB200_EVAL_VALUE_ONLY;
+  const int ntasks = vo ? h->n_ftasks_v : h->n_ftasks;
+  CK(cudaMalloc(&h->trace, (size_t)ntasks * 8 * sizeof(unsigned long long)));
+  CK(cudaMemset(h->trace, 0, (size_t)ntasks * 8 * sizeof(unsigned long long)));
   memcpy(h->h_p, p_host, (h->d + 1) * sizeof(double));
   CK(cudaMemcpyAsync(h->p_dev, h->h_p, (h->d + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  int rc = enqueue_eval(h, h->stream, 0, 2, nullptr, nullptr);
+  int rc = enqueue_eval(h, h->stream, mode, 2, nullptr, nullptr);
   cudaError_t e = cudaStreamSynchronize(h->stream);
   if (!rc && e == cudaSuccess) {
-    e = cudaMemcpy(out_host, h->trace, (size_t)h->n_ftasks * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    cudaMemcpy(tasks_out, h->ftasks, (size_t)h->n_ftasks * sizeof(FactorTask), cudaMemcpyDeviceToHost);
+    e = cudaMemcpy(out_host, h->trace, (size_t)ntasks * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(tasks_out, vo ? h->ftasks_v : h->ftasks, (size_t)ntasks * sizeof(FactorTask), cudaMemcpyDeviceToHost);
   }
   cudaFree(h->trace);
   h->trace = nullptr;
@@ -679,7 +683,14 @@ int eb200_gp_debug_factor_trace(eb200_gp* h, const double* p_host, unsigned long
   CK(e);
   return 0;
 }
+int eb200_gp_debug_factor_trace(eb200_gp* h, const double* p_host, unsigned long long* out_host, int* tasks_out) {
+  return factor_trace_impl(h, p_host, EB200_EVAL_LML, out_host, tasks_out);
+}
+int eb200_gp_debug_value_trace(eb200_gp* h, const double* p_host, unsigned long long* out_host, int* tasks_out) {
+  return factor_trace_impl(h, p_host, EB200_EVAL_VALUE_ONLY, out_host, tasks_out);
+}
 int eb200_gp_factor_tasks(const eb200_gp* h) { return h ? h->n_ftasks : -1; }
+int eb200_gp_value_tasks(const eb200_gp* h) { return h ? h->n_ftasks_v : -1; }
 
 int eb200_gp_profile_stages(eb200_gp* h, const double* p_host, int reps, float* ms_out) {
   if (!h || !p_host || !ms_out || reps < 1) return fail("profile_stages: bad argument");

@@ -8,9 +8,10 @@
 //
 //   POTRF (i, j), column-major:  C = K_ij - sum_{k<j} L_ik L_jk^T   (K_ij generated in-kernel:
 //        the kernel-matrix build is fused into the factorisation), then
-//          i == j : L_jj = chol(C) (8-column panels, warp-synchronous), published; afterwards,
-//                   off the critical path, X_jj = L_jj^-1 is written to the inverse's diagonal
-//          i  > j : L_ij = C L_jj^-T (panelled forward substitution against L_jj)
+//          i == j : L_jj = chol(C) (8-column panels, warp-synchronous), streamed out panel by panel;
+//                   X_jj = L_jj^-1 is the separate task XDIAG that follows those panels
+//          i  > j : L_ij = C L_jj^-T: panelled forward substitution against the streamed panels of L_jj
+//                   for the chain tile i = j + 1, one tile product with X_jj for all others
 //   TRTRI (r, J), J < r, listed one block column behind the Cholesky front:
 //          X_rJ = -X_rr * sum_{K=J}^{r-1} L_rK X_KJ                  (X goes to a second matrix)
 //
@@ -31,6 +32,7 @@ constexpr int PSTAGES = 4;             // cp.async ring depth (two CTAs per SM s
 constexpr int PSTAGE_DOUBLES = 2 * 64 * (KC + 4);
 constexpr int PS = TPS;                // stride of the 64x64 finalisation buffers (tile_ops.cuh)
 constexpr int TS = 68;                 // stride of a parked accumulator used as a [k][n] operand
+constexpr int NEAR_BAND = 2;           // tiles (j+1..j+NEAR_BAND, j) cannot wait for X_jj: they follow L_jj's panels
 
 // TASK_TRTRI_PART (r, J, k): helper that pre-accumulates sum_{K=J}^{k-1} L_rK X_KJ of a long inverse
 // tile into the (unused) mirrored upper tile of X, so that the tile's own task (k = first tile column
@@ -39,7 +41,10 @@ constexpr int TS = 68;                 // stride of a parked accumulator used as
 // pre-accumulated by a background task listed several block columns ahead and parked in the tile's
 // own (not yet published) storage, so that the tile's task -- which near the diagonal sits on or
 // next to the dependency chain -- has a bounded amount of work however late it is claimed.
-enum FactorTaskType : int { TASK_POTRF = 0, TASK_TRTRI = 1, TASK_TRTRI_PART = 2, TASK_POTRF_PART = 3 };
+// TASK_XDIAG (j, j): X_jj = L_jj^-1 by substitution on the identity, following the panels of L_jj as the
+// diagonal tile's owner streams them out, so that the inverse is published a few microseconds after
+// the factor itself: every tile of column j beyond the near band finishes with one product by X_jj^T.
+enum FactorTaskType : int { TASK_POTRF = 0, TASK_TRTRI = 1, TASK_TRTRI_PART = 2, TASK_POTRF_PART = 3, TASK_XDIAG = 4 };
 struct FactorTask {
   int type, i, j, k;
 };
@@ -332,6 +337,35 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     }
     double acc[CfgP::MI][CfgP::NI][2];
 
+    if (tk.type == TASK_XDIAG) {
+      double v[2][8];
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[sl][c] = (lane + 32 * sl == 8 * warp + c) ? 1.0 : 0.0;
+      int* my_sm = a.sm_chain + smid();
+      ok = wait_ready(a.lready + (size_t)tj * 8, a.abort_flag) && ok;  // from here on the wait is bounded
+      if (tid == 0) atomicAdd(my_sm, 1);
+      EB_STAMP(3);
+      {
+        int* abort_flag = a.abort_flag;
+        ok = tile_trsm_streamed(v, sL, rdiag, sC, a.A + (size_t)j0 * ld + j0, ld, a.rdiag + (size_t)tj * 64,
+                                a.lready + (size_t)tj * 8,
+                                [abort_flag](const int* f) { return wait_ready(f, abort_flag); }) && ok;
+      }
+      __syncthreads();
+      double* Wt = a.W + (size_t)j0 * ld + j0;  // sC = I L^-T = (L^-1)^T
+      for (int e = tid; e < 64 * 64; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        Wt[(size_t)r * ld + c] = (c <= r) ? sC[c * PS + r] : 0.0;
+      }
+      EB_STAMP(4);
+      const int x_ok = publish(a.xready + (size_t)tj * nt + tj, ok);
+      if (tid == 0) atomicSub(my_sm, 1);
+      EB_STAMP(5);
+      if (!x_ok) break;
+      continue;
+    }
     if (tk.type == TASK_POTRF_PART) {
       // ============  background pre-accumulation of a chain tile: sum_{c<k} L_ic L_jc^T  ============
 #pragma unroll
@@ -544,8 +578,71 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     // left-looking accumulation over the finished panels: acc += sum_k L_ik L_jk^T
     accumulate_flagged<KCONTIG>(acc, a.A + (size_t)i0 * ld + (size_t)kbeg * 64, ld, a.A + (size_t)j0 * ld + (size_t)kbeg * 64, ld,
                                 (tj - kbeg) * 4, a.ready + (size_t)ti * nt + kbeg, 1,
-                                (ti != tj) ? a.ready + (size_t)tj * nt + kbeg : nullptr, 1, a.abort_flag, gsm, ok, my_sm);
+                                (ti != tj) ? a.ready + (size_t)tj * nt + kbeg : nullptr, 1, a.abort_flag, gsm, ok,
+                                chain_tile ? nullptr : my_sm);
     __syncthreads();  // ring drained by every warp before the finalisation buffers overwrite it
+    double* At = a.A + (size_t)i0 * ld + j0;
+    const bool near_tile = (ti - tj) <= NEAR_BAND && ti < nt;  // finishes by substitution against the streamed panels
+    if (!near_tile) {
+      // Off-chain tiles: L_ij = C X_jj^T with the explicit inverse of the diagonal tile (published by
+      // its owner a few microseconds after L_jj itself) -- one 64^3 tensor-core product instead of a
+      // latency-bound substitution.  Tile (i, j) is an input of tile (i, j+1), so every tile row is a
+      // dependency chain of its own, and what a tile does after its last input arrives bounds the
+      // whole factorisation as much as the diagonal chain does.
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < CfgP::NI; ++ni) {
+          double* pc = sT + (wm0 + mi * 8 + g) * TS + wn0 + ni * 8 + 2 * t;  // C = -acc as a [m][k] operand
+          pc[0] = -acc[mi][ni][0];
+          pc[1] = -acc[mi][ni][1];
+        }
+      EB_STAMP(2);
+      ok = wait_ready(a.xready + (size_t)tj * nt + tj, a.abort_flag) && ok;
+      yield_to_chain(my_sm);
+      EB_STAMP(3);
+      using EK = Engine<CfgP, KCONTIG, KCONTIG>;
+      const double* Dg = a.W + (size_t)j0 * ld + j0;  // X_jj
+#pragma unroll
+      for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(sD + c * 64 * (KC + 4), Dg + c * KC, ld, tid);
+      cp_async_commit();
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < CfgP::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      cp_async_wait<0>();
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double* sB = sD + c * 64 * (KC + 4);
+#pragma unroll
+        for (int kk = 0; kk < KC; kk += 4) {
+          double af[CfgP::MI], bf[CfgP::NI];
+#pragma unroll
+          for (int mi = 0; mi < CfgP::MI; ++mi) af[mi] = sT[(wm0 + mi * 8 + g) * TS + c * KC + kk + t];
+#pragma unroll
+          for (int ni = 0; ni < CfgP::NI; ++ni) bf[ni] = sB[(wn0 + ni * 8 + g) * (KC + 4) + kk + t];
+#pragma unroll
+          for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        }
+      }
+#pragma unroll
+      for (int mi = 0; mi < CfgP::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < CfgP::NI; ++ni) {
+          double2 val;
+          val.x = acc[mi][ni][0];
+          val.y = acc[mi][ni][1];
+          *reinterpret_cast<double2*>(At + (size_t)(wm0 + mi * 8 + g) * ld + wn0 + ni * 8 + 2 * t) = val;
+        }
+      EB_STAMP(4);
+      const int all_ok = publish(a.ready + (size_t)ti * nt + tj, ok);
+      EB_STAMP(5);
+      if (!all_ok) break;
+      continue;
+    }
     // C = -acc parked in shared memory
 #pragma unroll
     for (int mi = 0; mi < CfgP::MI; ++mi) {
@@ -555,7 +652,6 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     }
     __syncthreads();
     EB_STAMP(2);
-    double* At = a.A + (size_t)i0 * ld + j0;
     double v[2][8];
 #pragma unroll
     for (int sl = 0; sl < 2; ++sl)
@@ -571,35 +667,25 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       int all_ok = publish(a.ready + (size_t)ti * nt + tj, ok);
       if (tid == 0) atomicSub(my_sm, 1);
       EB_STAMP(5);
-      // ---- off the critical path: log-determinant share and X_jj = L_jj^-1 ----
+      // ---- off the critical path: the log-determinant share ----
       if (tid < 64) colbuf[tid] = log(rdiag[tid]);
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[sl][c] = (lane + 32 * sl == 8 * warp + c) ? 1.0 : 0.0;
       __syncthreads();
       if (tid == 0) {
         double sum = 0.0;
         for (int j = 0; j < 64; ++j) sum += colbuf[j];
         a.logdet_part[tj] = -sum;  // sum_j log L_jj = -sum_j log(1 / L_jj)
       }
-      if (a.value_only) {
-        if (!all_ok) break;
-        continue;
-      }
-      tile_trsm(v, sL, rdiag, sC);  // sC = I L^-T = (L^-1)^T
-      double* Wt = a.W + (size_t)i0 * ld + j0;
-      for (int e = tid; e < 64 * 64; e += 256) {
-        const int r = e >> 6, c = e & 63;
-        Wt[(size_t)r * ld + c] = (c <= r) ? sC[c * PS + r] : 0.0;
-      }
-      all_ok &= publish(a.xready + (size_t)ti * nt + tj, ok);
       if (!all_ok) break;
     } else {
-      // substitution against L_jj, panel by panel as the diagonal tile's owner streams them out
-      // (no priority flag here: this phase waits for panels of another CTA, and a flag held across a
-      //  wait can starve the very producer it waits for)
-      if (!chain_tile) yield_to_chain(my_sm);
+      // near tiles (j+1 .. j+NEAR_BAND, j): substitution against L_jj, panel by panel as the diagonal
+      // tile's owner streams them out (no priority flag here: this phase waits for panels of another CTA, and a
+      // flag held across a wait can starve the very producer it waits for)
+      // The chain tile (j+1, j) takes the FP64 pipe of its SM for itself once panel 0 is out: from
+      // then on the diagonal tile's owner is inside its (bounded) tile factorisation.
+      if (chain_tile) {
+        ok = wait_ready(a.lready + (size_t)tj * 8, a.abort_flag) && ok;
+        if (tid == 0) atomicAdd(my_sm, 1);
+      }
       EB_STAMP(3);
       {
         int* abort_flag = a.abort_flag;
@@ -614,6 +700,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       }
       EB_STAMP(4);
       const int all_ok = publish(a.ready + (size_t)ti * nt + tj, ok);
+      if (chain_tile && tid == 0) atomicSub(my_sm, 1);
       EB_STAMP(5);
       if (!all_ok) break;
     }
