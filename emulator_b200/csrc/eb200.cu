@@ -666,14 +666,14 @@ static int factor_trace_impl(eb200_gp* h, const double* p_host, int mode, unsign
   CK(cudaSetDevice(h->device));
   const bool vo = mode == EB200_EVAL_VALUE_ONLY;
   const int ntasks = vo ? h->n_ftasks_v : h->n_ftasks;
-  CK(cudaMalloc(&h->trace, (size_t)ntasks * 8 * sizeof(unsigned long long)));
-  CK(cudaMemset(h->trace, 0, (size_t)ntasks * 8 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->trace, (size_t)ntasks * TRACE_SLOTS * sizeof(unsigned long long)));
+  CK(cudaMemset(h->trace, 0, (size_t)ntasks * TRACE_SLOTS * sizeof(unsigned long long)));
   memcpy(h->h_p, p_host, (h->d + 1) * sizeof(double));
   CK(cudaMemcpyAsync(h->p_dev, h->h_p, (h->d + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   int rc = enqueue_eval(h, h->stream, mode, 2, nullptr, nullptr);
   cudaError_t e = cudaStreamSynchronize(h->stream);
   if (!rc && e == cudaSuccess) {
-    e = cudaMemcpy(out_host, h->trace, (size_t)ntasks * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    e = cudaMemcpy(out_host, h->trace, (size_t)ntasks * TRACE_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaMemcpy(tasks_out, vo ? h->ftasks_v : h->ftasks, (size_t)ntasks * sizeof(FactorTask), cudaMemcpyDeviceToHost);
   }
   cudaFree(h->trace);

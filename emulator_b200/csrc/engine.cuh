@@ -9,10 +9,12 @@
 // Operand layouts (both live in row-major global matrices):
 //   KCONTIG : element (row, k) at base[row*ld + k]      ("N" for A, "T" for B)
 //   MCONTIG : element (row, k) at base[k*ld + row]      ("T" for A, "N" for B)
-// Shared-memory staging is padded so that every DMMA fragment load (8 rows x 4 k, one
-// double per lane) is bank-conflict free:
-//   KCONTIG : [rows][KC+4]   -> lane address row*20 + k   (half-warp covers 16 distinct 8B slots)
-//   MCONTIG : [KC][rows+4]   -> lane address k*(rows+4) + row
+// The k index inside a block of 8 is permuted between the two DMMAs that consume it: lane (g, t)
+// feeds k = 2t to the first and k = 2t+1 to the second (any permutation is legal as long as A and B
+// agree), so a KCONTIG operand needs ONE 16-byte shared load per two DMMAs.  Staging is padded so
+// that those loads are bank-conflict free:
+//   KCONTIG : [rows][KC+8]   -> lane address row*24 + 2t  (LDS.128: a quarter-warp covers 8 distinct 16B slots)
+//   MCONTIG : [KC][rows+2]   -> lane address (2t | 2t+1)*(rows+2) + row  (LDS.64: a half-warp covers 16 distinct 8B slots)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -42,8 +44,27 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 template <int ROWS, int LAYOUT>
+struct OperandSmem;
+
+// Fragments of N 8-row blocks for two consecutive DMMAs: f[0][i] = op(row0 + 8i, k0), f[1][i] = op(row0 + 8i, k0 + 1).
+template <int LAYOUT, int N>
+__device__ __forceinline__ void load_fragments(double (&f)[2][N], const double* s, int stride, int row0, int k0) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    if (LAYOUT == 0) {  // KCONTIG
+      const double2 v = *reinterpret_cast<const double2*>(s + (row0 + 8 * i) * stride + k0);
+      f[0][i] = v.x;
+      f[1][i] = v.y;
+    } else {
+      f[0][i] = s[k0 * stride + row0 + 8 * i];
+      f[1][i] = s[(k0 + 1) * stride + row0 + 8 * i];
+    }
+  }
+}
+
+template <int ROWS, int LAYOUT>
 struct OperandSmem {
-  static constexpr int STRIDE = (LAYOUT == KCONTIG) ? (KC + 4) : (ROWS + 4);
+  static constexpr int STRIDE = (LAYOUT == KCONTIG) ? (KC + 8) : (ROWS + 2);
   static constexpr int DOUBLES = (LAYOUT == KCONTIG) ? ROWS * STRIDE : KC * STRIDE;
 };
 
@@ -127,22 +148,16 @@ struct Engine {
           const double* sA = smem + ((kt + h) % STAGES) * STAGE_DOUBLES;
           const double* sB = sA + SA::DOUBLES;
 #pragma unroll
-          for (int kk = 0; kk < KC; kk += 4) {
-            double af[Cfg::MI], bf[Cfg::NI];
+          for (int kk = 0; kk < KC; kk += 8) {
+            double af[2][Cfg::MI], bf[2][Cfg::NI];
+            load_fragments<LA, Cfg::MI>(af, sA, SA::STRIDE, wm0 + g, kk + 2 * t);
+            load_fragments<LB, Cfg::NI>(bf, sB, SB::STRIDE, wn0 + g, kk + 2 * t);
 #pragma unroll
-            for (int mi = 0; mi < Cfg::MI; ++mi) {
-              int row = wm0 + mi * 8 + g;
-              af[mi] = (LA == KCONTIG) ? sA[row * SA::STRIDE + kk + t] : sA[(kk + t) * SA::STRIDE + row];
-            }
+            for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
-            for (int ni = 0; ni < Cfg::NI; ++ni) {
-              int col = wn0 + ni * 8 + g;
-              bf[ni] = (LB == KCONTIG) ? sB[col * SB::STRIDE + kk + t] : sB[(kk + t) * SB::STRIDE + col];
-            }
+              for (int mi = 0; mi < Cfg::MI; ++mi)
 #pragma unroll
-            for (int mi = 0; mi < Cfg::MI; ++mi)
-#pragma unroll
-              for (int ni = 0; ni < Cfg::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+                for (int ni = 0; ni < Cfg::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[h2][mi], bf[h2][ni]);
           }
         }
       }

@@ -29,9 +29,11 @@ namespace eb {
 
 using CfgP = TileCfg<64, 64, 32, 16>;  // 256 threads: 2 x 4 warps, 16 accumulator doubles / thread
 constexpr int PSTAGES = 4;             // cp.async ring depth (two CTAs per SM share 227 KB)
-constexpr int PSTAGE_DOUBLES = 2 * 64 * (KC + 4);
+constexpr int KS = KC + 8;               // stride of a staged KCONTIG slab (engine.cuh)
+constexpr int PSTAGE_DOUBLES = 2 * 64 * KS;
 constexpr int PS = TPS;                // stride of the 64x64 finalisation buffers (tile_ops.cuh)
-constexpr int TS = 68;                 // stride of a parked accumulator used as a [k][n] operand
+constexpr int TS = 66;                 // stride of a parked accumulator used as a [k][n] operand (conflict-free with permuted k)
+constexpr int TSK = 72;                // stride of a parked accumulator used as a [m][k] operand (LDS.128 fragments)
 constexpr int NEAR_BAND = 2;           // tiles (j+1..j+NEAR_BAND, j) cannot wait for X_jj: they follow L_jj's panels
 
 // TASK_TRTRI_PART (r, J, k): helper that pre-accumulates sum_{K=J}^{k-1} L_rK X_KJ of a long inverse
@@ -75,7 +77,7 @@ struct FactorArgs {
   double* rdiag;          // [nt][64] reciprocal pivots 1 / L_jj, published with the diagonal tile
   int* info;
   int* abort_flag;        // watchdog: set when a wait exceeded its budget
-  unsigned long long* trace;  // optional [ntasks][8]: 6 globaltimer stamps, SM id, CTA id (diagnostics), or nullptr
+  unsigned long long* trace;  // optional [ntasks][TRACE_SLOTS] (diagnostics), or nullptr
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -83,9 +85,16 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+constexpr int TRACE_SLOTS = 10;  // 6 stamps, SM id, CTA id, ns waited for flags, ns yielded to the chain
 #define EB_STAMP(slot)                                                                \
   do {                                                                                \
-    if (a.trace != nullptr && tid == 0) a.trace[(size_t)task * 8 + (slot)] = gtime(); \
+    if (a.trace != nullptr && tid == 0) {                                             \
+      a.trace[(size_t)task * TRACE_SLOTS + (slot)] = gtime();                          \
+      if ((slot) == 5) {                                                              \
+        a.trace[(size_t)task * TRACE_SLOTS + 8] = s_wait[0];                           \
+        a.trace[(size_t)task * TRACE_SLOTS + 9] = s_wait[1];                           \
+      }                                                                               \
+    }                                                                                 \
   } while (0)
 
 // Flags are polled with a relaxed gpu-scope load: an acquire load would make ptxas emit
@@ -152,7 +161,7 @@ template <int LB>
 __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP::NI][2], const double* Ag, int lda,
                                                    const double* Bg, int ldb, int nk, const int* fa, int sa,
                                                    const int* fb, int sb, int* abort_flag, double* pipe, bool& ok,
-                                                   const int* yield_to) {
+                                                   const int* yield_to, unsigned long long* waited = nullptr) {
   using E = Engine<CfgP, KCONTIG, LB>;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm0 = (warp / CfgP::WARPS_N) * CfgP::WM;
@@ -180,8 +189,10 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
     if ((kt & 3) == 0) {
       const int kc = kt >> 2;
       if (kc >= known) {
+        const unsigned long long w0 = waited ? gtime() : 0ull;
         ok = wait_ready(fa + (size_t)kc * sa, abort_flag) && ok;
         if (fb != nullptr) ok = wait_ready(fb + (size_t)kc * sb, abort_flag) && ok;
+        if (waited) *waited += gtime() - w0;
         rescan(kc + 1);  // producers usually publish several tile columns while we wait
       }
     }
@@ -221,19 +232,16 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
       const double* sA = pipe + ((kt + h) % PSTAGES) * PSTAGE_DOUBLES;
       const double* sB = sA + E::SA::DOUBLES;
 #pragma unroll
-      for (int kk = 0; kk < KC; kk += 4) {
-        double af[CfgP::MI], bf[CfgP::NI];
+      for (int kk = 0; kk < KC; kk += 8) {
+        double af[2][CfgP::MI], bf[2][CfgP::NI];
+        load_fragments<KCONTIG, CfgP::MI>(af, sA, E::SA::STRIDE, wm0 + g, kk + 2 * t);
+        load_fragments<LB, CfgP::NI>(bf, sB, E::SB::STRIDE, wn0 + g, kk + 2 * t);
 #pragma unroll
-        for (int mi = 0; mi < CfgP::MI; ++mi) af[mi] = sA[(wm0 + mi * 8 + g) * E::SA::STRIDE + kk + t];
+        for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
-        for (int ni = 0; ni < CfgP::NI; ++ni) {
-          const int col = wn0 + ni * 8 + g;
-          bf[ni] = (LB == KCONTIG) ? sB[col * E::SB::STRIDE + kk + t] : sB[(kk + t) * E::SB::STRIDE + col];
-        }
+          for (int mi = 0; mi < CfgP::MI; ++mi)
 #pragma unroll
-        for (int mi = 0; mi < CfgP::MI; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+            for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[h2][mi], bf[h2][ni]);
       }
     }
     if (more && !early) {
@@ -242,8 +250,10 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
       cp_async_commit();
     }
     if (busy != 0) {  // lane 0 only; the other lanes wait for it at the next barrier
+      const unsigned long long w0 = waited ? gtime() : 0ull;
       int spins = 0;
       while (ld_flag(yield_to) != 0 && ++spins < 256) __nanosleep(200);
+      if (waited) waited[1] += gtime() - w0;
     }
   }
   cp_async_wait<0>();
@@ -257,15 +267,16 @@ struct FactorSmem {
   static constexpr int C_OFF = 0;                   // [64][65]   C tile / substitution output
   static constexpr int L_OFF = C_OFF + 64 * PS;     // [64][65]   L_jj
   static constexpr int T_OFF = 0;                   // [64][68]   parked accumulator (inverse tasks)
-  static constexpr int DINV_OFF = T_OFF + 64 * TS;  // 4 x [64][KC+4] slabs of X_rr (inverse tasks)
-  static constexpr int XI_OFF = PIPE;               // [DP][64]
+  static constexpr int DINV_OFF = T_OFF + 64 * TSK;  // 4 x [64][KS] slabs of the diagonal inverse
+  static constexpr int XI_OFF = 0;                  // [DP][64]  (K generation happens before the ring is used)
   static constexpr int XJ_OFF = XI_OFF + DP * 64;   // [DP][64]
-  static constexpr int COL_OFF = XJ_OFF + DP * 64;  // [128]
+  static constexpr int COL_OFF = PIPE;              // [128]
   static constexpr int RD_OFF = COL_OFF + 128;      // [64]
   static constexpr int DOUBLES = RD_OFF + 64 + 16;
   static constexpr int BYTES = DOUBLES * (int)sizeof(double);
   static_assert(2 * 64 * PS <= PIPE, "finalisation buffers must fit the ring");
-  static_assert(DINV_OFF + 4 * 64 * (KC + 4) <= PIPE, "inverse finalisation must fit the ring");
+  static_assert(2 * DP * 64 <= PIPE, "input staging must fit the ring");
+  static_assert(DINV_OFF + 4 * 64 * KS <= PIPE, "inverse finalisation must fit the ring");
   static_assert(2 * BYTES + 2048 <= 227 * 1024, "two CTAs per SM");
 };
 
@@ -275,6 +286,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
   using SM = FactorSmem<DP>;
   __shared__ unsigned s_task;
   __shared__ int s_role;
+  __shared__ unsigned long long s_wait[2];  // diagnostics: time thread 0 spent waiting in the accumulation loops
   __shared__ int s_pflags[16];  // per-panel flags of the two tile finalisers (epoch-valued, never reset)
   double* sC = gsm + SM::C_OFF;
   double* sL = gsm + SM::L_OFF;
@@ -330,10 +342,12 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     const int ti = tk.i, tj = tk.j;
     const int i0 = ti * 64, j0 = tj * 64;
     bool ok = true;
+    unsigned long long* wait_acc = (a.trace != nullptr && tid == 0) ? s_wait : nullptr;
     EB_STAMP(0);
     if (a.trace != nullptr && tid == 0) {
-      a.trace[(size_t)task * 8 + 6] = smid();
-      a.trace[(size_t)task * 8 + 7] = blockIdx.x;
+      a.trace[(size_t)task * TRACE_SLOTS + 6] = smid();
+      a.trace[(size_t)task * TRACE_SLOTS + 7] = blockIdx.x;
+      s_wait[0] = s_wait[1] = 0ull;
     }
     double acc[CfgP::MI][CfgP::NI][2];
 
@@ -374,7 +388,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
         for (int ni = 0; ni < CfgP::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
       accumulate_flagged<KCONTIG>(acc, a.A + (size_t)i0 * ld, ld, a.A + (size_t)j0 * ld, ld, tk.k * 4,
                                   a.ready + (size_t)ti * nt, 1, (ti != tj) ? a.ready + (size_t)tj * nt : nullptr, 1,
-                                  a.abort_flag, gsm, ok, a.sm_chain + smid());
+                                  a.abort_flag, gsm, ok, a.sm_chain + smid(), wait_acc);
       double* cs = a.A + (size_t)i0 * ld + j0;  // the tile's own storage (nobody reads it before L_ij is published)
 #pragma unroll
       for (int mi = 0; mi < CfgP::MI; ++mi)
@@ -417,7 +431,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       accumulate_flagged<MCONTIG>(acc, a.A + (size_t)i0 * ld + (size_t)kbeg * 64, ld,
                                   a.W + (size_t)kbeg * 64 * ld + j0, ld, (kend - kbeg) * 4,
                                   a.ready + (size_t)ti * nt + kbeg, 1, a.xready + (size_t)kbeg * nt + tj, nt,
-                                  a.abort_flag, gsm, ok, a.sm_chain + smid());
+                                  a.abort_flag, gsm, ok, a.sm_chain + smid(), wait_acc);
       if (part) {
 #pragma unroll
         for (int mi = 0; mi < CfgP::MI; ++mi)
@@ -451,7 +465,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       using EK = Engine<CfgP, KCONTIG, KCONTIG>;
       const double* Dg = a.W + (size_t)i0 * ld + i0;  // X_rr
 #pragma unroll
-      for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(sD + c * 64 * (KC + 4), Dg + c * KC, ld, tid);
+      for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(sD + c * 64 * KS, Dg + c * KC, ld, tid);
       cp_async_commit();
 #pragma unroll
       for (int mi = 0; mi < CfgP::MI; ++mi)
@@ -461,18 +475,17 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       __syncthreads();
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const double* sA = sD + c * 64 * (KC + 4);
 #pragma unroll
-        for (int kk = 0; kk < KC; kk += 4) {
-          double af[CfgP::MI], bf[CfgP::NI];
+        for (int kk = 0; kk < KC; kk += 8) {
+          double af[2][CfgP::MI], bf[2][CfgP::NI];
+          load_fragments<KCONTIG, CfgP::MI>(af, sD + c * 64 * KS, KS, wm0 + g, kk + 2 * t);
+          load_fragments<MCONTIG, CfgP::NI>(bf, sT, TS, wn0 + g, c * KC + kk + 2 * t);
 #pragma unroll
-          for (int mi = 0; mi < CfgP::MI; ++mi) af[mi] = sA[(wm0 + mi * 8 + g) * (KC + 4) + kk + t];
+          for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
-          for (int ni = 0; ni < CfgP::NI; ++ni) bf[ni] = sT[(c * KC + kk + t) * TS + wn0 + ni * 8 + g];
+            for (int mi = 0; mi < CfgP::MI; ++mi)
 #pragma unroll
-          for (int mi = 0; mi < CfgP::MI; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+              for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[h2][mi], bf[h2][ni]);
         }
       }
       double* Wt = a.W + (size_t)i0 * ld + j0;
@@ -560,6 +573,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       }
     }
     }
+    __syncthreads();  // the staged inputs alias the cp.async ring
     EB_STAMP(1);
     const int kbeg = tk.k;  // > 0: tile columns [0, kbeg) were pre-accumulated by a TASK_POTRF_PART
     if (kbeg > 0) {
@@ -579,7 +593,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     accumulate_flagged<KCONTIG>(acc, a.A + (size_t)i0 * ld + (size_t)kbeg * 64, ld, a.A + (size_t)j0 * ld + (size_t)kbeg * 64, ld,
                                 (tj - kbeg) * 4, a.ready + (size_t)ti * nt + kbeg, 1,
                                 (ti != tj) ? a.ready + (size_t)tj * nt + kbeg : nullptr, 1, a.abort_flag, gsm, ok,
-                                chain_tile ? nullptr : my_sm);
+                                chain_tile ? nullptr : my_sm, wait_acc);
     __syncthreads();  // ring drained by every warp before the finalisation buffers overwrite it
     double* At = a.A + (size_t)i0 * ld + j0;
     const bool near_tile = (ti - tj) <= NEAR_BAND && ti < nt;  // finishes by substitution against the streamed panels
@@ -593,7 +607,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       for (int mi = 0; mi < CfgP::MI; ++mi)
 #pragma unroll
         for (int ni = 0; ni < CfgP::NI; ++ni) {
-          double* pc = sT + (wm0 + mi * 8 + g) * TS + wn0 + ni * 8 + 2 * t;  // C = -acc as a [m][k] operand
+          double* pc = sT + (wm0 + mi * 8 + g) * TSK + wn0 + ni * 8 + 2 * t;  // C = -acc as a [m][k] operand
           pc[0] = -acc[mi][ni][0];
           pc[1] = -acc[mi][ni][1];
         }
@@ -604,7 +618,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       using EK = Engine<CfgP, KCONTIG, KCONTIG>;
       const double* Dg = a.W + (size_t)j0 * ld + j0;  // X_jj
 #pragma unroll
-      for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(sD + c * 64 * (KC + 4), Dg + c * KC, ld, tid);
+      for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(sD + c * 64 * KS, Dg + c * KC, ld, tid);
       cp_async_commit();
 #pragma unroll
       for (int mi = 0; mi < CfgP::MI; ++mi)
@@ -614,18 +628,17 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       __syncthreads();
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const double* sB = sD + c * 64 * (KC + 4);
 #pragma unroll
-        for (int kk = 0; kk < KC; kk += 4) {
-          double af[CfgP::MI], bf[CfgP::NI];
+        for (int kk = 0; kk < KC; kk += 8) {
+          double af[2][CfgP::MI], bf[2][CfgP::NI];
+          load_fragments<KCONTIG, CfgP::MI>(af, sT, TSK, wm0 + g, c * KC + kk + 2 * t);
+          load_fragments<KCONTIG, CfgP::NI>(bf, sD + c * 64 * KS, KS, wn0 + g, kk + 2 * t);
 #pragma unroll
-          for (int mi = 0; mi < CfgP::MI; ++mi) af[mi] = sT[(wm0 + mi * 8 + g) * TS + c * KC + kk + t];
+          for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
-          for (int ni = 0; ni < CfgP::NI; ++ni) bf[ni] = sB[(wn0 + ni * 8 + g) * (KC + 4) + kk + t];
+            for (int mi = 0; mi < CfgP::MI; ++mi)
 #pragma unroll
-          for (int mi = 0; mi < CfgP::MI; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+              for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[h2][mi], bf[h2][ni]);
         }
       }
 #pragma unroll

@@ -90,9 +90,10 @@ int eb200_gp_debug_alpha(eb200_gp* gp, double* alpha_host);
 /* number of kernel launches issued by one eval (graph nodes) */
 int eb200_gp_eval_launches(const eb200_gp* gp, int mode);
 
-/* Per-task globaltimer stamps (ns) of the dataflow factorisation kernel: out[task][8] =
+/* Per-task globaltimer stamps (ns) of the dataflow factorisation kernel: out[task][10] =
  * {claimed, K generated / panels accumulated, C formed / diagonal inverse visible, diagonal
- * factor visible, tile stored, published, SM id, CTA id}; tasks_out[task][4] = (type 0 Cholesky / 1 inverse,
+ * factor visible, tile stored, published, SM id, CTA id, ns spent waiting for input flags, ns yielded
+ * to chain tiles}; tasks_out[task][4] = (type 0 Cholesky / 1 inverse,
  * tile row, tile column, 0).  The number of tasks is eb200_gp_factor_tasks(). */
 int eb200_gp_debug_factor_trace(eb200_gp* gp, const double* p_host, unsigned long long* out_host, int* tasks_out);
 int eb200_gp_factor_tasks(const eb200_gp* gp);

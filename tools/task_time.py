@@ -18,7 +18,9 @@ for ty in range(5):
     else: prods = np.zeros(m.sum())
     dur = t[m, 5] - t[m, 0]
     tot += dur.sum()
-    line = f"{NAMES[ty]:11s} n={m.sum():5d} CTA-time {dur.sum()/1e3:7.1f} ms  products {prods.sum():7d}  us/product {dur.sum()/max(prods.sum(),1):6.2f}"
+    line = f"{NAMES[ty]:11s} n={m.sum():5d} CTA-time {dur.sum()/1e3:7.1f} ms  products {int(prods.sum()):7d}  us/product {dur.sum()/max(prods.sum(),1):6.2f}"
+    if out.shape[1] >= 10:
+        line += f" | flag-wait {out[m, 8].sum()/1e6:6.1f} ms yield {out[m, 9].sum()/1e6:6.1f} ms"
     if ty == 1:
         line += f" | accumulate {np.sum(t[m,1]-t[m,0])/1e3:6.1f} park+waitX {np.sum(t[m,2]-t[m,1])/1e3:6.1f} finalize {np.sum(t[m,4]-t[m,2])/1e3:6.1f} publish {np.sum(t[m,5]-t[m,4])/1e3:6.1f}"
     if ty == 0:
