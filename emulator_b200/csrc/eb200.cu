@@ -91,10 +91,12 @@ struct eb200_gp {
   TileTask* tasks = nullptr;
   int2* ktiles = nullptr;
   FactorTask* ftasks = nullptr;  // dataflow task list: Cholesky tasks, then inverse tasks
-  int n_ftasks = 0, qbase[4] = {0, 0, 0, 0};
+  int n_ftasks = 0, qbase[5] = {0, 0, 0, 0, 0};
+  int* inv_order = nullptr;  // the inverse's tasks (indices into ftasks) in their dependency-safe order
+  int n_inv = 0;
   FactorTask* ftasks_v = nullptr;  // value-only list: Cholesky tiles + the residual row
   int n_ftasks_v = 0;
-  int qbase_v[4] = {0, 0, 0, 0};
+  int qbase_v[5] = {0, 0, 0, 0, 0};
   unsigned* counter = nullptr;
   int* ready = nullptr;
   int* xready = nullptr;
@@ -208,15 +210,16 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int mode, double* kinv
     case OP_FACTOR_DF: {
       const bool vo = mode == EB200_EVAL_VALUE_ONLY;
       const size_t nf = (size_t)(h->nt + 1) * h->nt;  // flags per array (tile row nt: the residual row)
-      cudaMemsetAsync(h->counter, 0, 4 * sizeof(unsigned), st);
-      cudaMemsetAsync(h->ready, 0, (4 * nf + 8 * h->nt + 512) * sizeof(int), st);  // ready, xready, pready, cready, lready, sm_chain
+      cudaMemsetAsync(h->counter, 0, 8 * sizeof(unsigned), st);
+      // ready, xready, pready, cready, lready, sm_chain, claimed
+      cudaMemsetAsync(h->ready, 0, (4 * nf + 8 * h->nt + 512 + (size_t)h->n_ftasks) * sizeof(int), st);
       FactorArgs fa;
       fa.A = h->A; fa.W = h->W; fa.ld = np; fa.nt = h->nt; fa.n = h->n; fa.X = h->X; fa.noise = h->noise; fa.kp = h->kp;
       fa.value_only = vo ? 1 : 0; fa.r = h->r;
       fa.tasks = vo ? h->ftasks_v : h->ftasks; fa.ntasks = vo ? h->n_ftasks_v : h->n_ftasks;
-      for (int q = 0; q < 4; ++q) fa.qbase[q] = vo ? h->qbase_v[q] : h->qbase[q];
+      for (int q = 0; q < 5; ++q) fa.qbase[q] = vo ? h->qbase_v[q] : h->qbase[q];
       fa.counter = h->counter; fa.ready = h->ready; fa.xready = fa.ready + nf; fa.pready = fa.xready + nf;
-      fa.cready = fa.pready + nf; fa.lready = fa.cready + nf; fa.sm_chain = fa.lready + 8 * h->nt;
+      fa.cready = fa.pready + nf; fa.lready = fa.cready + nf; fa.sm_chain = fa.lready + 8 * h->nt; fa.claimed = fa.sm_chain + 512; fa.inv_order = h->inv_order; fa.n_inv = vo ? 0 : h->n_inv;
       fa.logdet_part = h->logdet_part; fa.rdiag = h->rdiag; fa.info = h->info; fa.abort_flag = h->abort_flag;
       fa.trace = h->trace;
       // two CTAs per SM: the first wave (one per SM) serves the Cholesky queue, the second the inverse
@@ -400,8 +403,7 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMemset(h->alpha, 0, np * sizeof(double)));
   CK(cudaMemset(h->W, 0, mat));
   CK(cudaMemset(h->A, 0, mat_a));  // strictly-upper 64-blocks of diagonal 128-tiles must stay zero
-  CK(cudaMalloc(&h->counter, 4 * sizeof(unsigned)));
-  CK(cudaMalloc(&h->ready, ((size_t)4 * (h->nt + 1) * h->nt + 8 * h->nt + 512) * sizeof(int)));
+  CK(cudaMalloc(&h->counter, 8 * sizeof(unsigned)));
   CK(cudaMalloc(&h->abort_flag, sizeof(int)));
   CK(cudaMalloc(&h->rdiag, (size_t)np * sizeof(double)));
   CK(cudaMemset(h->abort_flag, 0, sizeof(int)));
@@ -441,16 +443,34 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
     // the work of the last rows -- the tail of the launch -- into the time the Cholesky chain
     // leaves SMs idle.
     const int MAIN_K = 12, MIN_PART = 8;
+    // The dependency-safe total order is row by row, a row's tiles followed by the helpers whose inputs
+    // exist once that row is done; `seq` records it.  Tiles go to queue 2 and helpers to queue 3, both
+    // claimed ready-first (factor_dataflow.cuh), falling back to this order.
     std::vector<std::vector<FactorTask>> after_row(nt);
     for (int r = 1; r < nt; ++r)
       for (int J = 0; J < r; ++J)
-        if (r - J > MAIN_K + MIN_PART) after_row[r - MAIN_K - 1].push_back({TASK_TRTRI_PART, r, J, r - MAIN_K});
+        if (r - J > MAIN_K + MIN_PART) after_row[r - MAIN_K - 1].push_back({TASK_TRTRI_PART, r, J, r - MAIN_K, 0});
+    std::vector<FactorTask> mains, helpers;
+    int seq = 0;
     for (int r = 1; r < nt; ++r) {
-      for (int J = 0; J < r; ++J) ft.push_back({TASK_TRTRI, r, J, (r - J > MAIN_K + MIN_PART) ? r - MAIN_K : J});
-      for (auto& tk : after_row[r]) ft.push_back(tk);
+      for (int J = 0; J < r; ++J) mains.push_back({TASK_TRTRI, r, J, (r - J > MAIN_K + MIN_PART) ? r - MAIN_K : J, seq++});
+      for (auto& tk : after_row[r]) {
+        tk.seq = seq++;
+        helpers.push_back(tk);
+      }
     }
+    std::vector<int> order(seq);
+    for (size_t k = 0; k < mains.size(); ++k) order[mains[k].seq] = (int)(ft.size() + k);
+    ft.insert(ft.end(), mains.begin(), mains.end());
+    h->qbase[3] = (int)ft.size();
+    for (size_t k = 0; k < helpers.size(); ++k) order[helpers[k].seq] = (int)(ft.size() + k);
+    ft.insert(ft.end(), helpers.begin(), helpers.end());
+    h->n_inv = seq;
+    CK(cudaMalloc(&h->inv_order, std::max<size_t>(1, order.size()) * sizeof(int)));
+    CK(cudaMemcpy(h->inv_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
     h->n_ftasks = (int)ft.size();
-    h->qbase[3] = h->n_ftasks;
+    h->qbase[4] = h->n_ftasks;
+    CK(cudaMalloc(&h->ready, ((size_t)4 * (h->nt + 1) * h->nt + 8 * h->nt + 512 + ft.size()) * sizeof(int)));  // flags + claim marks
     CK(cudaMalloc(&h->ftasks, ft.size() * sizeof(FactorTask)));
     CK(cudaMemcpy(h->ftasks, ft.data(), ft.size() * sizeof(FactorTask), cudaMemcpyHostToDevice));
     // Value-only list (likelihood without gradient, e.g. ensemble sampling): the Cholesky tasks of
@@ -466,7 +486,7 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
         for (int i = cc; i <= nt; ++i) fv.push_back({TASK_POTRF_PART, i, cc, cc - POTRF_LA});
     }
     h->n_ftasks_v = (int)fv.size();
-    h->qbase_v[2] = h->qbase_v[3] = h->n_ftasks_v;
+    h->qbase_v[2] = h->qbase_v[3] = h->qbase_v[4] = h->n_ftasks_v;
     CK(cudaMalloc(&h->ftasks_v, fv.size() * sizeof(FactorTask)));
     CK(cudaMemcpy(h->ftasks_v, fv.data(), fv.size() * sizeof(FactorTask), cudaMemcpyHostToDevice));
   }
@@ -514,7 +534,7 @@ int eb200_gp_destroy(eb200_gp* h) {
   if (h->g_val) cudaGraphExecDestroy(h->g_val);
   void* dev[] = {h->A, h->W, h->X, h->noise, h->r, h->z, h->alpha, h->logdet_part, h->tpartial,
                  h->trace_partial, h->p_dev, h->out_dev, h->kp, h->info, h->tasks, h->ktiles, h->T_dev, h->T_in,
-                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ftasks, h->ftasks_v, h->counter, h->ready, h->abort_flag, h->rdiag};
+                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ftasks, h->ftasks_v, h->inv_order, h->counter, h->ready, h->abort_flag, h->rdiag};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (h->h_p) cudaFreeHost(h->h_p);

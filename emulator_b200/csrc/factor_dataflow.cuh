@@ -49,6 +49,7 @@ constexpr int NEAR_BAND = 2;           // tiles (j+1..j+NEAR_BAND, j) cannot wai
 enum FactorTaskType : int { TASK_POTRF = 0, TASK_TRTRI = 1, TASK_TRTRI_PART = 2, TASK_POTRF_PART = 3, TASK_XDIAG = 4 };
 struct FactorTask {
   int type, i, j, k;
+  int seq;  // position in the dependency-safe total order of the inverse's tasks (ready-first queues)
 };
 
 struct FactorArgs {
@@ -60,12 +61,15 @@ struct FactorArgs {
   const double* X;        // [np][DP] padded training inputs
   const double* noise;    // [np]
   const KernelParams* kp;
-  const FactorTask* tasks;  // three queues back to back: chain tiles | other Cholesky tasks | inverse tasks
+  const FactorTask* tasks;  // four queues back to back: chain tiles | other Cholesky tasks | inverse tiles | inverse helpers
   int ntasks;
-  int qbase[4];             // queue q holds tasks [qbase[q], qbase[q+1])
+  int qbase[5];             // queue q holds tasks [qbase[q], qbase[q+1])
+  int* claimed;             // [ntasks] claim marks of the ready-first queues 2 and 3 (zeroed before the launch)
+  const int* inv_order;     // [n_inv] the inverse's tasks in their dependency-safe order (counter[4] walks it)
+  int n_inv;
   int n_sms;                // CTAs are numbered in two waves of n_sms
   int n_chain_sms;          // CTAs with (blockIdx % n_sms) < n_chain_sms serve the chain queue
-  unsigned* counter;        // three task counters (zeroed before the launch)
+  unsigned* counter;        // per queue: next task (queues 0, 1) / first task not known to be claimed (queues 2, 3)
   // flag arrays are [(nt+1)*nt], indexed tile_row * nt + tile_col (row nt: the residual row of value_only)
   int* ready;             // L tile flags (zeroed before the launch)
   int* xready;            // X tile flags (zeroed before the launch)
@@ -259,6 +263,107 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
   cp_async_wait<0>();
 }
 
+
+// ---- ready-first claiming (inverse queues) ---------------------------------------------------
+// In-order claiming makes a CTA block inside a task whose last inputs are still being produced
+// (measured: 16 % of all CTA time at N = 4096).  The inverse's tiles and helpers therefore sit in
+// two queues with per-task claim marks: warp 0 looks at a window of 32 unclaimed candidates per
+// queue and takes one whose LAST inputs are already published (earlier inputs then are, too).
+// Only if neither queue shows a ready task does it fall back to the next unclaimed task of the
+// original dependency-safe order (a ticket counter walks it) -- which may block, exactly as in-order
+// claiming would, and keeps the no-deadlock argument: every blocking claim has all its predecessors
+// claimed.
+__device__ __forceinline__ bool inverse_task_ready(const FactorArgs& a, const FactorTask& tk) {
+  const int nt = a.nt;
+  if (tk.type == TASK_TRTRI) {  // X_rJ: last inputs X_{r-1,J}, L_{r,r-1}, X_rr and (if split) its helper's partial sum
+    const int r = tk.i, J = tk.j;
+    int f = ld_flag(a.xready + (size_t)(r - 1) * nt + J) & ld_flag(a.ready + (size_t)r * nt + (r - 1)) &
+            ld_flag(a.xready + (size_t)r * nt + r);
+    if (tk.k > J) f &= ld_flag(a.pready + (size_t)r * nt + J);
+    return f != 0;
+  }
+  // helper (r, J, k): adds tile columns [J, k): last inputs X_{k-1,J} and L_{r,k-1}
+  return (ld_flag(a.xready + (size_t)(tk.k - 1) * nt + tk.j) & ld_flag(a.ready + (size_t)tk.i * nt + (tk.k - 1))) != 0;
+}
+
+struct WindowLook {
+  unsigned lo;        // window start (the queue's low-water mark when looked at)
+  unsigned ready;     // lanes whose candidate is unclaimed and ready
+  unsigned unclaimed; // lanes whose candidate is unclaimed
+};
+
+// Executed by all 32 lanes of warp 0.
+__device__ __forceinline__ WindowLook look_window(const FactorArgs& a, int q, int lane) {
+  WindowLook w;
+  const unsigned qn = (unsigned)(a.qbase[q + 1] - a.qbase[q]);
+  for (;;) {
+    unsigned lo = 0;
+    if (lane == 0) lo = (unsigned)ld_flag(reinterpret_cast<const int*>(a.counter + q));
+    lo = __shfl_sync(0xffffffffu, lo, 0);
+    w.lo = lo;
+    w.ready = w.unclaimed = 0u;
+    if (lo >= qn) return w;
+    const unsigned idx = lo + lane;
+    bool un = false, rdy = false;
+    if (idx < qn) {
+      const unsigned g = (unsigned)a.qbase[q] + idx;
+      un = ld_flag(a.claimed + g) == 0;
+      if (un) rdy = inverse_task_ready(a, a.tasks[g]);
+    }
+    w.unclaimed = __ballot_sync(0xffffffffu, un);
+    w.ready = __ballot_sync(0xffffffffu, rdy);
+    if (w.unclaimed != 0u) return w;
+    // the whole window is claimed: move the low-water mark and look again
+    if (lane == 0) atomicMax(a.counter + q, min(lo + 32u, qn));
+    __syncwarp();
+  }
+}
+
+// Try to take candidate `pick` (lane index) of window w in queue q; returns the global task index or NONE.
+__device__ __forceinline__ unsigned take_candidate(const FactorArgs& a, int q, const WindowLook& w, int pick, int lane) {
+  unsigned got = 0xffffffffu;
+  if (lane == 0) {
+    const unsigned g = (unsigned)a.qbase[q] + w.lo + (unsigned)pick;
+    if (atomicCAS(a.claimed + g, 0, 1) == 0) {
+      got = g;
+      if (pick == __ffs(w.unclaimed) - 1) atomicMax(a.counter + q, w.lo + (unsigned)pick + 1u);  // prefix fully claimed
+    }
+  }
+  return __shfl_sync(0xffffffffu, got, 0);
+}
+
+// Claim one task from the inverse queues (2: tiles, 3: helpers).  Returns NONE when all are claimed.
+__device__ __forceinline__ unsigned claim_inverse(const FactorArgs& a, int lane) {
+#pragma unroll 1
+  for (int attempt = 0; attempt < 2; ++attempt) {
+#pragma unroll 1
+    for (int q = 2; q <= 3; ++q) {
+      const WindowLook w = look_window(a, q, lane);
+      if (w.ready == 0u) continue;
+      // spread concurrent claimers over the ready candidates
+      const int n = __popc(w.ready), want = (int)((blockIdx.x + attempt) % (unsigned)n);
+      const unsigned g = take_candidate(a, q, w, __fns(w.ready, 0, want + 1), lane);
+      if (g != 0xffffffffu) return g;
+    }
+  }
+  // Nothing ready (or lost the races): the next unclaimed task of the safe order.  Tickets walk that
+  // order exactly like in-order claiming, skipping what the ready-first path has taken.
+  unsigned got = 0xffffffffu;
+  if (lane == 0) {
+    for (;;) {
+      if (ld_flag(reinterpret_cast<const int*>(a.counter + 4)) >= a.n_inv) break;
+      const unsigned s = atomicAdd(a.counter + 4, 1u);
+      if (s >= (unsigned)a.n_inv) break;
+      const unsigned g = (unsigned)a.inv_order[s];
+      if (atomicCAS(a.claimed + g, 0, 1) == 0) {
+        got = g;
+        break;
+      }
+    }
+  }
+  return __shfl_sync(0xffffffffu, got, 0);
+}
+
 // Shared memory of one CTA (two CTAs per SM).  The finalisation buffers alias the cp.async
 // ring: they are only touched after the accumulation loop has drained it.
 template <int DP>
@@ -307,33 +412,40 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
 
   for (;;) {
     __syncthreads();  // previous task fully retired (smem reuse, s_task reuse)
-    // Three queues.  (0) the Cholesky's chain tiles (diagonal + first sub-diagonal), served by the
-    // CTAs of a few SMs reserved for them so that the latency-bound finalisations never share an FP64
-    // pipe with bulk work; (1) all other Cholesky tasks, whose CTAs run ahead along the dependency
-    // chain exactly as if the inverse were not there; (2) the inverse's tasks, whose CTAs (co-resident
-    // with the queue-1 CTAs) use the cycles the chain leaves idle.  A CTA whose queue is empty helps
-    // the others.
-    if (tid == 0) {
-      if (s_role < 0) {
+    // Queues.  (0) the Cholesky's chain tiles (diagonal + first sub-diagonal + diagonal inverse), served
+    // by a dozen CTAs in order; (1) all other Cholesky tasks in order, whose CTAs run ahead along the
+    // dependency chain exactly as if the inverse were not there; (2, 3) the inverse's tiles and helpers,
+    // claimed ready-first (claim_inverse) by CTAs co-resident with the queue-1 CTAs.  A CTA whose
+    // queue is empty helps the others.
+    if (warp == 0) {
+      if (lane == 0 && s_role < 0) {
         // A dozen CTAs serve the chain queue, the rest of the first wave the Cholesky queue, the
-        // second wave the inverse queue.  (Measured alternatives: reserving whole SMs for the chain by
+        // second wave the inverse queues.  (Measured alternatives: reserving whole SMs for the chain by
         // %smid -- 6 or 12 SMs, band of 1 or 3 sub-diagonals -- made its tile factorisations 25 %
         // faster but lost more in look-ahead and bulk capacity: 307-314 vs 321 evals/s at N = 4096.)
         const int slot = (int)(blockIdx.x % (unsigned)a.n_sms);
         s_role = (slot < a.n_chain_sms) ? 0 : ((blockIdx.x < (unsigned)a.n_sms || a.value_only) ? 1 : 2);
       }
+      __syncwarp();
       const int role = s_role;
       unsigned tk0 = 0xffffffffu;
 #pragma unroll 1
       for (int attempt = 0; attempt < 3 && tk0 == 0xffffffffu; ++attempt) {
         const int q = (role + attempt) % 3;
-        const unsigned qn = (unsigned)(a.qbase[q + 1] - a.qbase[q]);
-        if (ld_flag(reinterpret_cast<const int*>(a.counter + q)) < (int)qn) {
-          const unsigned k = atomicAdd(a.counter + q, 1u);
-          if (k < qn) tk0 = (unsigned)a.qbase[q] + k;
+        if (q == 2) {
+          tk0 = claim_inverse(a, lane);
+        } else {
+          if (lane == 0) {
+            const unsigned qn = (unsigned)(a.qbase[q + 1] - a.qbase[q]);
+            if (ld_flag(reinterpret_cast<const int*>(a.counter + q)) < (int)qn) {
+              const unsigned k = atomicAdd(a.counter + q, 1u);
+              if (k < qn) tk0 = (unsigned)a.qbase[q] + k;
+            }
+          }
+          tk0 = __shfl_sync(0xffffffffu, tk0, 0);
         }
       }
-      s_task = tk0;
+      if (lane == 0) s_task = tk0;
     }
     __syncthreads();
     const unsigned task = s_task;
