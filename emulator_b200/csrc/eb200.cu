@@ -442,18 +442,30 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
     // columns [J, k), the tile's own task adds the last MAIN_K and finalises.  This moves most of
     // the work of the last rows -- the tail of the launch -- into the time the Cholesky chain
     // leaves SMs idle.
-    const int MAIN_K = 12, MIN_PART = 8;
+    // (Measured: cutting a tile's helper into chained chunks of 8 tile columns, each claimable as soon as
+    //  its inputs exist, fills the starved first 300 us but makes the chunks wait on one another later:
+    //  3.11 ms per evaluation against 3.00 ms with one helper per tile.)
+    const int MAIN_K = 12, MIN_PART = 8, INV_CHUNK = 1 << 20;
     // The dependency-safe total order is row by row, a row's tiles followed by the helpers whose inputs
     // exist once that row is done; `seq` records it.  Tiles go to queue 2 and helpers to queue 3, both
     // claimed ready-first (factor_dataflow.cuh), falling back to this order.
     std::vector<std::vector<FactorTask>> after_row(nt);
     for (int r = 1; r < nt; ++r)
       for (int J = 0; J < r; ++J)
-        if (r - J > MAIN_K + MIN_PART) after_row[r - MAIN_K - 1].push_back({TASK_TRTRI_PART, r, J, r - MAIN_K, 0});
+        if (r - J > MAIN_K + MIN_PART) {
+          // helper chunks [c0, c1) of INV_CHUNK tile columns, each listed once row c1 - 1 of X exists
+          const int end = r - MAIN_K;
+          for (int c0 = J; c0 < end;) {
+            int c1 = std::min(c0 + INV_CHUNK, end);
+            if (end - c1 < INV_CHUNK / 2) c1 = end;  // no tiny last chunk
+            after_row[c1 - 1].push_back({TASK_TRTRI_PART, r, J, c1, 0, c0});
+            c0 = c1;
+          }
+        }
     std::vector<FactorTask> mains, helpers;
     int seq = 0;
     for (int r = 1; r < nt; ++r) {
-      for (int J = 0; J < r; ++J) mains.push_back({TASK_TRTRI, r, J, (r - J > MAIN_K + MIN_PART) ? r - MAIN_K : J, seq++});
+      for (int J = 0; J < r; ++J) mains.push_back({TASK_TRTRI, r, J, (r - J > MAIN_K + MIN_PART) ? r - MAIN_K : J, seq++, 0});
       for (auto& tk : after_row[r]) {
         tk.seq = seq++;
         helpers.push_back(tk);

@@ -36,9 +36,11 @@ constexpr int TS = 66;                 // stride of a parked accumulator used as
 constexpr int TSK = 72;                // stride of a parked accumulator used as a [m][k] operand (LDS.128 fragments)
 constexpr int NEAR_BAND = 2;           // tiles (j+1..j+NEAR_BAND, j) cannot wait for X_jj: they follow L_jj's panels
 
-// TASK_TRTRI_PART (r, J, k): helper that pre-accumulates sum_{K=J}^{k-1} L_rK X_KJ of a long inverse
-// tile into the (unused) mirrored upper tile of X, so that the tile's own task (k = first tile column
-// it still has to add) is short when the last rows of the inverse form the tail of the launch.
+// TASK_TRTRI_PART (r, J, [k0, k)): helper that adds sum_{K=k0}^{k-1} L_rK X_KJ of a long inverse tile to
+// the partial sum kept in the (unused) mirrored upper tile of X.  A tile's helpers form a chain of
+// chunks, each claimable as soon as row k-1 of X exists, so the bulk of the last rows of the inverse
+// -- the tail of the launch -- is done while the Cholesky chain leaves the SMs idle, and the tile's
+// own task (k = first tile column it still has to add) is short.
 // TASK_POTRF_PART (i, j, k): the same idea for the Cholesky: sum_{c<k} L_ic L_jc^T of tile (i, j) is
 // pre-accumulated by a background task listed several block columns ahead and parked in the tile's
 // own (not yet published) storage, so that the tile's task -- which near the diagonal sits on or
@@ -50,6 +52,7 @@ enum FactorTaskType : int { TASK_POTRF = 0, TASK_TRTRI = 1, TASK_TRTRI_PART = 2,
 struct FactorTask {
   int type, i, j, k;
   int seq;  // position in the dependency-safe total order of the inverse's tasks (ready-first queues)
+  int k0;   // helpers of the inverse: first tile column of this chunk (the chunk adds [k0, k))
 };
 
 struct FactorArgs {
@@ -119,11 +122,11 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 }
 
 // Lane 0 of every warp polls; returns false if the watchdog fired.
-__device__ __forceinline__ bool wait_ready(const int* flag, int* abort_flag) {
+__device__ __forceinline__ bool wait_ready(const int* flag, int* abort_flag, int need = 1) {
   bool ok = true;
   if ((threadIdx.x & 31) == 0) {
     long long spins = 0;
-    while (ld_flag(flag) == 0) {
+    while (ld_flag(flag) < need) {
       __nanosleep(20);
       if ((++spins & 0x3ff) == 0) {
         if (spins > (1ll << 24) || ld_flag(abort_flag) != 0) {  // ~1 s
@@ -149,11 +152,11 @@ __device__ __forceinline__ void yield_to_chain(const int* sm_flag) {
 
 // Publish a tile: all of the CTA's stores happen-before the barrier, thread 0's cumulative
 // device-scope fence orders them before the flag.
-__device__ __forceinline__ int publish(int* flag, bool ok) {
+__device__ __forceinline__ int publish(int* flag, bool ok, int value = 1) {
   const int all_ok = __syncthreads_and(ok ? 1 : 0);
   if (threadIdx.x == 0) {
     __threadfence();
-    st_release(flag, 1);
+    st_release(flag, value);
   }
   return all_ok;
 }
@@ -279,11 +282,13 @@ __device__ __forceinline__ bool inverse_task_ready(const FactorArgs& a, const Fa
     const int r = tk.i, J = tk.j;
     int f = ld_flag(a.xready + (size_t)(r - 1) * nt + J) & ld_flag(a.ready + (size_t)r * nt + (r - 1)) &
             ld_flag(a.xready + (size_t)r * nt + r);
-    if (tk.k > J) f &= ld_flag(a.pready + (size_t)r * nt + J);
+    if (f != 0 && tk.k > J) f = ld_flag(a.pready + (size_t)r * nt + J) >= tk.k;
     return f != 0;
   }
-  // helper (r, J, k): adds tile columns [J, k): last inputs X_{k-1,J} and L_{r,k-1}
-  return (ld_flag(a.xready + (size_t)(tk.k - 1) * nt + tk.j) & ld_flag(a.ready + (size_t)tk.i * nt + (tk.k - 1))) != 0;
+  // helper (r, J, [k0, k)): last inputs X_{k-1,J} and L_{r,k-1}, and the previous chunk's partial sum
+  int f = ld_flag(a.xready + (size_t)(tk.k - 1) * nt + tk.j) & ld_flag(a.ready + (size_t)tk.i * nt + (tk.k - 1));
+  if (f != 0 && tk.k0 > tk.j) f = ld_flag(a.pready + (size_t)tk.i * nt + tk.j) >= tk.k0;
+  return f != 0;
 }
 
 struct WindowLook {
@@ -520,11 +525,12 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     if (tk.type != TASK_POTRF) {
       // =====================  X_rJ = -X_rr * sum_{K=J}^{r-1} L_rK X_KJ  =====================
       const bool part = tk.type == TASK_TRTRI_PART;
-      const int kbeg = part ? tj : tk.k;   // first tile column this task adds
-      const int kend = part ? tk.k : ti;   // one past the last
+      const int kbeg = part ? tk.k0 : tk.k;  // first tile column this task adds
+      const int kend = part ? tk.k : ti;     // one past the last
       double* scratch = a.W + (size_t)j0 * ld + i0;  // mirrored upper tile (J, r): never read as X
-      if (!part && kbeg > tj) {
-        ok = wait_ready(a.pready + (size_t)ti * nt + tj, a.abort_flag) && ok;
+      if (kbeg > tj) {
+        // the helpers of a tile form a chain; pready holds the number of tile columns summed so far
+        ok = wait_ready(a.pready + (size_t)ti * nt + tj, a.abort_flag, kbeg) && ok;
 #pragma unroll
         for (int mi = 0; mi < CfgP::MI; ++mi)
 #pragma unroll
@@ -555,7 +561,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
             *reinterpret_cast<double2*>(scratch + (size_t)(wm0 + mi * 8 + g) * ld + wn0 + ni * 8 + 2 * t) = val;
           }
         EB_STAMP(4);
-        const int part_ok = publish(a.pready + (size_t)ti * nt + tj, ok);
+        const int part_ok = publish(a.pready + (size_t)ti * nt + tj, ok, kend);
         EB_STAMP(5);
         if (!part_ok) break;
         continue;

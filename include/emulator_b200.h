@@ -93,7 +93,7 @@ int eb200_gp_eval_launches(const eb200_gp* gp, int mode);
 /* Per-task globaltimer stamps (ns) of the dataflow factorisation kernel: out[task][10] =
  * {claimed, K generated / panels accumulated, C formed / diagonal inverse visible, diagonal
  * factor visible, tile stored, published, SM id, CTA id, ns spent waiting for input flags, ns yielded
- * to chain tiles}; tasks_out[task][5] = (type 0 Cholesky / 1 inverse / 2, 3 helpers / 4 diagonal inverse,
+ * to chain tiles}; tasks_out[task][6] = (type 0 Cholesky / 1 inverse / 2, 3 helpers / 4 diagonal inverse,
  * tile row, tile column, 0).  The number of tasks is eb200_gp_factor_tasks(). */
 int eb200_gp_debug_factor_trace(eb200_gp* gp, const double* p_host, unsigned long long* out_host, int* tasks_out);
 int eb200_gp_factor_tasks(const eb200_gp* gp);

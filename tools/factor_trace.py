@@ -16,7 +16,7 @@ gp.evaluate(p, True)
 nt = gp.padded_n // 64
 ntasks = (gp._lib.eb200_gp_value_tasks if value_only else gp._lib.eb200_gp_factor_tasks)(gp.handle)
 trace_fn = gp._lib.eb200_gp_debug_value_trace if value_only else gp._lib.eb200_gp_debug_factor_trace
-out = np.zeros((ntasks, 10), dtype=np.uint64); tasks = np.zeros((ntasks, 5), dtype=np.int32)
+out = np.zeros((ntasks, 10), dtype=np.uint64); tasks = np.zeros((ntasks, 6), dtype=np.int32)
 for rep in range(2):
     _lib.check(trace_fn(gp.handle, _lib.as_double_ptr(p), out.ctypes.data_as(ctypes.POINTER(ctypes.c_ulonglong)),
                                                     tasks.ctypes.data_as(ctypes.POINTER(ctypes.c_int))), "trace")

@@ -13,7 +13,7 @@ for ty in range(5):
     i, j, k = tasks[m, 1], tasks[m, 2], tasks[m, 3]
     if ty == 0: prods = j - k
     elif ty == 1: prods = i - np.where(k > j, k, j) + 1  # + the finalisation product
-    elif ty == 2: prods = k - j
+    elif ty == 2: prods = k - (tasks[m, 5] if tasks.shape[1] > 5 else j)
     elif ty == 3: prods = k
     else: prods = np.zeros(m.sum())
     dur = t[m, 5] - t[m, 0]
