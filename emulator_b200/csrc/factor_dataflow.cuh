@@ -141,6 +141,29 @@ __device__ __forceinline__ bool wait_ready(const int* flag, int* abort_flag, int
   return ok;
 }
 
+// The same for two flags at once (f2 may be null): one L2 round trip per poll instead of two.
+__device__ __forceinline__ bool wait_ready2(const int* f1, const int* f2, int* abort_flag) {
+  bool ok = true;
+  if ((threadIdx.x & 31) == 0) {
+    long long spins = 0;
+    for (;;) {
+      const int v1 = ld_flag(f1);
+      const int v2 = (f2 != nullptr) ? ld_flag(f2) : 1;
+      if (v1 != 0 && v2 != 0) break;
+      __nanosleep(20);
+      if ((++spins & 0x3ff) == 0) {
+        if (spins > (1ll << 24) || ld_flag(abort_flag) != 0) {
+          atomicExch(abort_flag, 1);
+          ok = false;
+          break;
+        }
+      }
+    }
+  }
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  return ok;
+}
+
 // Background work stands aside while a chain tile is being finalised on this SM.
 __device__ __forceinline__ void yield_to_chain(const int* sm_flag) {
   if ((threadIdx.x & 31) == 0) {
@@ -193,14 +216,16 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
   };
   rescan(0);
   auto issue = [&](int kt) {
+    int look_from = -1;
     if ((kt & 3) == 0) {
       const int kc = kt >> 2;
       if (kc >= known) {
+        // at the dependency frontier every L2 round trip is on the critical path: both flags are
+        // polled together, and the look at the following columns waits until the loads are out
         const unsigned long long w0 = waited ? gtime() : 0ull;
-        ok = wait_ready(fa + (size_t)kc * sa, abort_flag) && ok;
-        if (fb != nullptr) ok = wait_ready(fb + (size_t)kc * sb, abort_flag) && ok;
+        ok = wait_ready2(fa + (size_t)kc * sa, fb != nullptr ? fb + (size_t)kc * sb : nullptr, abort_flag) && ok;
         if (waited) *waited += gtime() - w0;
-        rescan(kc + 1);  // producers usually publish several tile columns while we wait
+        look_from = kc + 1;
       }
     }
     double* stage = pipe + (kt % PSTAGES) * PSTAGE_DOUBLES;
@@ -208,6 +233,7 @@ __device__ __forceinline__ void accumulate_flagged(double (&acc)[CfgP::MI][CfgP:
     const double* bp = (LB == KCONTIG) ? Bg + (size_t)kt * KC : Bg + (size_t)kt * KC * ldb;
     E::template load_operand<64, KCONTIG>(stage, ap, lda, tid);
     E::template load_operand<64, LB>(stage + E::SA::DOUBLES, bp, ldb, tid);
+    if (look_from >= 0) rescan(look_from);  // producers usually publish several tile columns while we wait
   };
   // Ring of PSTAGES = 4 stages, two chunks (one "pair") per barrier.  While pair kt is in the math,
   // pair kt+2 is in flight into the other two stages: it is issued right after the barrier whenever
