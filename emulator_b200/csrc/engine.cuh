@@ -43,7 +43,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-template <int ROWS, int LAYOUT>
+template <int ROWS, int LAYOUT, bool PERMK = true>
 struct OperandSmem;
 
 // Fragments of N 8-row blocks for two consecutive DMMAs: f[0][i] = op(row0 + 8i, k0), f[1][i] = op(row0 + 8i, k0 + 1).
@@ -62,9 +62,13 @@ __device__ __forceinline__ void load_fragments(double (&f)[2][N], const double* 
   }
 }
 
-template <int ROWS, int LAYOUT>
+// PERMK = false keeps the plain k order (lane t feeds k = t): strides [rows][KC+4] / [KC][rows+4], one
+// 8-byte load per DMMA operand.  Measured on B200: the permutation gains 12 % on the 64x64 KCONTIG loop
+// (fewer shared loads per DMMA), nothing on the 128x128 KCONTIG tile, and costs the MCONTIG x MCONTIG
+// tile of the K^-1 pass 4 % (no 16-byte loads to gain, coarser interleaving), which therefore opts out.
+template <int ROWS, int LAYOUT, bool PERMK>
 struct OperandSmem {
-  static constexpr int STRIDE = (LAYOUT == KCONTIG) ? (KC + 8) : (ROWS + 2);
+  static constexpr int STRIDE = PERMK ? ((LAYOUT == KCONTIG) ? (KC + 8) : (ROWS + 2)) : ((LAYOUT == KCONTIG) ? (KC + 4) : (ROWS + 4));
   static constexpr int DOUBLES = (LAYOUT == KCONTIG) ? ROWS * STRIDE : KC * STRIDE;
 };
 
@@ -78,17 +82,17 @@ struct TileCfg {
 };
 using Cfg128 = TileCfg<128, 128, 64, 32>;  // 256 threads, 64 accumulator doubles / thread
 
-template <class Cfg, int LA, int LB>
+template <class Cfg, int LA, int LB, bool PERMK = true>
 struct Engine {
-  using SA = OperandSmem<Cfg::BM, LA>;
-  using SB = OperandSmem<Cfg::BN, LB>;
+  using SA = OperandSmem<Cfg::BM, LA, PERMK>;
+  using SB = OperandSmem<Cfg::BN, LB, PERMK>;
   static constexpr int STAGE_DOUBLES = SA::DOUBLES + SB::DOUBLES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);
 
   // Stage one ROWS x KC operand slab into shared memory with 16-byte cp.async.
   template <int ROWS, int LAYOUT>
   static __device__ __forceinline__ void load_operand(double* s, const double* g, int ld, int tid) {
-    constexpr int STRIDE = OperandSmem<ROWS, LAYOUT>::STRIDE;
+    constexpr int STRIDE = OperandSmem<ROWS, LAYOUT, PERMK>::STRIDE;
     if (LAYOUT == KCONTIG) {
       constexpr int CHUNKS = ROWS * (KC / 2);
 #pragma unroll
@@ -147,17 +151,38 @@ struct Engine {
         for (int h = 0; h < 2; ++h) {
           const double* sA = smem + ((kt + h) % STAGES) * STAGE_DOUBLES;
           const double* sB = sA + SA::DOUBLES;
+          if (PERMK) {
 #pragma unroll
-          for (int kk = 0; kk < KC; kk += 8) {
-            double af[2][Cfg::MI], bf[2][Cfg::NI];
-            load_fragments<LA, Cfg::MI>(af, sA, SA::STRIDE, wm0 + g, kk + 2 * t);
-            load_fragments<LB, Cfg::NI>(bf, sB, SB::STRIDE, wn0 + g, kk + 2 * t);
+            for (int kk = 0; kk < KC; kk += 8) {
+              double af[2][Cfg::MI], bf[2][Cfg::NI];
+              load_fragments<LA, Cfg::MI>(af, sA, SA::STRIDE, wm0 + g, kk + 2 * t);
+              load_fragments<LB, Cfg::NI>(bf, sB, SB::STRIDE, wn0 + g, kk + 2 * t);
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2)
+              for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+                for (int mi = 0; mi < Cfg::MI; ++mi)
+#pragma unroll
+                  for (int ni = 0; ni < Cfg::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[h2][mi], bf[h2][ni]);
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < KC; kk += 4) {
+              double af[Cfg::MI], bf[Cfg::NI];
+#pragma unroll
+              for (int mi = 0; mi < Cfg::MI; ++mi) {
+                const int row = wm0 + mi * 8 + g;
+                af[mi] = (LA == KCONTIG) ? sA[row * SA::STRIDE + kk + t] : sA[(kk + t) * SA::STRIDE + row];
+              }
+#pragma unroll
+              for (int ni = 0; ni < Cfg::NI; ++ni) {
+                const int col = wn0 + ni * 8 + g;
+                bf[ni] = (LB == KCONTIG) ? sB[col * SB::STRIDE + kk + t] : sB[(kk + t) * SB::STRIDE + col];
+              }
 #pragma unroll
               for (int mi = 0; mi < Cfg::MI; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < Cfg::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[h2][mi], bf[h2][ni]);
+                for (int ni = 0; ni < Cfg::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+            }
           }
         }
       }

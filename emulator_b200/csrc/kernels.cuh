@@ -218,7 +218,7 @@ struct LauumSmem {
   static constexpr int RED_OFF = INV_OFF + DP;
   static constexpr int DOUBLES = RED_OFF + 8 * (DP + 1);
   static constexpr int EPI_BYTES = DOUBLES * (int)sizeof(double);
-  static constexpr int ENGINE_BYTES = Engine<Cfg128, MCONTIG, MCONTIG>::SMEM_BYTES;
+  static constexpr int ENGINE_BYTES = Engine<Cfg128, MCONTIG, MCONTIG, false>::SMEM_BYTES;
   static constexpr int BYTES = EPI_BYTES > ENGINE_BYTES ? EPI_BYTES : ENGINE_BYTES;
 };
 
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) lauum_trace_kernel(const TileTask* __rest
                                                            double* __restrict__ partial, double* kinv_out) {
   extern __shared__ __align__(16) double gsm[];
   using Cfg = Cfg128;
-  using E = Engine<Cfg, MCONTIG, MCONTIG>;
+  using E = Engine<Cfg, MCONTIG, MCONTIG, false>;  // plain k order: see OperandSmem
   using SM = LauumSmem<DP>;
   constexpr int XS = SM::XS;
   const TileTask tk = tasks[blockIdx.x];
