@@ -375,10 +375,19 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
     out[1 + d + 2] = ld;
     out[1 + d + 3] = quad;
   }
-  if (want_grad && threadIdx.x <= d) {
-    double v = 0.0;
-    for (int k = 0; k < ntask; ++k) v += partial[(size_t)k * (dp + 1) + threadIdx.x];
-    out[1 + threadIdx.x] = 0.5 * v;
+  // gradient: component c is summed by 8 threads over interleaved tasks, then combined in fixed
+  // order (deterministic; 528 serial dependent loads by one thread took 30 us)
+  __syncthreads();
+  const int c = threadIdx.x >> 3, part = threadIdx.x & 7;
+  double v = 0.0;
+  if (want_grad && c <= d)
+    for (int k = part; k < ntask; k += 8) v += partial[(size_t)k * (dp + 1) + c];
+  red[threadIdx.x] = v;
+  __syncthreads();
+  if (want_grad && part == 0 && c <= d) {
+    double sum = 0.0;
+    for (int q = 0; q < 8; ++q) sum += red[threadIdx.x + q];
+    out[1 + c] = 0.5 * sum;
   }
 }
 
