@@ -62,4 +62,21 @@ for _ in range(3): gp.evaluate(p, True)
 ms = (time.perf_counter() - t0) / 3 * 1e3
 out["eval_C4_N8176"] = {"ms": ms, "tflops": 8176.0 ** 3 / ms / 1e9, "projected_refit_s_at_150_evals": 150 * ms / 1e3,
                         "projected_loo_512_refits_8gpu_min": 512 * 150 * ms / 1e3 / 8 / 60}
+gp.close()
+# ---- value-only evaluations (what the ensemble sampler asks for): Cholesky factor alone ----
+for n_, d_ in ((4096, 9), (8176, 9), (256, 8)):
+    x, y, yerr = synthetic.design_arrays(n_, d_, seed=1239)
+    noise = np.sqrt(np.ascontiguousarray(yerr ** 2, dtype=np.float64) + 1.25e-12) ** 2
+    gp = DeviceProblem(x.astype(np.float64), noise); gp.set_residual(y.astype(np.float64))
+    p = synthetic.perturbed_parameter_vectors(d_, 1)[0]
+    res = {}
+    for kind, kw in (("value_only", dict(want_grad=False, value_only=True)), ("lml_with_prediction_state", dict(want_grad=False)),
+                     ("lml_and_grad", dict(want_grad=True))):
+        gp.evaluate(p, **kw)
+        reps = 20 if n_ <= 4096 else 5
+        t0 = time.perf_counter()
+        for _ in range(reps): gp.evaluate(p, **kw)
+        res[kind + "_ms"] = (time.perf_counter() - t0) / reps * 1e3
+    out[f"eval_modes_N{n_}"] = res
+    gp.close()
 print(json.dumps(out, indent=1))
