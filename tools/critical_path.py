@@ -18,7 +18,7 @@ pub = lambda key: t[idx[key], 5]
 
 
 def inputs(k):
-    ty, i, j, kk = (int(v) for v in tasks[k])
+    ty, i, j, kk = (int(v) for v in tasks[k][:4])
     res = []
     if ty == 0:      # L_ij: needs L_ik, L_jk for k in [kbeg, j), the partial, and the diagonal tile
         for c in range(kk, j):
@@ -48,7 +48,7 @@ while True:
     if not ins:
         break
     last = max(ins, key=pub)
-    ty, i, j, kk = (int(v) for v in tasks[k])
+    ty, i, j, kk = (int(v) for v in tasks[k][:4])
     own = t[k, 5] - max(t[k, 0], pub(last))
     path.append((NAMES[ty], i, j, t[k, 0], pub(last), t[k, 2], t[k, 5], own, last))
     k = idx[last]
