@@ -94,6 +94,17 @@ struct eb200_gp {
   int n_ftasks = 0, qbase[5] = {0, 0, 0, 0, 0};
   int* inv_order = nullptr;  // the inverse's tasks (indices into ftasks) in their dependency-safe order
   int n_inv = 0;
+  // State of batched value-only evaluations (allocated on first use).  Problem 0 factorises in the handle's
+  // own matrix, problems 1.. in matrices of their own; the small per-problem arrays are contiguous so that
+  // one memset, one copy and one launch serve the whole batch.
+  struct BatchState {
+    double* A[MAX_BATCH] = {nullptr};
+    double *Xd = nullptr, *logdet = nullptr, *rdiag = nullptr, *out = nullptr, *p_dev = nullptr;  // [MAX_BATCH][..]
+    int* zeroed = nullptr;  // [MAX_BATCH] x (flags | counters (8) | info, abort (2)), cleared per batch
+    KernelParams* kp = nullptr;
+    double* h_stage = nullptr;  // pinned: MAX_BATCH parameter vectors + results
+    int slots = 0;             // matrices allocated so far
+  } batch;
   FactorTask* ftasks_v = nullptr;  // value-only list: Cholesky tiles + the residual row
   int n_ftasks_v = 0;
   int qbase_v[5] = {0, 0, 0, 0, 0};
@@ -196,6 +207,24 @@ void build_program(eb200_gp* h, std::vector<TileTask>& tasks) {
   }
 }
 
+// The dataflow kernel's arguments for the handle's own state (slot 0).
+void fill_factor_args(eb200_gp* h, bool vo, FactorArgs& fa) {
+  const int np = h->np;
+  const size_t nf = (size_t)(h->nt + 1) * h->nt;
+  fa.A = h->A; fa.W = h->W; fa.ld = np; fa.nt = h->nt; fa.n = h->n; fa.X = h->X; fa.noise = h->noise; fa.kp = h->kp;
+  fa.Xd = h->W; fa.xd_tile = (long long)TB * np + TB; fa.xd_ld = np;
+  fa.value_only = vo ? 1 : 0; fa.r = h->r;
+  fa.tasks = vo ? h->ftasks_v : h->ftasks; fa.ntasks = vo ? h->n_ftasks_v : h->n_ftasks;
+  for (int q = 0; q < 5; ++q) fa.qbase[q] = vo ? h->qbase_v[q] : h->qbase[q];
+  fa.counter = h->counter; fa.ready = h->ready; fa.xready = fa.ready + nf; fa.pready = fa.xready + nf;
+  fa.cready = fa.pready + nf; fa.lready = fa.cready + nf; fa.sm_chain = fa.lready + 8 * h->nt; fa.claimed = fa.sm_chain + 512;
+  fa.inv_order = h->inv_order; fa.n_inv = vo ? 0 : h->n_inv;
+  fa.logdet_part = h->logdet_part; fa.rdiag = h->rdiag; fa.info = h->info; fa.abort_flag = h->abort_flag;
+  fa.trace = h->trace;
+  fa.n_sms = h->n_sms;
+  fa.n_chain_sms = 1;
+}
+
 // Enqueue one op.  Returns number of kernel launches issued.
 int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int mode, double* kinv_out) {
   const int want_grad = mode == EB200_EVAL_GRAD;
@@ -213,21 +242,15 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int mode, double* kinv
       cudaMemsetAsync(h->counter, 0, 8 * sizeof(unsigned), st);
       // ready, xready, pready, cready, lready, sm_chain, claimed
       cudaMemsetAsync(h->ready, 0, (4 * nf + 8 * h->nt + 512 + (size_t)h->n_ftasks) * sizeof(int), st);
-      FactorArgs fa;
-      fa.A = h->A; fa.W = h->W; fa.ld = np; fa.nt = h->nt; fa.n = h->n; fa.X = h->X; fa.noise = h->noise; fa.kp = h->kp;
-      fa.value_only = vo ? 1 : 0; fa.r = h->r;
-      fa.tasks = vo ? h->ftasks_v : h->ftasks; fa.ntasks = vo ? h->n_ftasks_v : h->n_ftasks;
-      for (int q = 0; q < 5; ++q) fa.qbase[q] = vo ? h->qbase_v[q] : h->qbase[q];
-      fa.counter = h->counter; fa.ready = h->ready; fa.xready = fa.ready + nf; fa.pready = fa.xready + nf;
-      fa.cready = fa.pready + nf; fa.lready = fa.cready + nf; fa.sm_chain = fa.lready + 8 * h->nt; fa.claimed = fa.sm_chain + 512; fa.inv_order = h->inv_order; fa.n_inv = vo ? 0 : h->n_inv;
-      fa.logdet_part = h->logdet_part; fa.rdiag = h->rdiag; fa.info = h->info; fa.abort_flag = h->abort_flag;
-      fa.trace = h->trace;
+      FactorBatch fb;
+      fb.nb = 1;
+      FactorArgs& fa = fb.p[0];
+      fill_factor_args(h, vo, fa);
       // two CTAs per SM: the first wave (one per SM) serves the Cholesky queue, the second the inverse
       const int grid = std::min(2 * h->n_sms, fa.ntasks);
       // at least one CTA always serves the chain queue, never so many that the other queues starve
-      fa.n_sms = h->n_sms;
       fa.n_chain_sms = std::max(1, std::min({6, h->nt / 8, grid / 4}));
-      DP_SWITCH(h->dp, (factor_dataflow_kernel<DP><<<grid, 256, FactorSmem<DP>::BYTES, st>>>(fa)));
+      DP_SWITCH(h->dp, (factor_dataflow_kernel<DP, false><<<grid, 256, FactorSmem<DP>::BYTES, st>>>(fb)));
       return 1;
     }
     case OP_TRMV:
@@ -293,7 +316,9 @@ int set_attrs() {
   CK(cudaFuncSetAttribute(var_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES));
 #define SET_POTRF(DPV)                                                                                       \
-  CK(cudaFuncSetAttribute(factor_dataflow_kernel<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+  CK(cudaFuncSetAttribute(factor_dataflow_kernel<DPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                          FactorSmem<DPV>::BYTES));                                                        \
+  CK(cudaFuncSetAttribute(factor_dataflow_kernel<DPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                           FactorSmem<DPV>::BYTES));
   SET_POTRF(2) SET_POTRF(3) SET_POTRF(4) SET_POTRF(5) SET_POTRF(6) SET_POTRF(8) SET_POTRF(9) SET_POTRF(10)
   SET_POTRF(12) SET_POTRF(16)
@@ -550,6 +575,14 @@ int eb200_gp_destroy(eb200_gp* h) {
                  h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ftasks, h->ftasks_v, h->inv_order, h->counter, h->ready, h->abort_flag, h->rdiag};
   for (void* p : dev)
     if (p) cudaFree(p);
+  {
+    eb200_gp::BatchState& bs = h->batch;
+    for (int b = 1; b < bs.slots; ++b) cudaFree(bs.A[b]);
+    void* own[] = {bs.Xd, bs.logdet, bs.rdiag, bs.out, bs.p_dev, bs.zeroed, bs.kp};
+    for (void* q : own)
+      if (q) cudaFree(q);
+    if (bs.h_stage) cudaFreeHost(bs.h_stage);
+  }
   if (h->h_p) cudaFreeHost(h->h_p);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->h_pred) cudaFreeHost(h->h_pred);
@@ -617,6 +650,75 @@ int eb200_gp_eval_host(eb200_gp* h, const double* p_host, int mode, double* resu
   if (mode != EB200_EVAL_GRAD)
     for (int i = 0; i <= h->d; ++i) result_host[1 + i] = 0.0;
   h->factor_valid = mode != EB200_EVAL_VALUE_ONLY;
+  return 0;
+}
+
+// nb value-only evaluations whose factorisations share launches, MAX_BATCH at a time.
+int eb200_gp_eval_value_batch_host(eb200_gp* h, int nb, const double* p_host, double* result_host) {
+  if (!h || !p_host || !result_host || nb < 1) return fail("eval_value_batch: bad argument");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int np = h->np, nt = h->nt, P = h->d + 1, len = EB200_RESULT_LEN(h->d);
+  const size_t nf = (size_t)(nt + 1) * nt;
+  const size_t flag_ints = 4 * nf + 8 * nt + 512 + (size_t)h->n_ftasks;
+  const size_t zero_ints = flag_ints + 8 + 2;  // per problem: flags, 8 counters, info + abort flag
+  const int PS_ = MAXD + 1, OS_ = MAXD + 8;    // strides of the parameter / result arrays
+  eb200_gp::BatchState& bs = h->batch;
+  if (!bs.zeroed) {
+    CK(cudaMalloc(&bs.zeroed, (size_t)MAX_BATCH * zero_ints * sizeof(int)));
+    CK(cudaMalloc(&bs.Xd, (size_t)MAX_BATCH * nt * TB * TB * sizeof(double)));
+    CK(cudaMalloc(&bs.logdet, (size_t)MAX_BATCH * nt * sizeof(double)));
+    CK(cudaMalloc(&bs.rdiag, (size_t)MAX_BATCH * np * sizeof(double)));
+    CK(cudaMalloc(&bs.out, (size_t)MAX_BATCH * OS_ * sizeof(double)));
+    CK(cudaMalloc(&bs.p_dev, (size_t)MAX_BATCH * PS_ * sizeof(double)));
+    CK(cudaMalloc(&bs.kp, (size_t)MAX_BATCH * sizeof(KernelParams)));
+    CK(cudaMallocHost(&bs.h_stage, (size_t)MAX_BATCH * (PS_ + OS_) * sizeof(double)));
+    bs.A[0] = h->A;
+    bs.slots = 1;
+  }
+  double* stage_p = bs.h_stage;
+  double* stage_out = bs.h_stage + (size_t)MAX_BATCH * PS_;
+  for (int g0 = 0; g0 < nb; g0 += MAX_BATCH) {
+    const int m = std::min(MAX_BATCH, nb - g0);
+    for (; bs.slots < m; ++bs.slots) {
+      CK(cudaMalloc(&bs.A[bs.slots], ((size_t)np + TB) * np * sizeof(double)));
+      CK(cudaMemset(bs.A[bs.slots], 0, ((size_t)np + TB) * np * sizeof(double)));
+    }
+    FactorBatch fb;
+    fb.nb = m;
+    ValueBatchPtrs zs;
+    const int grid = std::min(2 * h->n_sms, m * h->n_ftasks_v);
+    for (int b = 0; b < m; ++b) {
+      memcpy(stage_p + (size_t)b * PS_, p_host + (size_t)(g0 + b) * P, P * sizeof(double));
+      int* zb = bs.zeroed + (size_t)b * zero_ints;
+      FactorArgs& fa = fb.p[b];
+      fill_factor_args(h, true, fa);
+      fa.A = bs.A[b]; fa.kp = bs.kp + b;
+      fa.ready = zb; fa.xready = fa.ready + nf; fa.pready = fa.xready + nf; fa.cready = fa.pready + nf;
+      fa.lready = fa.cready + nf;
+      fa.sm_chain = bs.zeroed + 4 * nf + 8 * nt;  // one priority flag per SM, shared by the batch (problem 0's)
+      fa.claimed = fa.lready + 8 * nt + 512;
+      fa.counter = reinterpret_cast<unsigned*>(zb + flag_ints);
+      fa.info = zb + flag_ints + 8; fa.abort_flag = fa.info + 1;
+      fa.Xd = bs.Xd + (size_t)b * nt * TB * TB; fa.xd_tile = (long long)TB * TB; fa.xd_ld = TB;
+      fa.logdet_part = bs.logdet + (size_t)b * nt; fa.rdiag = bs.rdiag + (size_t)b * np;
+      fa.trace = nullptr;
+      fa.n_chain_sms = std::max(1, std::min({8, nt / 4, (grid / m) / 4}));
+      zs.z[b] = bs.A[b] + (size_t)np * np;
+    }
+    CK(cudaMemcpyAsync(bs.p_dev, stage_p, (size_t)m * PS_ * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(bs.zeroed, 0, (size_t)m * zero_ints * sizeof(int), st));
+    prep_params_kernel<<<m, 32, 0, st>>>(bs.p_dev, h->d, bs.kp, PS_);
+    DP_SWITCH(h->dp, (factor_dataflow_kernel<DP, true><<<grid, 256, FactorSmem<DP>::BYTES, st>>>(fb)));
+    // info lives at a fixed offset inside each problem's zeroed block: hand the reduction a strided view
+    finalize_value_batch_kernel<<<m, 256, 0, st>>>(bs.logdet, nt, zs, h->n, h->d,
+                                                   bs.zeroed + flag_ints + 8, bs.out, OS_, (int)zero_ints);
+    CK(cudaMemcpyAsync(stage_out, bs.out, (size_t)m * OS_ * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    for (int b = 0; b < m; ++b) memcpy(result_host + (size_t)(g0 + b) * len, stage_out + (size_t)b * OS_, len * sizeof(double));
+  }
+  h->factor_valid = false;  // value-only evaluations leave no L^-1 / alpha behind
   return 0;
 }
 

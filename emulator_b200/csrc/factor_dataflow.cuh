@@ -58,6 +58,10 @@ struct FactorTask {
 struct FactorArgs {
   double* A;   // K -> L (lower triangle)
   double* W;   // X = L^-1 (lower triangle)
+  double* Xd;  // where the diagonal tiles X_jj live: W itself (xd_tile = 64 ld + 64, xd_ld = ld), or a compact
+               // [nt][64][64] buffer for batched value-only evaluations, which keep no X
+  long long xd_tile;
+  int xd_ld;
   int ld, nt, n;
   int value_only;         // 1: Cholesky only, plus the residual carried as tile row nt (see TASK_POTRF); no inverse
   const double* r;        // [np] residual (value_only)
@@ -85,6 +89,16 @@ struct FactorArgs {
   int* info;
   int* abort_flag;        // watchdog: set when a wait exceeded its budget
   unsigned long long* trace;  // optional [ntasks][TRACE_SLOTS] (diagnostics), or nullptr
+};
+
+// Several independent value-only factorisations (same shapes, different hyperparameters) can share
+// one launch: a value-only evaluation is bound by its 64-step dependency chain and leaves most SMs
+// idle, so the chains of up to MAX_BATCH problems are interleaved (the ensemble sampler proposes
+// half its walkers at once).  CTA c is at home in problem c % nb and helps the others.
+constexpr int MAX_BATCH = 8;
+struct FactorBatch {
+  int nb;
+  FactorArgs p[MAX_BATCH];
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -434,12 +448,35 @@ struct FactorSmem {
   static_assert(2 * BYTES + 2048 <= 227 * 1024, "two CTAs per SM");
 };
 
-template <int DP>
-__global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArgs a) {
+// Claim the next task of one problem for a CTA of the given role; NONE if all its queues are empty.
+__device__ __forceinline__ unsigned claim_task(const FactorArgs& a, int role, int lane) {
+  unsigned tk0 = 0xffffffffu;
+#pragma unroll 1
+  for (int attempt = 0; attempt < 3 && tk0 == 0xffffffffu; ++attempt) {
+    const int q = (role + attempt) % 3;
+    if (q == 2) {
+      tk0 = claim_inverse(a, lane);
+    } else {
+      if (lane == 0) {
+        const unsigned qn = (unsigned)(a.qbase[q + 1] - a.qbase[q]);
+        if (ld_flag(reinterpret_cast<const int*>(a.counter + q)) < (int)qn) {
+          const unsigned k = atomicAdd(a.counter + q, 1u);
+          if (k < qn) tk0 = (unsigned)a.qbase[q] + k;
+        }
+      }
+      tk0 = __shfl_sync(0xffffffffu, tk0, 0);
+    }
+  }
+  return tk0;
+}
+
+template <int DP, bool BATCH>
+__global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBatch batch) {
   extern __shared__ __align__(16) double gsm[];
   using SM = FactorSmem<DP>;
   __shared__ unsigned s_task;
   __shared__ int s_role;
+  __shared__ int s_prob;
   __shared__ unsigned long long s_wait[2];  // diagnostics: time thread 0 spent waiting in the accumulation loops
   __shared__ int s_pflags[16];  // per-panel flags of the two tile finalisers (epoch-valued, never reset)
   double* sC = gsm + SM::C_OFF;
@@ -455,7 +492,8 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
   const int wm0 = (warp / CfgP::WARPS_N) * CfgP::WM;
   const int wn0 = (warp % CfgP::WARPS_N) * CfgP::WN;
   const int g = lane >> 2, t = lane & 3;
-  const int ld = a.ld, nt = a.nt;
+  const int ld = batch.p[0].ld, nt = batch.p[0].nt;  // the problems of a batch share their shapes
+  const int nb = BATCH ? batch.nb : 1;
   if (tid < 16) s_pflags[tid] = 0;
   if (tid == 0) s_role = -1;
 
@@ -467,38 +505,35 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
     // claimed ready-first (claim_inverse) by CTAs co-resident with the queue-1 CTAs.  A CTA whose
     // queue is empty helps the others.
     if (warp == 0) {
+      const FactorArgs& a0 = batch.p[0];
+      const int local = (int)blockIdx.x / nb;  // CTA index within its home problem
       if (lane == 0 && s_role < 0) {
         // A dozen CTAs serve the chain queue, the rest of the first wave the Cholesky queue, the
         // second wave the inverse queues.  (Measured alternatives: reserving whole SMs for the chain by
         // %smid -- 6 or 12 SMs, band of 1 or 3 sub-diagonals -- made its tile factorisations 25 %
         // faster but lost more in look-ahead and bulk capacity: 307-314 vs 321 evals/s at N = 4096.)
-        const int slot = (int)(blockIdx.x % (unsigned)a.n_sms);
-        s_role = (slot < a.n_chain_sms) ? 0 : ((blockIdx.x < (unsigned)a.n_sms || a.value_only) ? 1 : 2);
+        const int slot = BATCH ? local : (int)(blockIdx.x % (unsigned)a0.n_sms);
+        const int first_wave = BATCH ? 1 : (blockIdx.x < (unsigned)a0.n_sms);
+        s_role = (slot < a0.n_chain_sms) ? 0 : ((first_wave || a0.value_only) ? 1 : 2);
       }
       __syncwarp();
       const int role = s_role;
       unsigned tk0 = 0xffffffffu;
+      int prob = 0;
 #pragma unroll 1
-      for (int attempt = 0; attempt < 3 && tk0 == 0xffffffffu; ++attempt) {
-        const int q = (role + attempt) % 3;
-        if (q == 2) {
-          tk0 = claim_inverse(a, lane);
-        } else {
-          if (lane == 0) {
-            const unsigned qn = (unsigned)(a.qbase[q + 1] - a.qbase[q]);
-            if (ld_flag(reinterpret_cast<const int*>(a.counter + q)) < (int)qn) {
-              const unsigned k = atomicAdd(a.counter + q, 1u);
-              if (k < qn) tk0 = (unsigned)a.qbase[q] + k;
-            }
-          }
-          tk0 = __shfl_sync(0xffffffffu, tk0, 0);
-        }
+      for (int pp = 0; pp < nb && tk0 == 0xffffffffu; ++pp) {
+        prob = BATCH ? ((int)(blockIdx.x % (unsigned)nb) + pp) % nb : 0;
+        tk0 = claim_task(batch.p[prob], role, lane);
       }
-      if (lane == 0) s_task = tk0;
+      if (lane == 0) {
+        s_task = tk0;
+        s_prob = prob;
+      }
     }
     __syncthreads();
     const unsigned task = s_task;
     if (task == 0xffffffffu) break;
+    const FactorArgs& a = batch.p[BATCH ? s_prob : 0];
     const FactorTask tk = a.tasks[task];
     const int ti = tk.i, tj = tk.j;
     const int i0 = ti * 64, j0 = tj * 64;
@@ -529,10 +564,10 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
                                 [abort_flag](const int* f) { return wait_ready(f, abort_flag); }) && ok;
       }
       __syncthreads();
-      double* Wt = a.W + (size_t)j0 * ld + j0;  // sC = I L^-T = (L^-1)^T
+      double* Wt = a.Xd + (size_t)tj * a.xd_tile;  // sC = I L^-T = (L^-1)^T
       for (int e = tid; e < 64 * 64; e += 256) {
         const int r = e >> 6, c = e & 63;
-        Wt[(size_t)r * ld + c] = (c <= r) ? sC[c * PS + r] : 0.0;
+        Wt[(size_t)r * a.xd_ld + c] = (c <= r) ? sC[c * PS + r] : 0.0;
       }
       EB_STAMP(4);
       const int x_ok = publish(a.xready + (size_t)tj * nt + tj, ok);
@@ -778,9 +813,9 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorArg
       yield_to_chain(my_sm);
       EB_STAMP(3);
       using EK = Engine<CfgP, KCONTIG, KCONTIG>;
-      const double* Dg = a.W + (size_t)j0 * ld + j0;  // X_jj
+      const double* Dg = a.Xd + (size_t)tj * a.xd_tile;  // X_jj
 #pragma unroll
-      for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(sD + c * 64 * KS, Dg + c * KC, ld, tid);
+      for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(sD + c * 64 * KS, Dg + c * KC, a.xd_ld, tid);
       cp_async_commit();
 #pragma unroll
       for (int mi = 0; mi < CfgP::MI; ++mi)

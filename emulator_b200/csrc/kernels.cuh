@@ -22,8 +22,11 @@ struct KernelParams {
   double inv_m[MAXD];   // 1 / exp(p_{i+1}); zero for padded dimensions
 };
 
-__global__ void prep_params_kernel(const double* __restrict__ p, int d, KernelParams* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+// One block per problem of a batch: problem b reads p + b * p_stride and writes out[b].
+__global__ void prep_params_kernel(const double* __restrict__ p, int d, KernelParams* __restrict__ out, int p_stride = 0) {
+  if (threadIdx.x == 0) {
+    p += (size_t)blockIdx.x * p_stride;
+    out += blockIdx.x;
     out->amp = (double)d * exp(p[0]);
     for (int i = 0; i < MAXD; ++i) out->inv_m[i] = (i < d) ? 1.0 / exp(p[i + 1]) : 0.0;
   }
@@ -388,6 +391,41 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
     double sum = 0.0;
     for (int q = 0; q < 8; ++q) sum += red[threadIdx.x + q];
     out[1 + c] = 0.5 * sum;
+  }
+}
+
+// The value-only reduction for a batch: block b finalises problem b (z rows live in different matrices).
+struct ValueBatchPtrs {
+  const double* z[8];
+};
+__global__ void __launch_bounds__(256) finalize_value_batch_kernel(const double* __restrict__ logdet_all, int nt,
+                                                                    const ValueBatchPtrs zs, int n, int d,
+                                                                    const int* __restrict__ info_all,
+                                                                    double* __restrict__ out_all, int out_stride,
+                                                                    int info_stride) {
+  __shared__ double red[256];
+  const int b = blockIdx.x;
+  const double* z = zs.z[b];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s = fma(z[i], z[i], s);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double* out = out_all + (size_t)b * out_stride;
+    double ld = 0.0;
+    for (int t = 0; t < nt; ++t) ld += logdet_all[(size_t)b * nt + t];
+    ld *= 2.0;
+    const double quad = red[0];
+    out[0] = -0.5 * ((double)n * TWO_PI_LOG + ld) - 0.5 * quad;  // same expression and order as finalize_kernel
+    for (int i = 0; i <= d; ++i) out[1 + i] = 0.0;
+    const int* info = info_all + (size_t)b * info_stride;  // {info, abort flag}
+    out[1 + d + 1] = (info[1] != 0) ? -1.0 : (double)info[0];
+    out[1 + d + 2] = ld;
+    out[1 + d + 3] = quad;
   }
 }
 

@@ -91,6 +91,24 @@ class DeviceProblem:
         d = self.d
         return float(out[0]), out[1 : d + 2].copy(), int(out[d + 2]), float(out[d + 3]), float(out[d + 4])
 
+    def evaluate_value_batch(self, ps: np.ndarray):
+        """Value-only evaluations at the rows of ps[nb, P]; returns (lml[nb], info[nb], logdet[nb], quad[nb]).
+
+        The factorisations share launches (up to four at a time): a value-only evaluation is bound by
+        its dependency chain, not by throughput.  Leaves no prediction state."""
+        ps = np.ascontiguousarray(ps, dtype=np.float64)
+        if ps.ndim != 2 or ps.shape[1] != self.d + 1:
+            raise ValueError(f"parameter vectors must be [nb, {self.d + 1}]")
+        nb, length = ps.shape[0], _lib.result_len(self.d)
+        out = np.zeros((nb, length))
+        if nb:
+            _lib.check(
+                self._lib.eb200_gp_eval_value_batch_host(self._h, nb, _lib.as_double_ptr(ps), _lib.as_double_ptr(out)),
+                "eb200_gp_eval_value_batch_host",
+            )
+        d = self.d
+        return out[:, 0].copy(), out[:, d + 2].astype(np.int64), out[:, d + 3].copy(), out[:, d + 4].copy()
+
     def predict(self, t: np.ndarray, want_var: bool = True):
         t = np.ascontiguousarray(t, dtype=np.float64)
         if t.ndim != 2 or t.shape[1] != self.d:

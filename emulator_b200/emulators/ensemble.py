@@ -13,10 +13,12 @@ import numpy as np
 
 
 class EnsembleSampler:
-    def __init__(self, nwalkers: int, ndim: int, log_prob_fn, a: float = 2.0, seed=None):
+    def __init__(self, nwalkers: int, ndim: int, log_prob_fn, a: float = 2.0, seed=None, vectorize: bool = False):
         if nwalkers < 2 or nwalkers % 2:
             raise ValueError("the stretch move needs an even number (>= 2) of walkers")
         self.nwalkers, self.ndim, self.log_prob_fn, self.a = nwalkers, ndim, log_prob_fn, a
+        #: emcee's option of the same name: log_prob_fn takes the whole (n, ndim) block of positions
+        self.vectorize = vectorize
         self.rng = np.random.default_rng(seed)
         self._chain = []
         self._log_prob = []
@@ -24,7 +26,12 @@ class EnsembleSampler:
         self._last = None
 
     def _evaluate(self, coords):
-        values = np.array([self.log_prob_fn(c) for c in coords], dtype=np.float64)
+        if self.vectorize:
+            values = np.asarray(self.log_prob_fn(coords), dtype=np.float64)
+            if values.shape != (len(coords),):
+                raise ValueError("a vectorized probability function must return one value per position")
+        else:
+            values = np.array([self.log_prob_fn(c) for c in coords], dtype=np.float64)
         if np.any(np.isnan(values)):
             raise ValueError("Probability function returned NaN")
         return values

@@ -8,7 +8,8 @@ Deviations, all at documented reference defects (SURVEY.md section 3.4 / Appendi
   * the hyperparameter-error loop indexes samples and columns the evident way (the reference
     swaps them, :420-426, and can write out of range);
   * the random generator is seeded through `seed` (the reference uses the unseeded global RNG).
-Sampling evaluates the likelihood value only (no gradient) on the device.
+Sampling evaluates the likelihood value only (no gradient): each half-ensemble of proposals is one
+batched device call (`GP.log_likelihood_batch`, Cholesky factor alone, factorisations sharing launches).
 """
 
 from __future__ import annotations
@@ -62,15 +63,14 @@ class GaussianProcessEmulatorMCMC(BaseEmulator):
         self.fit_result = optimise_gp(gp, y)
         start = self.fit_result.x
 
-        def log_likelihood(p):
-            gp.set_parameter_vector(p)
-            return gp.log_likelihood(y, quiet=True)
+        def log_likelihood(positions):  # a block of walker positions per call (value-only, batched on the device)
+            return gp.log_likelihood_batch(y, positions, quiet=True)
 
         ndim = len(gp)
         rng = np.random.default_rng(self.seed)
         gp.eager_gradient = False  # value-only evaluations while sampling
         try:
-            sampler = EnsembleSampler(self.walkers, ndim, log_likelihood, seed=rng)
+            sampler = EnsembleSampler(self.walkers, ndim, log_likelihood, seed=rng, vectorize=True)
             p0 = start + 1e-4 * rng.standard_normal((self.walkers, ndim))
             p0, _, _ = sampler.run_mcmc(p0, self.burn_in_steps)
             sampler.run_mcmc(p0, self.mcmc_steps)

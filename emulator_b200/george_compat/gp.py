@@ -170,6 +170,20 @@ class GP:
             raise
         return lml if np.isfinite(lml) else -np.inf
 
+    def log_likelihood_batch(self, y, vectors, quiet=True):
+        """log_likelihood at each row of `vectors` (value only), evaluated together on the device: the
+        call an ensemble sampler makes per move (emcee's ``vectorize=True`` protocol).  Does not change
+        the GP's own parameter vector.  Failed factorisations / non-finite values give -inf (quiet)."""
+        self._residual(y)
+        vectors = np.atleast_2d(np.asarray(vectors, dtype=np.float64))
+        lml, info, _, _ = self._problem.evaluate_value_batch(vectors)
+        self.n_device_evaluations += len(vectors)
+        self._device_p = None  # no prediction state survives
+        self._cache_key = self._cache = None
+        if np.any(info != 0) and not quiet:
+            raise np.linalg.LinAlgError("a leading minor of the array is not positive definite")
+        return np.where((info == 0) & np.isfinite(lml), lml, -np.inf)
+
     def grad_log_likelihood(self, y, quiet=False):
         self._residual(y)
         try:

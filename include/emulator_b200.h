@@ -66,6 +66,12 @@ int eb200_gp_set_residual_device(eb200_gp* gp, const double* r_dev, void* stream
 int eb200_gp_eval_host(eb200_gp* gp, const double* p_host, int mode, double* result_host);
 int eb200_gp_eval_device(eb200_gp* gp, const double* p_dev, int mode, double* result_dev, void* stream);
 
+/* nb value-only evaluations (EB200_EVAL_VALUE_ONLY semantics) at the parameter vectors p_host[nb][d+1];
+ * result_host[nb][EB200_RESULT_LEN(d)].  A value-only factorisation is bound by its dependency chain
+ * and leaves most SMs idle, so up to four share one launch.  This is the half-ensemble of proposals
+ * the ensemble sampler evaluates per move (gaussian_process_mcmc.py:259-265; emcee's `vectorize`). */
+int eb200_gp_eval_value_batch_host(eb200_gp* gp, int nb, const double* p_host, double* result_host);
+
 /* Replaces gp.predict(y, t, return_cov=False, return_var=bool)  (gaussian_process.py:285-287,
  * :344-346; gaussian_process_bins.py:354-359, :452-457).  Requires a preceding eval at the
  * hyperparameters to predict with in mode EB200_EVAL_LML or EB200_EVAL_GRAD (L^-1 and alpha stay

@@ -57,6 +57,15 @@ class OracleBackedGP:
                 return -np.inf
             raise
 
+    def log_likelihood_batch(self, y, vectors, quiet=True):
+        keep = self.get_parameter_vector().copy()
+        out = []
+        for v in np.atleast_2d(vectors):
+            self.set_parameter_vector(v)
+            out.append(self.log_likelihood(y, quiet=quiet))
+        self.set_parameter_vector(keep)
+        return np.array(out, dtype=np.float64)
+
     def grad_log_likelihood(self, y, quiet=False):
         try:
             return self._gp.grad_log_likelihood(y)

@@ -119,6 +119,41 @@ def test_value_only_evaluation_leaves_no_prediction_state():
     gp.close()
 
 
+@pytest.mark.parametrize("n,d,nb", [(200, 3, 1), (300, 4, 3), (129, 2, 4), (640, 9, 7), (1536, 5, 4)])
+def test_batched_value_only_evaluations_match_single_ones(n, d, nb):
+    """Several factorisations share one launch; every one must equal its stand-alone evaluation bit for bit."""
+    x, y, diag = problem(n, d, seed=3 * n + nb)
+    gp = device_problem(x, diag, y)
+    rng = np.random.default_rng(nb)
+    ps = orc.default_parameter_vector(d) + 0.3 * rng.standard_normal((nb, d + 1))
+    lml, info, logdet, quad = gp.evaluate_value_batch(ps)
+    assert lml.shape == (nb,) and np.all(info == 0)
+    for b in range(nb):
+        single = gp.evaluate(ps[b], False, value_only=True)
+        assert (lml[b], logdet[b], quad[b]) == (single[0], single[3], single[4])
+        ref = orc.lml_and_grad(ps[b], x, diag, y)
+        assert abs(lml[b] - ref[0]) <= TOL * abs(ref[0])
+    # repeated batches are bit-identical, and the batch leaves no prediction state
+    again = gp.evaluate_value_batch(ps)
+    assert np.array_equal(again[0], lml)
+    with pytest.raises(RuntimeError):
+        gp.predict(x[:3], False)
+    gp.close()
+
+
+def test_batched_value_only_reports_failed_factorisations_per_problem():
+    x = np.zeros((40, 2))
+    x[:, 0] = np.repeat(np.arange(20), 2) * 0.05  # duplicated rows, no noise: singular at any p
+    gp = device_problem(x, np.full(40, 0.0), np.ones(40))
+    gp2 = device_problem(x, np.full(40, 1e-2), np.ones(40))
+    ps = np.array([[5.0, 3.0, 3.0], [0.0, 0.0, 0.0], [1.0, -1.0, 2.0]])
+    _, info, _, _ = gp.evaluate_value_batch(ps)
+    assert np.all(info > 0)
+    lml2, info2, _, _ = gp2.evaluate_value_batch(ps)
+    assert np.all(info2 == 0) and np.all(np.isfinite(lml2))
+    gp.close(); gp2.close()
+
+
 def test_value_only_not_positive_definite_reports_info():
     x = np.zeros((40, 2))
     x[:, 0] = np.repeat(np.arange(20), 2) * 0.05

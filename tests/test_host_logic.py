@@ -257,3 +257,27 @@ def test_ensemble_sampler_recovers_a_gaussian():
     assert np.allclose(flat.std(axis=0), sigma, rtol=0.25)
     with pytest.raises(ValueError):
         EnsembleSampler(7, 2, lambda p: 0.0)
+
+
+def test_vectorized_ensemble_sampler_walks_the_same_chain():
+    """`vectorize=True` (one call per half-ensemble, what the batched device path uses) must not
+    change the chain: same proposals, same acceptances."""
+    from emulator_b200.emulators.ensemble import EnsembleSampler
+
+    mean = np.array([0.3, -1.0, 2.0])
+    scalar = EnsembleSampler(12, 3, lambda p: -0.5 * np.sum((p - mean) ** 2), seed=5)
+    blocks = []
+
+    def block_fn(ps):
+        blocks.append(len(ps))
+        return -0.5 * np.sum((ps - mean) ** 2, axis=1)
+
+    vector = EnsembleSampler(12, 3, block_fn, seed=5, vectorize=True)
+    p0 = mean + 0.1 * np.random.default_rng(1).standard_normal((12, 3))
+    a = scalar.run_mcmc(p0, 25)
+    b = vector.run_mcmc(p0, 25)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(scalar.get_chain(), vector.get_chain())
+    assert blocks[0] == 12 and set(blocks[1:]) == {6}  # initial ensemble, then half-ensembles
+    with pytest.raises(ValueError):
+        EnsembleSampler(4, 2, lambda ps: np.zeros(3), vectorize=True).run_mcmc(np.zeros((4, 2)), 1)

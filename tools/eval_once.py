@@ -13,6 +13,16 @@ y = np.sin(x.sum(1) * 2.0)
 diag = orc.noise_diagonal((0.02 * np.abs(y) + 1e-3).astype(np.float32))
 gp = DeviceProblem(x, diag); gp.set_residual(y)
 p = orc.default_parameter_vector(d)
+if kind.startswith("batch"):   # batchNB: NB value-only evaluations per call
+    nb = int(kind[5:])
+    ps = p + 0.05 * np.random.default_rng(1).standard_normal((nb, d + 1))
+    gp.evaluate_value_batch(ps)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = gp.evaluate_value_batch(ps)
+    dt = (time.perf_counter() - t0) / reps
+    print(json.dumps({"n": n, "d": d, "kind": kind, "ms_per_call": dt * 1e3, "ms_per_eval": dt * 1e3 / nb, "info": int(out[1].max())}))
+    sys.exit(0)
 gp.evaluate(p, want_grad, value_only=value_only)  # warm-up
 t0 = time.perf_counter()
 for _ in range(reps):
