@@ -79,4 +79,16 @@ for n_, d_ in ((4096, 9), (8176, 9), (256, 8)):
         res[kind + "_ms"] = (time.perf_counter() - t0) / reps * 1e3
     out[f"eval_modes_N{n_}"] = res
     gp.close()
+    gp = DeviceProblem(x.astype(np.float64), noise); gp.set_residual(y.astype(np.float64))
+    ps = p + 0.05 * np.random.default_rng(2).standard_normal((40, d_ + 1))
+    gp.evaluate_value_batch(ps)
+    t0 = time.perf_counter(); gp.evaluate_value_batch(ps); dt = time.perf_counter() - t0
+    out[f"eval_modes_N{n_}"]["value_only_batched_ms_per_eval"] = dt / 40 * 1e3
+    gp.close()
+# ---- ensemble-MCMC emulator (reference defaults: 40 walkers, 50 + 100 steps = 6000 value-only likelihoods) ----
+from emulator_b200.emulators import GaussianProcessEmulatorMCMC
+spec, params, values = synthetic.make_config("C1")
+emu = GaussianProcessEmulatorMCMC(seed=0)
+t0 = time.perf_counter(); emu.fit_model(spec, params, values); dt = time.perf_counter() - t0
+out["fit_C1_mcmc_N1000_6000_likelihoods"] = {"seconds": dt, "device_evals": int(emu.emulator.n_device_evaluations)}
 print(json.dumps(out, indent=1))
