@@ -496,6 +496,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
   const int nb = BATCH ? batch.nb : 1;
   if (tid < 16) s_pflags[tid] = 0;
   if (tid == 0) s_role = -1;
+  int chol_epoch = 0;
 
   for (;;) {
     __syncthreads();  // previous task fully retired (smem reuse, s_task reuse)
@@ -871,7 +872,8 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
     if (ti == tj) {
       if (tid == 0) atomicAdd(my_sm, 1);
       // (the panels of L_jj and the reciprocal pivots are streamed to global memory as they are produced)
-      tile_cholesky(v, sL, rdiag, a.info, j0, s_pflags, (int)task + 1, At, ld, a.rdiag + (size_t)tj * 64,
+      // (epoch: unique per call within this CTA -- task numbers repeat across the problems of a batch)
+      tile_cholesky(v, sL, rdiag, a.info, j0, s_pflags, ++chol_epoch, At, ld, a.rdiag + (size_t)tj * 64,
                     a.lready + (size_t)tj * 8);
       EB_STAMP(4);
       int all_ok = publish(a.ready + (size_t)ti * nt + tj, ok);

@@ -141,6 +141,23 @@ def test_batched_value_only_evaluations_match_single_ones(n, d, nb):
     gp.close()
 
 
+def test_batched_value_only_full_size_is_stable_under_repetition():
+    """Regression: per-CTA panel flags were keyed by task number, which repeats across the problems of a
+    batch; at N = 4096 a CTA helping a second problem could see a stale flag (intermittent NaN)."""
+    n, d = 4096, 9
+    x, y, diag = problem(n, d, seed=1235)
+    gp = device_problem(x, diag, y)
+    ps = orc.default_parameter_vector(d) + 0.05 * np.random.default_rng(0).standard_normal((11, d + 1))
+    first = gp.evaluate_value_batch(ps)
+    assert np.all(first[1] == 0) and np.all(np.isfinite(first[0]))
+    for b in (0, 5, 10):
+        assert gp.evaluate(ps[b], False, value_only=True)[0] == first[0][b]
+    for _ in range(40):
+        again = gp.evaluate_value_batch(ps)
+        assert np.array_equal(again[1], first[1]) and np.array_equal(again[0], first[0])
+    gp.close()
+
+
 def test_batched_value_only_reports_failed_factorisations_per_problem():
     x = np.zeros((40, 2))
     x[:, 0] = np.repeat(np.arange(20), 2) * 0.05  # duplicated rows, no noise: singular at any p
