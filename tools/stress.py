@@ -7,7 +7,7 @@ from emulator_b200.device import DeviceProblem
 from emulator_b200 import synthetic
 from oracle import gp_oracle as orc
 bad = 0
-for n, d, reps in ((4096, 9, 300), (2500, 8, 300), (640, 9, 1500), (1536, 5, 800), (200, 3, 3000)):
+for n, d, reps in [(int(a), int(b), int(c)) for a, b, c in (t.split(":") for t in (sys.argv[1] if len(sys.argv) > 1 else "4096:9:300,2500:8:300,640:9:1500,1536:5:800,200:3:3000").split(","))]:
     x, y, yerr = synthetic.design_arrays(n, d, seed=n)
     gp = DeviceProblem(x.astype(np.float64), orc.noise_diagonal(yerr)); gp.set_residual(y.astype(np.float64))
     p = orc.default_parameter_vector(d) + 0.1
