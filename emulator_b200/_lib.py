@@ -34,6 +34,7 @@ SIGNATURES = {
     "eb200_version": (c_int, []),
     "eb200_last_error": (c_char_p, []),
     "eb200_device_count": (c_int, []),
+    "eb200_device_mem_info": (c_int, [c_int, POINTER(ctypes.c_ulonglong), POINTER(ctypes.c_ulonglong)]),
     "eb200_gp_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, _dp, _dp]),
     "eb200_gp_destroy": (c_int, [c_void_p]),
     "eb200_gp_n": (c_int, [c_void_p]),

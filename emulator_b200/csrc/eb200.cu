@@ -383,6 +383,16 @@ int eb200_device_count(void) {
   return c;
 }
 
+int eb200_device_mem_info(int device, unsigned long long* free_bytes, unsigned long long* total_bytes) {
+  if (!free_bytes || !total_bytes) return fail("device_mem_info: null argument");
+  CK(cudaSetDevice(device));
+  size_t f = 0, t = 0;
+  CK(cudaMemGetInfo(&f, &t));
+  *free_bytes = f;
+  *total_bytes = t;
+  return 0;
+}
+
 int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_host, const double* noise_host) {
   if (!out || !x_host || !noise_host) return fail("eb200_gp_create: null argument");
   if (n < 1) return fail("eb200_gp_create: n must be >= 1");

@@ -19,13 +19,77 @@ scipy.optimize calls fun(p) and jac(p) separately (gaussian_process.py:208-221).
 
 from __future__ import annotations
 
+import collections
+import contextlib
+import ctypes
+import threading
+import weakref
+
 import numpy as np
 
+from .. import _lib
 from ..device import DeviceProblem
 from . import kernels as _kernels
 from .modeling import CallableModel, ConstantModel, Model
 
 TINY = 1.25e-12  # george.gp.TINY
+
+
+class _Residency:
+    """Keeps the device handles of all GP objects of this process within the GPU's memory.
+
+    A handle costs about 2 N^2 doubles (1.07 GB at the N = 8176 of a leave-one-out refit), and the
+    reference's drivers keep every fitted GP: CrossCheck holds one per simulation (512 at BASELINE
+    configuration C4).  A GP therefore only *needs* its handle while one of its methods runs; handles
+    are created lazily and the least recently used unpinned ones are released when a new one would
+    not fit.  A released GP keeps its data and parameters and gets a new handle on its next use
+    (one re-factorisation)."""
+
+    RESERVE = 1 << 30  # bytes kept free for everything else (CUDA context growth, torch, NCCL)
+
+    def __init__(self):
+        self.lock = threading.RLock()
+        self.lru = collections.OrderedDict()  # id(gp) -> weakref
+
+    @staticmethod
+    def needed_bytes(n: int) -> int:
+        npad = -(-n // 128) * 128
+        return int(2.2 * npad * npad * 8) + (64 << 20)
+
+    @staticmethod
+    def free_bytes(device: int) -> int:
+        lib = _lib.require_gpu()
+        free, total = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+        _lib.check(lib.eb200_device_mem_info(device, ctypes.byref(free), ctypes.byref(total)), "device_mem_info")
+        return int(free.value)
+
+    def touch(self, gp):
+        with self.lock:
+            self.lru[id(gp)] = weakref.ref(gp)
+            self.lru.move_to_end(id(gp))
+
+    def forget(self, gp):
+        with self.lock:
+            self.lru.pop(id(gp), None)
+
+    def make_room(self, device: int, need: int, keep):
+        """Release least-recently-used, unpinned handles on `device` until `need` bytes fit."""
+        with self.lock:
+            if self.free_bytes(device) >= need + self.RESERVE:
+                return
+            for key in list(self.lru.keys()):
+                other = self.lru[key]()
+                if other is None:
+                    self.lru.pop(key, None)
+                    continue
+                if other is keep or other.device != device or other._pins > 0 or other._problem is None:
+                    continue
+                other._release_locked()
+                if self.free_bytes(device) >= need + self.RESERVE:
+                    return
+
+
+_residency = _Residency()
 
 
 class GP:
@@ -69,12 +133,16 @@ class GP:
         self._problem = None
         self._x = None
         self._yerr2 = None
-        self._residual_key = None
+        self._residual_key = None       # residual held by the device handle
+        self._host_residual_key = None  # residual the cached values belong to
+        self._r = None
         self._cache_key = None      # (p bytes) of the cached evaluation
         self._cache = None          # (lml, grad or None, info)
         self._device_p = None       # p bytes the resident factorisation belongs to
         self.computed = False
         self.n_device_evaluations = 0
+        self._noise = None
+        self._pins = 0              # > 0 while a method is using the device handle
 
     # ---- modeling protocol ----------------------------------------------------------------
     def __len__(self):
@@ -108,16 +176,55 @@ class GP:
             yerr2 = yerr ** 2  # in the caller's dtype, as george does
         self._yerr2 = np.ascontiguousarray(yerr2, dtype=np.float64)
         # GP.compute -> sqrt(yerr2 + white noise); BasicSolver.compute squares it again
-        noise = np.sqrt(self._yerr2 + TINY) ** 2
+        self._noise = np.sqrt(self._yerr2 + TINY) ** 2
+        if self._x.shape[1] > _lib.MAX_DIM:
+            raise ValueError(f"kernel dimension {self._x.shape[1]} exceeds the supported maximum {_lib.MAX_DIM}")
+        _lib.require_gpu()  # fail here, loudly, when the CUDA library or a GPU is missing
+        self.release_device()
+        self._cache_key = self._cache = None
+        self._host_residual_key = self._r = None
+        self.computed = True
+        # george factorises inside compute(); here the device handle and the factorisation are deferred
+        # to the first likelihood / predict call (which every reference call site makes next), so a
+        # matrix that is not positive definite raises LinAlgError there instead.
+
+    # ---- device residency -----------------------------------------------------------------------
+    @contextlib.contextmanager
+    def _using_device(self):
+        """Pins this GP's handle (creating it if needed) for the duration of one method."""
+        with _residency.lock:
+            self._pins += 1
+        try:
+            if self._problem is None:
+                if not self.computed:
+                    raise RuntimeError("You need to compute the model first")
+                _residency.make_room(self.device, _Residency.needed_bytes(len(self._x)), keep=self)
+                self._problem = DeviceProblem(self._x, self._noise, device=self.device)
+                self._residual_key = None
+                self._device_p = None
+            _residency.touch(self)
+            yield self._problem
+        finally:
+            with _residency.lock:
+                self._pins -= 1
+
+    def _release_locked(self):
         if self._problem is not None:
             self._problem.close()
-        self._problem = DeviceProblem(self._x, noise, device=self.device)
+            self._problem = None
         self._residual_key = None
-        self._cache_key = self._cache = self._device_p = None
-        self.computed = True
-        # george factorises inside compute(); here the factorisation is deferred to the first
-        # likelihood / predict call (which every reference call site makes next), so a matrix
-        # that is not positive definite raises LinAlgError there instead.
+        self._device_p = None
+
+    def release_device(self):
+        """Free the device handle (data, parameters and cached values stay); the next use re-creates it."""
+        with _residency.lock:
+            if self._pins > 0:
+                raise RuntimeError("the device handle is in use")
+            self._release_locked()
+
+    @property
+    def resident(self) -> bool:
+        return self._problem is not None
 
     # ---- internals ----------------------------------------------------------------------------
     def _call_mean(self, x):
@@ -131,30 +238,39 @@ class GP:
             raise ValueError("Dimension mismatch")
         return y
 
-    def _set_residual(self, r):
-        key = r.tobytes()
-        if key != self._residual_key:
-            self._problem.set_residual(r)
-            self._residual_key = key
-            self._cache_key = self._cache = self._device_p = None
-
     def _residual(self, y):
+        """Host part: r = y - mean(x); a new residual invalidates cached values and the device state."""
         if not self.computed:
             raise RuntimeError("You need to compute the model first")
         r = np.ascontiguousarray(self._check_dimensions(y) - self._call_mean(self._x), dtype=np.float64)
-        self._set_residual(r)
+        key = r.tobytes()
+        if key != self._host_residual_key:
+            self._host_residual_key = key
+            self._r = r
+            self._cache_key = self._cache = self._device_p = None
 
-    def _evaluate(self, want_grad: bool, value_only: bool = False):
+    def _sync_residual(self):
+        """Device part (handle pinned): upload the residual if the handle holds another one."""
+        if self._residual_key != self._host_residual_key:
+            self._problem.set_residual(self._r)
+            self._residual_key = self._host_residual_key
+            self._device_p = None
+
+    def _evaluate(self, want_grad: bool, value_only: bool = False, need_state: bool = False):
         p = np.ascontiguousarray(self.get_parameter_vector(), dtype=np.float64)
         key = p.tobytes()
-        if self._cache_key == key and (self._cache[1] is not None or not want_grad):
+        cached = self._cache_key == key and (self._cache[1] is not None or not want_grad)
+        if cached and not (need_state and self._device_p != key):
             return self._cache
-        lml, grad, info, _logdet, _quad = self._problem.evaluate(p, want_grad, value_only=value_only)
+        with self._using_device():
+            self._sync_residual()
+            lml, grad, info, _logdet, _quad = self._problem.evaluate(p, want_grad, value_only=value_only)
         self.n_device_evaluations += 1
         # a value-only evaluation (Cholesky factor alone) leaves no prediction state behind
         self._device_p = None if value_only else key
-        self._cache_key = key
-        self._cache = (lml, grad if want_grad else None, info)
+        if not (cached and not want_grad):  # keep a cached gradient when only the device state was refreshed
+            self._cache_key = key
+            self._cache = (lml, grad if want_grad else None, info)
         if info != 0:
             raise np.linalg.LinAlgError(f"{info}-th leading minor of the array is not positive definite")
         return self._cache
@@ -176,10 +292,11 @@ class GP:
         the GP's own parameter vector.  Failed factorisations / non-finite values give -inf (quiet)."""
         self._residual(y)
         vectors = np.atleast_2d(np.asarray(vectors, dtype=np.float64))
-        lml, info, _, _ = self._problem.evaluate_value_batch(vectors)
+        with self._using_device():
+            self._sync_residual()
+            lml, info, _, _ = self._problem.evaluate_value_batch(vectors)
         self.n_device_evaluations += len(vectors)
         self._device_p = None  # no prediction state survives
-        self._cache_key = self._cache = None
         if np.any(info != 0) and not quiet:
             raise np.linalg.LinAlgError("a leading minor of the array is not positive definite")
         return np.where((info == 0) & np.isfinite(lml), lml, -np.inf)
@@ -211,11 +328,6 @@ class GP:
                 "the full predictive covariance is never requested by swiftemulator and has no device path"
             )
         self._residual(y)
-        p = np.ascontiguousarray(self.get_parameter_vector(), dtype=np.float64)
-        if self._device_p != p.tobytes():
-            # factor + alpha at the current parameters must be resident
-            self._cache_key = None
-            self._evaluate(want_grad=False)
         xs = np.asarray(t)
         if xs.ndim == 1:
             xs = xs[:, None]
@@ -223,21 +335,25 @@ class GP:
             raise ValueError("Dimension mismatch")
         xs = np.ascontiguousarray(xs, dtype=np.float64)
         mean_t = self._call_mean(xs)
-        if not return_var:
-            return self._problem.predict(xs, want_var=False) + mean_t
-        mu, var = self._problem.predict(xs, want_var=True)
+        with self._using_device():  # pinned across factorisation and prediction
+            # factor + alpha at the current parameters must be resident
+            self._evaluate(want_grad=False, need_state=True)
+            if not return_var:
+                return self._problem.predict(xs, want_var=False) + mean_t
+            mu, var = self._problem.predict(xs, want_var=True)
         return mu + mean_t, var
 
-    # ---- access for batched drivers ---------------------------------------------------------
-    @property
-    def problem(self) -> DeviceProblem:
-        return self._problem
-
+    # ---- lifetime ---------------------------------------------------------------------------------
     def close(self):
-        if self._problem is not None:
-            self._problem.close()
-            self._problem = None
-            self.computed = False
+        self.release_device()
+        _residency.forget(self)
+        self.computed = False
+
+    def __del__(self):  # pragma: no cover
+        try:
+            _residency.forget(self)
+        except Exception:
+            pass
 
     def __deepcopy__(self, memo):
         raise TypeError("a device-resident GP cannot be deep-copied; copy the kernel and build a new GP")

@@ -36,6 +36,8 @@ typedef struct eb200_gp eb200_gp;
 int eb200_version(void);
 const char* eb200_last_error(void);
 int eb200_device_count(void);
+/* free / total device memory in bytes (the host side keeps the number of resident GP handles within it) */
+int eb200_device_mem_info(int device, unsigned long long* free_bytes, unsigned long long* total_bytes);
 
 /* Replaces george.GP.compute(x, yerr)  (swiftemulator/emulators/gaussian_process.py:203-206,
  * gaussian_process_bins.py:239-242, gaussian_process_mcmc.py:235-238,

@@ -137,3 +137,42 @@ def test_sobol_sweep_on_device():
     out = sobol_indices(emu, spec, np.linspace(0.1, 0.9, 4), base_samples=256)
     assert out["S1"].shape == (3, 4) and np.all(np.isfinite(out["ST"]))
     assert np.all(out["ST"] > -0.05)
+
+
+def test_device_handles_are_released_and_recreated_within_the_memory_budget():
+    """CrossCheck keeps one fitted GP per simulation (512 at BASELINE C4, 1.07 GB of device state
+    each): handles are created lazily and the least recently used ones released when memory runs
+    short.  Shrink the budget so that two handles do not fit and check results survive eviction."""
+    from emulator_b200 import george_compat as george
+    from emulator_b200.george_compat import gp as gp_module
+    from emulator_b200 import synthetic
+
+    res = gp_module._residency
+    n, d = 300, 3
+    gps, ys, outs = [], [], []
+    old_reserve = res.RESERVE
+    try:
+        for k in range(3):
+            x, y, yerr = synthetic.design_arrays(n, d, seed=k)
+            g = george.GP(1**2 * george.kernels.ExpSquaredKernel(np.ones(d), ndim=d))
+            g.compute(x, yerr)
+            assert not g.resident  # lazy: no device memory until first use
+            gps.append(g); ys.append(y)
+        # budget: nothing fits next to what is resident, so every new handle evicts the others
+        res.RESERVE = gp_module._Residency.free_bytes(0)
+        for g, y in zip(gps, ys):
+            outs.append((g.log_likelihood(y), g.grad_log_likelihood(y), g.predict(y, g._x[:5] + 0.01, return_cov=False, return_var=True)))
+        assert sum(g.resident for g in gps) == 1 and gps[2].resident
+        # an evicted GP answers from its cache without touching the device ...
+        evals = gps[0].n_device_evaluations
+        assert gps[0].log_likelihood(ys[0]) == outs[0][0] and not gps[0].resident
+        assert gps[0].n_device_evaluations == evals
+        # ... and re-creates its handle (one re-factorisation) for a prediction, bit-identical
+        mu, var = gps[0].predict(ys[0], gps[0]._x[:5] + 0.01, return_cov=False, return_var=True)
+        assert gps[0].resident and not gps[2].resident
+        assert np.array_equal(mu, outs[0][2][0]) and np.array_equal(var, outs[0][2][1])
+        assert np.array_equal(gps[0].grad_log_likelihood(ys[0]), outs[0][1])
+    finally:
+        res.RESERVE = old_reserve
+        for g in gps:
+            g.close()
