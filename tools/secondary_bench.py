@@ -91,4 +91,23 @@ spec, params, values = synthetic.make_config("C1")
 emu = GaussianProcessEmulatorMCMC(seed=0)
 t0 = time.perf_counter(); emu.fit_model(spec, params, values); dt = time.perf_counter() - t0
 out["fit_C1_mcmc_N1000_6000_likelihoods"] = {"seconds": dt, "device_evals": int(emu.emulator.n_device_evaluations)}
+# ---- leave-one-out refits at C4 size (512 sims x 16 points; each refit N = 8176): two measured refits,
+#      sequentially and from two host threads (CrossCheck's `workers`), projected to all 512 ----
+from concurrent.futures import ThreadPoolExecutor
+from emulator_b200.backend.model_values import ModelValues
+spec, params, values = synthetic.make_config("C4")
+uids = list(values.model_values.keys())
+def refit(uid):
+    emu = GaussianProcessEmulator()
+    t0 = time.perf_counter()
+    emu.fit_model(spec, params, ModelValues({k: v for k, v in values.model_values.items() if k != uid}))
+    return time.perf_counter() - t0, int(emu.fit_result.nfev), int(emu.emulator.n_device_evaluations)
+r0 = refit(uids[0])
+t0 = time.perf_counter()
+with ThreadPoolExecutor(max_workers=2) as pool:
+    r12 = list(pool.map(refit, uids[1:3]))
+pair = time.perf_counter() - t0
+out["loo_C4_refit_N8176"] = {"one_refit_seconds": r0[0], "nfev": r0[1], "device_evals": r0[2],
+                             "two_refits_two_threads_seconds": pair, "their_device_evals": [r[2] for r in r12],
+                             "projected_512_refits_8gpu_min": 512 / 8 * min(r0[0], pair / 2) / 60}
 print(json.dumps(out, indent=1))
