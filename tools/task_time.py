@@ -3,17 +3,18 @@ import sys
 import numpy as np
 f = np.load(sys.argv[1]); out, tasks, nt = f["out"], f["tasks"], int(f["nt"])
 t = (out[:, :6].astype(np.int64) - int(out[:, 0].min())) / 1e3
-NAMES = {0: "POTRF", 1: "TRTRI", 2: "TRTRI_PART", 3: "POTRF_PART", 4: "XDIAG"}
+NAMES = {0: "POTRF", 1: "TRTRI", 2: "TRTRI_PART", 3: "POTRF_PART", 4: "XDIAG", 5: "KINV"}
 end = t[:, 5].max()
 print("kernel end us", end, " CTA-time available (296 CTAs) ms", 296 * end / 1e3)
 tot = 0
-for ty in range(5):
+for ty in range(6):
     m = tasks[:, 0] == ty
     if not m.any(): continue
     i, j, k = tasks[m, 1], tasks[m, 2], tasks[m, 3]
     if ty == 0: prods = j - k
     elif ty == 1: prods = i - np.where(k > j, k, j) + 1  # + the finalisation product
     elif ty == 2: prods = k - (tasks[m, 5] if tasks.shape[1] > 5 else j)
+    elif ty == 5: prods = k - tasks[m, 5]
     elif ty == 3: prods = k
     else: prods = np.zeros(m.sum())
     dur = t[m, 5] - t[m, 0]
