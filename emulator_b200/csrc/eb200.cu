@@ -165,19 +165,31 @@ void build_program(eb200_gp* h, std::vector<TileTask>& tasks) {
   }
   // ---- K^-1 tiles + gradient traces ----
   // Tile (I, J) contracts over k >= I*128.  A contraction can be cut into K-slices (the trace is
-  // linear in K^-1; exactly one slice per tile carries the alpha alpha^T term); measured on B200 at
-  // N=4096 slicing at 1024 rows costs more in repeated epilogues (0.99 ms) than it gains in balance
-  // (0.91 ms unsliced), so slicing is off.  The unsplit list also serves the diagnostics path that
-  // stores K^-1.
+  // linear in K^-1; exactly one slice per tile carries the alpha alpha^T term).  The unsplit list also
+  // serves the diagnostics path that stores K^-1.
   {
-    const int LAUUM_SLICE = 1 << 20;  // contraction rows / KC per slice (effectively: no slicing)
+    // Small and medium problems have few tiles per SM, each with a long serial contraction (a 128x128 tile
+    // with 1024 rows keeps one SM busy for 134 us), so the longest tile bounds the kernel.
+    // Rule: no task longer than the average load of one SM.  Measured on B200 (whole evaluation, ms,
+    // unsliced -> sliced): N = 256 0.197 -> 0.170, 1000 0.538 -> 0.427, 2048 1.059 -> 0.912,
+    // 2500 1.327 -> 1.199, 3000 1.635 -> 1.571, 4096 and 8176 unchanged (shorter slices lose to the
+    // repeated epilogues there: 3.07 ms at a quarter of the average load).
+    int LAUUM_SLICE;  // contraction rows / KC per slice
+    {
+      long long units = 0;
+      for (int J = 0; J < nT; ++J)
+        for (int I = J; I < nT; ++I) units += (np - I * 128) / KC;
+      const long long per = units / h->n_sms;
+      LAUUM_SLICE = (int)std::max(4ll, (per + 1) / 2 * 2);  // even (the main loop takes chunks in pairs)
+    }
     size_t off = tasks.size();
     for (int J = 0; J < nT; ++J)
       for (int I = J; I < nT; ++I) {
         const int total = (np - I * 128) / KC;
         const int nslice = (total + LAUUM_SLICE - 1) / LAUUM_SLICE;
         for (int sidx = 0; sidx < nslice; ++sidx) {
-          const int c0 = (int)((long long)total * sidx / nslice), c1 = (int)((long long)total * (sidx + 1) / nslice);
+          // slice boundaries in pairs of chunks (total is a multiple of 8)
+          const int c0 = 2 * (int)((long long)(total / 2) * sidx / nslice), c1 = 2 * (int)((long long)(total / 2) * (sidx + 1) / nslice);
           const int k0 = I * 128 + c0 * KC;
           tasks.push_back({I * 128, J * 128, k0, I * 128, k0, J * 128, c1 - c0, (I == J ? 1 : 0) | (sidx == 0 ? 2 : 0)});
         }
