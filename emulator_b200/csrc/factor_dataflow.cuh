@@ -496,7 +496,6 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
   const int nb = BATCH ? batch.nb : 1;
   if (tid < 16) s_pflags[tid] = 0;
   if (tid == 0) s_role = -1;
-  int chol_epoch = 0;
 
   for (;;) {
     __syncthreads();  // previous task fully retired (smem reuse, s_task reuse)
@@ -565,10 +564,12 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
                                 [abort_flag](const int* f) { return wait_ready(f, abort_flag); }) && ok;
       }
       __syncthreads();
-      double* Wt = a.Xd + (size_t)tj * a.xd_tile;  // sC = I L^-T = (L^-1)^T
+      // (single evaluations keep X_jj in W itself; batched value-only ones in a compact buffer of their own)
+      double* Wt = BATCH ? a.Xd + (size_t)tj * a.xd_tile : a.W + (size_t)j0 * ld + j0;  // sC = I L^-T = (L^-1)^T
+      const int xld = BATCH ? a.xd_ld : ld;
       for (int e = tid; e < 64 * 64; e += 256) {
         const int r = e >> 6, c = e & 63;
-        Wt[(size_t)r * a.xd_ld + c] = (c <= r) ? sC[c * PS + r] : 0.0;
+        Wt[(size_t)r * xld + c] = (c <= r) ? sC[c * PS + r] : 0.0;
       }
       EB_STAMP(4);
       const int x_ok = publish(a.xready + (size_t)tj * nt + tj, ok);
@@ -814,9 +815,10 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
       yield_to_chain(my_sm);
       EB_STAMP(3);
       using EK = Engine<CfgP, KCONTIG, KCONTIG>;
-      const double* Dg = a.Xd + (size_t)tj * a.xd_tile;  // X_jj
+      const double* Dg = BATCH ? a.Xd + (size_t)tj * a.xd_tile : a.W + (size_t)j0 * ld + j0;  // X_jj
+      const int xld = BATCH ? a.xd_ld : ld;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(sD + c * 64 * KS, Dg + c * KC, a.xd_ld, tid);
+      for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(sD + c * 64 * KS, Dg + c * KC, xld, tid);
       cp_async_commit();
 #pragma unroll
       for (int mi = 0; mi < CfgP::MI; ++mi)
@@ -873,7 +875,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
       if (tid == 0) atomicAdd(my_sm, 1);
       // (the panels of L_jj and the reciprocal pivots are streamed to global memory as they are produced)
       // (epoch: unique per call within this CTA -- task numbers repeat across the problems of a batch)
-      tile_cholesky(v, sL, rdiag, a.info, j0, s_pflags, ++chol_epoch, At, ld, a.rdiag + (size_t)tj * 64,
+      tile_cholesky(v, sL, rdiag, a.info, j0, s_pflags, (int)task + 1 + (BATCH ? s_prob * a.ntasks : 0), At, ld, a.rdiag + (size_t)tj * 64,
                     a.lready + (size_t)tj * 8);
       EB_STAMP(4);
       int all_ok = publish(a.ready + (size_t)ti * nt + tj, ok);
