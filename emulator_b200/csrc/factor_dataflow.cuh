@@ -1,17 +1,19 @@
 // Persistent dataflow factorisation (sm_100a, fp64): Cholesky K = L L^T and the triangular
 // inverse X = L^-1 in ONE launch.
 //
-// The lower triangle is cut into 64x64 tiles.  A static task list (built on the host) is
-// handed out through an atomic counter, so every claimed task is owned by a CTA that is
-// already running and depends only on lower-numbered tasks: no co-residency assumption, no
-// deadlock.  Two task kinds share the list:
+// The lower triangle is cut into 64x64 tiles.  Static task lists (built on the host) are handed out to
+// the CTAs of a persistent launch: the Cholesky's queues in order through atomic counters, the
+// inverse's queues ready-first with a ticket fallback over a dependency-safe order (claim_inverse).
+// Every task a CTA may block in has all its predecessors claimed by CTAs that are already running:
+// no co-residency assumption, no deadlock.  Task kinds:
 //
 //   POTRF (i, j), column-major:  C = K_ij - sum_{k<j} L_ik L_jk^T   (K_ij generated in-kernel:
 //        the kernel-matrix build is fused into the factorisation), then
 //          i == j : L_jj = chol(C) (8-column panels, warp-synchronous), streamed out panel by panel;
 //                   X_jj = L_jj^-1 is the separate task XDIAG that follows those panels
 //          i  > j : L_ij = C L_jj^-T: panelled forward substitution against the streamed panels of L_jj
-//                   for the chain tile i = j + 1, one tile product with X_jj for all others
+//                   for the near tiles i <= j + NEAR_BAND, one tile product with X_jj for all others
+//          i == nt (value-only evaluations): the residual row, see the kernel
 //   TRTRI (r, J), J < r, listed one block column behind the Cholesky front:
 //          X_rJ = -X_rr * sum_{K=J}^{r-1} L_rK X_KJ                  (X goes to a second matrix)
 //
@@ -29,7 +31,7 @@ namespace eb {
 
 using CfgP = TileCfg<64, 64, 32, 16>;  // 256 threads: 2 x 4 warps, 16 accumulator doubles / thread
 constexpr int PSTAGES = 4;             // cp.async ring depth (two CTAs per SM share 227 KB)
-constexpr int KS = KC + 8;               // stride of a staged KCONTIG slab (engine.cuh)
+constexpr int KS = KC + 8;             // stride of a staged KCONTIG slab (engine.cuh)
 constexpr int PSTAGE_DOUBLES = 2 * 64 * KS;
 constexpr int PS = TPS;                // stride of the 64x64 finalisation buffers (tile_ops.cuh)
 constexpr int TS = 66;                 // stride of a parked accumulator used as a [k][n] operand (conflict-free with permuted k)
