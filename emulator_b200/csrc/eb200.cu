@@ -456,9 +456,10 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   CK(cudaMemset(h->abort_flag, 0, sizeof(int)));
   CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device));
   {
-    // Queue 0: the Cholesky's chain tiles (diagonal, first sub-diagonal) in order.  Queue 1: the other
-    // Cholesky tiles column by column plus the background pre-accumulation tasks.  Queue 2: the
-    // inverse's tiles row by row plus their pre-accumulation tasks.
+    // Queue 0: the Cholesky's chain tasks (diagonal tile, first sub-diagonal tile, inverse of the diagonal
+    // tile) in order.  Queue 1: the other Cholesky tiles column by column plus the background
+    // pre-accumulation tasks.  Queues 2 and 3: the inverse's tiles row by row and their pre-accumulation
+    // tasks, claimed ready-first.
     //
     // A Cholesky tile (i, c) with more than POTRF_LA + POTRF_MINP tile products is split: a background
     // task listed right after column c - POTRF_LA - 1 (when its inputs exist) pre-accumulates tile
