@@ -104,12 +104,17 @@ def all_gather_concat(block: np.ndarray, count: int) -> np.ndarray:
     world = td.get_world_size()
     per_rank = (count + world - 1) // world
     width = int(np.prod(block.shape[1:])) if block.ndim > 1 else 1
-    send = np.zeros((per_rank, width))
-    send[: len(block)] = block.reshape(len(block), width)
+    if len(block) == per_rank:  # the common case (count divisible by world): no staging copy
+        send = block.reshape(per_rank, width)
+    else:
+        send = np.zeros((per_rank, width))
+        send[: len(block)] = block.reshape(len(block), width)
     use_cuda = td.get_backend() == "nccl"
     dev = torch.device("cuda", local_device()) if use_cuda else torch.device("cpu")
     recv_t = torch.empty((world * per_rank, width), dtype=torch.float64, device=dev)
     td.all_gather_into_tensor(recv_t, torch.from_numpy(send).to(dev))
+    if count == world * per_rank:  # slices are equal: the gathered buffer already is the result
+        return recv_t.cpu().numpy().reshape((count,) + block.shape[1:])
     recv = recv_t.cpu().numpy().reshape(world, per_rank, width)
     parts = []
     for r in range(world):
