@@ -123,6 +123,9 @@ struct eb200_gp {
   // prediction scratch
   double *T_dev = nullptr, *mu_dev = nullptr, *var_dev = nullptr, *rowss = nullptr, *T_in = nullptr;
   double *h_pred = nullptr;  // pinned staging for predict (np * (d + 2) doubles)
+  // grow-only device buffers of the grid prediction (parameter rows, independent values, results)
+  double *grid_theta = nullptr, *grid_ind = nullptr, *grid_mu = nullptr, *grid_var = nullptr;
+  size_t grid_theta_cap = 0, grid_ind_cap = 0, grid_out_cap = 0;
   TileTask* var_tasks = nullptr;
   int var_tasks_mt = -1, var_tasks_cnt = 0;
 };
@@ -351,6 +354,34 @@ __global__ void pad_rows_kernel(const double* __restrict__ src, int m, int d, in
   int c = (int)(e % dp);
   size_t r = e / dp;
   dst[e] = (c < d) ? src[r * d + c] : 0.0;
+}
+
+// Query rows of a prediction grid, built on the device: row q = (independent[q % n_ind], theta[q / n_ind][:]),
+// optionally rounded to float32 first (the reference's emulators cast their query points to float32,
+// gaussian_process.py:277-279), written zero-padded to dp columns.
+__global__ void grid_rows_kernel(const double* __restrict__ theta, const double* __restrict__ ind, size_t q0, int mc,
+                                 int n_ind, int d, int dp, int round_f32, double* __restrict__ dst) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)mc * dp) return;
+  const int c = (int)(e % dp);
+  const size_t q = q0 + e / dp;
+  double v = 0.0;
+  if (c == 0)
+    v = ind[q % n_ind];
+  else if (c < d)
+    v = theta[(q / n_ind) * (size_t)(d - 1) + (c - 1)];
+  if (round_f32) v = (double)(float)v;
+  dst[e] = v;
+}
+
+int grow(double** buf, size_t* cap, size_t need) {
+  if (*cap >= need) return 0;
+  if (*buf) CK(cudaFree(*buf));
+  *buf = nullptr;
+  *cap = 0;
+  CK(cudaMalloc(buf, need * sizeof(double)));
+  *cap = need;
+  return 0;
 }
 
 int ensure_var_tasks(eb200_gp* h, int mt) {
@@ -595,7 +626,7 @@ int eb200_gp_destroy(eb200_gp* h) {
   if (h->g_val) cudaGraphExecDestroy(h->g_val);
   void* dev[] = {h->A, h->W, h->X, h->noise, h->r, h->z, h->alpha, h->logdet_part, h->tpartial,
                  h->trace_partial, h->p_dev, h->out_dev, h->kp, h->info, h->tasks, h->ktiles, h->T_dev, h->T_in,
-                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->ftasks, h->ftasks_v, h->inv_order, h->counter, h->ready, h->abort_flag, h->rdiag};
+                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->grid_theta, h->grid_ind, h->grid_mu, h->grid_var, h->ftasks, h->ftasks_v, h->inv_order, h->counter, h->ready, h->abort_flag, h->rdiag};
   for (void* p : dev)
     if (p) cudaFree(p);
   {
@@ -782,6 +813,41 @@ int eb200_gp_predict_host(eb200_gp* h, int m, const double* t_host, int want_var
     memcpy(mu_host + q0, stage_mu, mc * sizeof(double));
     if (want_var) memcpy(var_host + q0, stage_var, mc * sizeof(double));
   }
+  return 0;
+}
+
+int eb200_gp_predict_grid_host(eb200_gp* h, int n_theta, const double* theta_host, int n_ind, const double* ind_host,
+                               int round_f32, int want_var, double* mu_host, double* var_host) {
+  if (!h || !theta_host || !ind_host || !mu_host || (want_var && !var_host)) return fail("predict_grid: null argument");
+  if (n_theta < 0 || n_ind < 1 || h->d < 2) return fail("predict_grid: needs n_ind >= 1 and a kernel dimension >= 2");
+  if (!h->factor_valid) return fail("predict: no factorisation resident (evaluate with EB200_EVAL_LML or EB200_EVAL_GRAD first)");
+  if (n_theta == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t m = (size_t)n_theta * n_ind;
+  if (grow(&h->grid_theta, &h->grid_theta_cap, (size_t)n_theta * (h->d - 1))) return 1;
+  if (grow(&h->grid_ind, &h->grid_ind_cap, (size_t)n_ind)) return 1;
+  if (m > h->grid_out_cap) {
+    if (h->grid_mu) CK(cudaFree(h->grid_mu));
+    if (h->grid_var) CK(cudaFree(h->grid_var));
+    h->grid_mu = h->grid_var = nullptr;
+    h->grid_out_cap = 0;
+    CK(cudaMalloc(&h->grid_mu, m * sizeof(double)));
+    CK(cudaMalloc(&h->grid_var, m * sizeof(double)));
+    h->grid_out_cap = m;
+  }
+  CK(cudaMemcpyAsync(h->grid_theta, theta_host, (size_t)n_theta * (h->d - 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->grid_ind, ind_host, (size_t)n_ind * sizeof(double), cudaMemcpyHostToDevice, st));
+  for (size_t q0 = 0; q0 < m; q0 += h->np) {
+    const int mc = (int)std::min<size_t>(h->np, m - q0);
+    const size_t tot = (size_t)mc * h->dp;
+    grid_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->grid_theta, h->grid_ind, q0, mc, n_ind, h->d, h->dp,
+                                                                      round_f32, h->T_dev);
+    if (predict_chunk(h, mc, want_var, h->grid_mu + q0, want_var ? h->grid_var + q0 : nullptr, st)) return 1;
+  }
+  CK(cudaMemcpyAsync(mu_host, h->grid_mu, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (want_var) CK(cudaMemcpyAsync(var_host, h->grid_var, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return 0;
 }
 

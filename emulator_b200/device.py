@@ -125,6 +125,25 @@ class DeviceProblem:
         )
         return (mu, var) if want_var else mu
 
+    def predict_grid(self, theta: np.ndarray, independent: np.ndarray, want_var: bool = True, round_f32: bool = True):
+        """Predict every row of theta[n_theta, d-1] at every independent value; returns arrays
+        [n_theta, n_ind].  The query rows (independent, theta...) are formed on the device."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        independent = np.ascontiguousarray(independent, dtype=np.float64)
+        if theta.ndim != 2 or theta.shape[1] != self.d - 1 or independent.ndim != 1 or len(independent) < 1:
+            raise ValueError(f"theta must be [n_theta, {self.d - 1}] and independent a non-empty vector")
+        n_theta, n_ind = theta.shape[0], len(independent)
+        mu = np.empty((n_theta, n_ind))
+        var = np.empty((n_theta, n_ind)) if want_var else None
+        _lib.check(
+            self._lib.eb200_gp_predict_grid_host(
+                self._h, n_theta, _lib.as_double_ptr(theta), n_ind, _lib.as_double_ptr(independent), int(bool(round_f32)),
+                int(bool(want_var)), _lib.as_double_ptr(mu), _lib.as_double_ptr(var) if want_var else None,
+            ),
+            "eb200_gp_predict_grid_host",
+        )
+        return (mu, var) if want_var else mu
+
     # -- device-pointer variants (inputs already in HBM; asynchronous) ----------------------------
     def evaluate_device(self, p_ptr: int, want_grad: bool, result_ptr: int, stream: int = 0, value_only: bool = False):
         _lib.check(

@@ -59,6 +59,15 @@ class GaussianProcessEmulator(BaseEmulator):
         t = query_matrix(independent, model_parameters, self.parameter_order)
         return self.emulator.predict(y=self.dependent_variables, t=t, return_cov=False, return_var=False)
 
+    def predict_grid(self, theta_rows: np.ndarray, independent: np.ndarray, want_var: bool = True):
+        """
+        Every parameter row of `theta_rows` (columns in `parameter_order`) at every value of `independent`,
+        with the query rows formed on the device: mean[n_theta, n_ind] (and variance).  Same values as
+        predict_values row by row (not in the reference API; what the sweeps are built on).
+        """
+        self._require_trained()
+        return self.emulator.predict_grid(self.dependent_variables, theta_rows, independent, return_var=want_var)
+
     def predict_batch(self, query_rows: np.ndarray, want_var: bool = True):
         """
         Batched prediction at arbitrary rows [independent, theta...] in ONE device call (the

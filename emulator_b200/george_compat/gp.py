@@ -343,6 +343,29 @@ class GP:
             mu, var = self._problem.predict(xs, want_var=True)
         return mu + mean_t, var
 
+    def predict_grid(self, y, theta, independent, return_var=True, round_f32=True):
+        """
+        Predictions at every row of `theta` [n_theta, ndim-1] for every value of `independent`: the query
+        rows (independent_b, theta_r...) that the sweeps of swiftemulator build on the host, one emulator
+        call per parameter row (mocking/__init__.py:84-95), are formed on the device instead.  Returns
+        mean[n_theta, n_ind] (and var).  `round_f32` rounds the rows to float32 first, as the emulators do.
+        """
+        self._residual(y)
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        independent = np.ascontiguousarray(independent, dtype=np.float64)
+        with self._using_device():
+            self._evaluate(want_grad=False, need_state=True)
+            out = self._problem.predict_grid(theta, independent, want_var=return_var, round_f32=round_f32)
+        mu = out[0] if return_var else out
+        if not (isinstance(self.mean, ConstantModel) and self.mean.value == 0.0):
+            # a non-trivial mean model is a host callable: it needs the rows
+            dtype = np.float32 if round_f32 else np.float64
+            rows = np.empty((theta.shape[0] * len(independent), self.ndim), dtype=dtype)
+            rows[:, 0] = np.tile(independent, theta.shape[0])
+            rows[:, 1:] = np.repeat(theta, len(independent), axis=0)
+            mu = mu + self._call_mean(rows.astype(np.float64)).reshape(mu.shape)
+        return (mu, out[1]) if return_var else mu
+
     # ---- lifetime ---------------------------------------------------------------------------------
     def close(self):
         self.release_device()

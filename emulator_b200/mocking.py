@@ -2,8 +2,9 @@
 Prediction sweeps: `mock_hypercube` and `mock_sweep` with the reference's signatures and
 outputs (/root/reference/swiftemulator/mocking/__init__.py:17-200).  Where the reference calls
 `emulator.predict_values` once per parameter point in a Python loop (:84-95, :187-198), all
-(theta x independent) query rows go to the device in one batched call when the emulator
-offers `predict_batch`; other emulators take the per-point path.
+(theta x independent) query rows are predicted in one batched device call -- formed on the device
+when the emulator offers `predict_grid`, on the host with `predict_batch` -- and other emulators take
+the per-point path.
 """
 
 from __future__ import annotations
@@ -23,7 +24,14 @@ def _unique_independents(emulator) -> np.ndarray:
 def _predict_all(emulator, parameters: ModelParameters, independent: np.ndarray, kwargs) -> ModelValues:
     out = {}
     uids = list(parameters.model_parameters.keys())
-    if hasattr(emulator, "predict_batch") and not kwargs:
+    if hasattr(emulator, "predict_grid") and not kwargs:
+        # one device call; the (independent, theta) query rows are formed on the device
+        order = emulator.parameter_order
+        theta = np.array([[parameters.model_parameters[uid][name] for name in order] for uid in uids], dtype=np.float64)
+        mean, var = emulator.predict_grid(theta.reshape(len(uids), len(order)), independent, want_var=True)
+        for k, uid in enumerate(uids):
+            out[uid] = {"independent": independent, "dependent": mean[k], "dependent_error": var[k]}
+    elif hasattr(emulator, "predict_batch") and not kwargs:
         order = emulator.parameter_order
         rows = np.empty((len(uids) * len(independent), len(order) + 1), dtype=np.float32)
         for k, uid in enumerate(uids):

@@ -40,7 +40,7 @@ def saltelli_design(model_specification: ModelSpecification, base_samples: int, 
 
 
 def sweep_predict(emulator, theta_rows: np.ndarray, independent: np.ndarray, want_var: bool = True,
-                  chunk_rows: int = 1 << 16):
+                  chunk_rows: int = 1 << 20):
     """
     Predict every theta row at every independent value: returns mean[n_theta, n_ind]
     (and var).  This rank handles a contiguous slice of the theta rows; results are
@@ -52,16 +52,20 @@ def sweep_predict(emulator, theta_rows: np.ndarray, independent: np.ndarray, wan
     mean = np.empty((len(mine), n_ind))
     var = np.empty((len(mine), n_ind)) if want_var else None
     thetas_per_chunk = max(1, chunk_rows // n_ind)
+    on_device = hasattr(emulator, "predict_grid")  # query rows formed on the device: only theta crosses the bus
     for c0 in range(0, len(mine), thetas_per_chunk):
         block = mine[c0 : c0 + thetas_per_chunk]
-        rows = np.empty((len(block) * n_ind, theta_rows.shape[1] + 1), dtype=np.float32)
-        rows[:, 0] = np.tile(independent, len(block))
-        rows[:, 1:] = np.repeat(block, n_ind, axis=0)
-        if want_var:
-            m, v = emulator.predict_batch(rows, want_var=True)
-            var[c0 : c0 + len(block)] = v.reshape(len(block), n_ind)
+        if on_device:
+            out = emulator.predict_grid(block, independent, want_var=want_var)
+            m, v = out if want_var else (out, None)
         else:
-            m = emulator.predict_batch(rows, want_var=False)
+            rows = np.empty((len(block) * n_ind, theta_rows.shape[1] + 1), dtype=np.float32)
+            rows[:, 0] = np.tile(independent, len(block))
+            rows[:, 1:] = np.repeat(block, n_ind, axis=0)
+            out = emulator.predict_batch(rows, want_var=want_var)
+            m, v = out if want_var else (out, None)
+        if want_var:
+            var[c0 : c0 + len(block)] = v.reshape(len(block), n_ind)
         mean[c0 : c0 + len(block)] = m.reshape(len(block), n_ind)
     mean = dist.all_gather_concat(mean, n_theta)
     if want_var:

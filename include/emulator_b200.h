@@ -84,6 +84,14 @@ int eb200_gp_predict_host(eb200_gp* gp, int m, const double* t_host, int want_va
 int eb200_gp_predict_device(eb200_gp* gp, int m, const double* t_dev, int want_var, double* mu_dev,
                             double* var_dev, void* stream);
 
+/* Prediction on a grid: every parameter row theta[r][0..d-2] at every independent value ind[b]; query row
+ * r * n_ind + b is (ind[b], theta[r][:]) -- the rows mock_sweep / mock_hypercube and the Sobol sweep
+ * build on the host one emulator call at a time (mocking/__init__.py:84-95, :187-198).  The rows are
+ * formed on the device (round_f32: rounded to float32 first, as the reference's emulators do with
+ * their query points); only theta, ind and the results cross the bus.  mu, var: [n_theta * n_ind]. */
+int eb200_gp_predict_grid_host(eb200_gp* gp, int n_theta, const double* theta_host, int n_ind, const double* ind_host,
+                               int round_f32, int want_var, double* mu_host, double* var_host);
+
 int eb200_gp_synchronize(eb200_gp* gp);
 
 /* Test / diagnostics hooks (not used by the product path).

@@ -77,6 +77,16 @@ class OracleBackedGP:
     def predict(self, y, t, return_cov=True, return_var=False, **kwargs):
         return self._gp.predict(y, t, return_cov=return_cov, return_var=return_var)
 
+    def predict_grid(self, y, theta, independent, return_var=True, round_f32=True):
+        theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        independent = np.asarray(independent, dtype=np.float64)
+        rows = np.empty((len(theta) * len(independent), self.ndim), dtype=np.float32 if round_f32 else np.float64)
+        rows[:, 0] = np.tile(independent, len(theta))
+        rows[:, 1:] = np.repeat(theta, len(independent), axis=0)
+        out = self.predict(y, rows.astype(np.float64), return_cov=False, return_var=return_var)
+        shape = (len(theta), len(independent))
+        return (out[0].reshape(shape), out[1].reshape(shape)) if return_var else out.reshape(shape)
+
     def close(self):
         pass
 

@@ -81,6 +81,34 @@ def test_prediction_matches_oracle(n, d, m):
     gp.close()
 
 
+@pytest.mark.parametrize("n,d,n_theta,n_ind", [(300, 4, 7, 5), (640, 9, 300, 32), (200, 2, 1, 1), (1000, 3, 4097, 3)])
+def test_grid_prediction_equals_row_by_row_prediction(n, d, n_theta, n_ind):
+    """Query rows formed on the device (float32-rounded like the emulators' query points) must give
+    exactly what predict gives on the same rows built on the host."""
+    x, y, diag = problem(n, d, seed=n + n_theta)
+    gp = device_problem(x, diag, y)
+    p = orc.default_parameter_vector(d) + 0.15
+    gp.evaluate(p, False)
+    rng = np.random.default_rng(n_theta)
+    theta = rng.random((n_theta, d - 1)) * 1.7 - 0.3
+    ind = np.linspace(0.0, 1.0, n_ind) + 1e-9
+    rows = np.empty((n_theta * n_ind, d), dtype=np.float32)
+    rows[:, 0] = np.tile(ind, n_theta)
+    rows[:, 1:] = np.repeat(theta, n_ind, axis=0)
+    mu_ref, var_ref = gp.predict(rows.astype(np.float64), True)
+    mu, var = gp.predict_grid(theta, ind, True)
+    assert mu.shape == (n_theta, n_ind)
+    assert np.array_equal(mu.ravel(), mu_ref) and np.array_equal(var.ravel(), var_ref)
+    assert np.array_equal(gp.predict_grid(theta, ind, False), mu)
+    # unrounded rows: against the oracle
+    k = min(3, n_theta)
+    mu64, var64 = gp.predict_grid(theta[:k], ind, True, round_f32=False)
+    rows64 = np.column_stack([np.tile(ind, k), np.repeat(theta[:k], n_ind, axis=0)])
+    ref = orc.predict(p, x, diag, y, rows64)
+    assert relmax(mu64.ravel(), ref[0]) <= TOL and np.max(np.abs(var64.ravel() - ref[1])) <= TOL * orc.amplitude(p, d)
+    gp.close()
+
+
 def test_prediction_requires_factorisation_and_follows_latest_parameters():
     x, y, diag = problem(120, 3)
     gp = device_problem(x, diag, y)
