@@ -190,7 +190,8 @@ __device__ __forceinline__ void tile_cholesky(double (&v)[2][8], double* sL, dou
 // Y = V L^-T for the tile held in v (rows independent), L in sL, reciprocal pivots in rd; forward
 // substitution by 8-column panels with a CTA barrier per panel (measured: the flag-synchronised
 // variant is slower here -- 9.8k vs 7.6k cycles -- because every warp has the same amount of
-// update work and nothing to hide it behind).  Result in sOut ([64][TPS]).
+// update work and nothing to hide it behind).  Result in sOut ([64][TPS]).  The kernels use the streamed
+// variant below; this one is the reference point of tools/microbench/tile_ops.cu.
 __device__ __forceinline__ void tile_trsm(double (&v)[2][8], const double* sL, const double* rd, double* sOut) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int p = 0; p < 8; ++p) {
