@@ -281,3 +281,66 @@ def test_vectorized_ensemble_sampler_walks_the_same_chain():
     assert blocks[0] == 12 and set(blocks[1:]) == {6}  # initial ensemble, then half-ensembles
     with pytest.raises(ValueError):
         EnsembleSampler(4, 2, lambda ps: np.zeros(3), vectorize=True).run_mcmc(np.zeros((4, 2)), 1)
+
+
+def test_gp_handle_residency_logic_with_a_fake_device(monkeypatch):
+    """Pin / evict / re-create logic of george_compat.GP, exercised without a GPU: the device problem is
+    replaced by a fake that counts its live instances and answers with the oracle."""
+    from emulator_b200 import george_compat as george
+    from emulator_b200.george_compat import gp as gp_module
+    from oracle import gp_oracle
+
+    live = {"count": 0, "created": 0}
+
+    class FakeProblem:
+        def __init__(self, x, noise, device=0):
+            self.x, self.noise, self.r = x, noise, None
+            live["count"] += 1
+            live["created"] += 1
+
+        def close(self):
+            live["count"] -= 1
+
+        def set_residual(self, r):
+            self.r = r.copy()
+
+        def evaluate(self, p, want_grad=True, value_only=False):
+            lml, grad, logdet, quad = gp_oracle.lml_and_grad(p, self.x, self.noise, self.r)
+            return lml, (grad if want_grad else np.zeros(len(p))), 0, logdet, quad
+
+        def predict(self, t, want_var=True):
+            raise AssertionError("not used here")
+
+    monkeypatch.setattr(gp_module, "DeviceProblem", FakeProblem)
+    monkeypatch.setattr(gp_module._lib, "require_gpu", lambda: None)
+    budget = {"free": 10}
+    monkeypatch.setattr(gp_module._Residency, "free_bytes", staticmethod(lambda device: budget["free"] - live["count"] * 4))
+    monkeypatch.setattr(gp_module._Residency, "needed_bytes", staticmethod(lambda n: 4))
+    monkeypatch.setattr(gp_module._residency, "RESERVE", 0)
+
+    gps, ys = [], []
+    for k in range(4):
+        x, y, yerr = synthetic.design_arrays(30, 2, seed=k)
+        g = george.GP(1**2 * george.kernels.ExpSquaredKernel(np.ones(2), ndim=2))
+        g.compute(x, yerr)
+        gps.append(g); ys.append(y)
+    assert live["count"] == 0  # lazy
+    values = [g.log_likelihood(y) for g, y in zip(gps, ys)]
+    # the budget (10) holds two handles of 4 "bytes": the two least recently used ones were released
+    assert live["count"] == 2 and [g.resident for g in gps] == [False, False, True, True]
+    # cached values are served without a handle
+    assert gps[0].log_likelihood(ys[0]) == values[0] and not gps[0].resident and live["created"] == 4
+    # a new parameter vector needs the device again: the LRU handle (gps[2]) goes
+    gps[0].set_parameter_vector(gps[0].get_parameter_vector() + 0.1)
+    assert np.isfinite(gps[0].log_likelihood(ys[0]))
+    assert [g.resident for g in gps] == [True, False, False, True] and live["created"] == 5
+    # a pinned handle is never evicted, and cannot be released by hand
+    with gps[3]._using_device():
+        gps[1].set_parameter_vector(gps[1].get_parameter_vector() - 0.1)
+        gps[1].log_likelihood(ys[1])
+        assert gps[3].resident and not gps[0].resident
+        with pytest.raises(RuntimeError):
+            gps[3].release_device()
+    for g in gps:
+        g.close()
+    assert live["count"] == 0
