@@ -417,3 +417,40 @@ def test_concurrent_handles_from_threads_agree_with_sequential():
         threaded = list(pool.map(work, problems))
     for a, b in zip(sequential, threaded):
         assert a[0] == b[0] and np.array_equal(a[1], b[1]) and b[2] == 0
+
+
+def test_empty_and_invalid_inputs():
+    """Empty query / parameter blocks return empty results; impossible problems are refused with a message."""
+    from emulator_b200.device import DeviceProblem
+
+    x, y, diag = problem(70, 3)
+    gp = device_problem(x, diag, y)
+    p = orc.default_parameter_vector(3)
+    gp.evaluate(p, False)
+    mu, var = gp.predict(np.zeros((0, 3)), True)
+    assert mu.shape == (0,) and var.shape == (0,)
+    mu, var = gp.predict_grid(np.zeros((0, 2)), np.array([0.5]), True)
+    assert mu.shape == (0, 1) and var.shape == (0, 1)
+    lml, info, _, _ = gp.evaluate_value_batch(np.zeros((0, 4)))
+    assert lml.shape == (0,) and info.shape == (0,)
+    with pytest.raises(ValueError):
+        gp.evaluate(np.zeros(3), True)            # wrong parameter count
+    with pytest.raises(ValueError):
+        gp.predict(np.zeros((4, 2)), True)        # wrong query dimension
+    with pytest.raises(ValueError):
+        gp.set_residual(np.zeros(69))             # wrong residual length
+    with pytest.raises(ValueError):
+        gp.predict_grid(np.zeros((2, 3)), np.array([0.5]), True)  # theta must have d - 1 columns
+    gp.close()
+    with pytest.raises(ValueError):
+        DeviceProblem(np.zeros((5, 17)), np.ones(5))   # kernel dimension above the supported maximum
+    with pytest.raises(RuntimeError):
+        DeviceProblem(np.zeros((0, 2)), np.ones(0))    # no training rows
+    # non-finite hyperparameters: the factorisation fails (info != 0) or the value is not finite, never a hang
+    gp = device_problem(x, diag, y)
+    out = gp.evaluate(np.array([np.nan, 0.0, 0.0, 0.0]), True)
+    assert out[2] != 0 or not np.isfinite(out[0])
+    out = gp.evaluate(np.array([800.0, 0.0, 0.0, 0.0]), False, value_only=True)   # exp overflow
+    assert out[2] != 0 or not np.isfinite(out[0])
+    assert gp.evaluate(p, True)[2] == 0  # and the handle recovers
+    gp.close()
