@@ -117,7 +117,10 @@ struct eb200_gp {
   int n_sms = 148;
   int n_ktiles = 0, n_lauum = 0, lauum_full_off = 0, lauum_full_cnt = 0;
   std::vector<Op> ops;
-  cudaGraphExec_t g_grad = nullptr, g_lml = nullptr, g_val = nullptr;
+  cudaGraphExec_t g_grad = nullptr, g_lml = nullptr, g_val = nullptr;  // kernels only (device-pointer entry points)
+  // the same with the copy of the parameters from h_p and of the result into h_out as graph nodes: one API
+  // call per evaluation from host buffers
+  cudaGraphExec_t gh_grad = nullptr, gh_lml = nullptr, gh_val = nullptr;
   int launches_grad = 0, launches_lml = 0, launches_val = 0;
   bool factor_valid = false;
   // prediction scratch
@@ -309,10 +312,13 @@ int enqueue_eval(eb200_gp* h, cudaStream_t st, int mode, int max_stage, double* 
   return 0;
 }
 
-int capture_graph(eb200_gp* h, int mode, cudaGraphExec_t* exec, int* launches) {
+int capture_graph(eb200_gp* h, int mode, cudaGraphExec_t* exec, int* launches, bool host_copies = false) {
   cudaGraph_t graph;
   CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  if (host_copies) cudaMemcpyAsync(h->p_dev, h->h_p, (h->d + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream);
   int rc = enqueue_eval(h, h->stream, mode, 99, nullptr, launches);
+  if (host_copies)
+    cudaMemcpyAsync(h->h_out, h->out_dev, EB200_RESULT_LEN(h->d) * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
   cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
   if (rc) return rc;
   CK(e);
@@ -613,6 +619,9 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   if (capture_graph(h, EB200_EVAL_GRAD, &h->g_grad, &h->launches_grad)) return 1;
   if (capture_graph(h, EB200_EVAL_LML, &h->g_lml, &h->launches_lml)) return 1;
   if (capture_graph(h, EB200_EVAL_VALUE_ONLY, &h->g_val, &h->launches_val)) return 1;
+  if (capture_graph(h, EB200_EVAL_GRAD, &h->gh_grad, nullptr, true)) return 1;
+  if (capture_graph(h, EB200_EVAL_LML, &h->gh_lml, nullptr, true)) return 1;
+  if (capture_graph(h, EB200_EVAL_VALUE_ONLY, &h->gh_val, nullptr, true)) return 1;
   *out = h;
   return 0;
 }
@@ -624,6 +633,8 @@ int eb200_gp_destroy(eb200_gp* h) {
   if (h->g_grad) cudaGraphExecDestroy(h->g_grad);
   if (h->g_lml) cudaGraphExecDestroy(h->g_lml);
   if (h->g_val) cudaGraphExecDestroy(h->g_val);
+  for (cudaGraphExec_t g : {h->gh_grad, h->gh_lml, h->gh_val})
+    if (g) cudaGraphExecDestroy(g);
   void* dev[] = {h->A, h->W, h->X, h->noise, h->r, h->z, h->alpha, h->logdet_part, h->tpartial,
                  h->trace_partial, h->p_dev, h->out_dev, h->kp, h->info, h->tasks, h->ktiles, h->T_dev, h->T_in,
                  h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->grid_theta, h->grid_ind, h->grid_mu, h->grid_var, h->ftasks, h->ftasks_v, h->inv_order, h->counter, h->ready, h->abort_flag, h->rdiag};
@@ -676,6 +687,9 @@ int eb200_gp_set_residual_device(eb200_gp* h, const double* r_dev, void* stream)
 static cudaGraphExec_t eval_graph(eb200_gp* h, int mode) {
   return mode == EB200_EVAL_GRAD ? h->g_grad : (mode == EB200_EVAL_VALUE_ONLY ? h->g_val : h->g_lml);
 }
+static cudaGraphExec_t eval_graph_host(eb200_gp* h, int mode) {
+  return mode == EB200_EVAL_GRAD ? h->gh_grad : (mode == EB200_EVAL_VALUE_ONLY ? h->gh_val : h->gh_lml);
+}
 
 int eb200_gp_eval_device(eb200_gp* h, const double* p_dev, int mode, double* result_dev, void* stream) {
   if (!h || !p_dev) return fail("eval: null argument");
@@ -696,14 +710,40 @@ int eb200_gp_eval_host(eb200_gp* h, const double* p_host, int mode, double* resu
   CK(cudaSetDevice(h->device));
   const int len = EB200_RESULT_LEN(h->d);
   memcpy(h->h_p, p_host, (h->d + 1) * sizeof(double));
-  CK(cudaMemcpyAsync(h->p_dev, h->h_p, (h->d + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaGraphLaunch(eval_graph(h, mode), h->stream));
-  CK(cudaMemcpyAsync(h->h_out, h->out_dev, len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaGraphLaunch(eval_graph_host(h, mode), h->stream));  // parameters in, kernels, result out: one launch
   CK(cudaStreamSynchronize(h->stream));
   memcpy(result_host, h->h_out, len * sizeof(double));
   if (mode != EB200_EVAL_GRAD)
     for (int i = 0; i <= h->d; ++i) result_host[1 + i] = 0.0;
   h->factor_valid = mode != EB200_EVAL_VALUE_ONLY;
+  return 0;
+}
+
+// One evaluation on each of nb handles, enqueued back to back on the handles' own streams and collected
+// afterwards: small problems (the per-bin GPs) overlap on the device instead of paying one launch
+// latency after the other, and the host makes ONE call instead of nb.
+int eb200_gp_eval_multi_host(eb200_gp** gps, int nb, const double* p_host, int p_stride, int mode, double* result_host,
+                             int result_stride) {
+  if (!gps || !p_host || !result_host || nb < 0) return fail("eval_multi: bad argument");
+  if (mode < 0 || mode > 2) return fail("eval: mode must be EB200_EVAL_LML, EB200_EVAL_GRAD or EB200_EVAL_VALUE_ONLY");
+  for (int b = 0; b < nb; ++b) {
+    eb200_gp* h = gps[b];
+    if (!h) return fail("eval_multi: null handle");
+    if (p_stride < h->d + 1 || result_stride < EB200_RESULT_LEN(h->d)) return fail("eval_multi: stride too small");
+    CK(cudaSetDevice(h->device));
+    memcpy(h->h_p, p_host + (size_t)b * p_stride, (h->d + 1) * sizeof(double));
+    CK(cudaGraphLaunch(eval_graph_host(h, mode), h->stream));
+  }
+  for (int b = 0; b < nb; ++b) {
+    eb200_gp* h = gps[b];
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    double* dst = result_host + (size_t)b * result_stride;
+    memcpy(dst, h->h_out, EB200_RESULT_LEN(h->d) * sizeof(double));
+    if (mode != EB200_EVAL_GRAD)
+      for (int i = 0; i <= h->d; ++i) dst[1 + i] = 0.0;
+    h->factor_valid = mode != EB200_EVAL_VALUE_ONLY;
+  }
   return 0;
 }
 

@@ -190,3 +190,28 @@ class DeviceProblem:
         out = np.empty(self.n)
         _lib.check(self._lib.eb200_gp_debug_alpha(self._h, _lib.as_double_ptr(out)), "debug_alpha")
         return out
+
+
+def evaluate_many(problems, ps, want_grad: bool = True, value_only: bool = False):
+    """
+    One evaluation on each problem of `problems` (DeviceProblem, equal kernel dimension) at the rows of
+    ps[nb, P], in ONE native call: the evaluations are enqueued on the problems' own streams and overlap
+    on the device.  Returns (lml[nb], grad[nb, P], info[nb]).
+    """
+    nb = len(problems)
+    ps = np.ascontiguousarray(ps, dtype=np.float64)
+    if nb == 0:
+        return np.zeros(0), np.zeros((0, ps.shape[1] if ps.ndim == 2 else 0)), np.zeros(0, dtype=np.int64)
+    d = problems[0].d
+    if ps.shape != (nb, d + 1) or any(q.d != d for q in problems):
+        raise ValueError(f"need one parameter vector of {d + 1} entries per problem, all of kernel dimension {d}")
+    lib = problems[0]._lib
+    length = _lib.result_len(d)
+    out = np.zeros((nb, length))
+    handles = (c_void_p * nb)(*[q._h for q in problems])
+    _lib.check(
+        lib.eb200_gp_eval_multi_host(handles, nb, _lib.as_double_ptr(ps), d + 1, _mode(want_grad, value_only),
+                                     _lib.as_double_ptr(out), length),
+        "eb200_gp_eval_multi_host",
+    )
+    return out[:, 0].copy(), out[:, 1 : d + 2].copy(), out[:, d + 2].astype(np.int64)

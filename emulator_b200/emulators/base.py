@@ -55,6 +55,31 @@ def optimise_gp(gp, y):
     return result
 
 
+def optimise_gps_lockstep(gps, ys):
+    """
+    The same optimisation for many equally shaped GPs at once (per-bin emulators): all problems advance
+    together, one batched device call per round (emulator_b200/optimise.py).  Starts from each kernel's
+    current parameter vector and leaves every GP at its optimum, whatever the status says -- as
+    optimise_gp does.  Opt-in: the optimiser is not scipy's, so iterates (not optima) differ.
+    """
+    from ..optimise import minimise_lockstep
+
+    backend = george
+    if not hasattr(backend, "pinned_evaluator"):
+        raise NotImplementedError("lock-step fitting needs the device backend (george_compat)")
+    with backend.pinned_evaluator(gps, ys) as evaluate:
+
+        def fun_and_grad(indices, points):
+            lml, grad, info = evaluate(list(indices), points)
+            bad = (info != 0) | ~np.isfinite(lml)
+            return np.where(bad, np.inf, -lml), -grad
+
+        result = minimise_lockstep(fun_and_grad, np.array([gp.get_parameter_vector() for gp in gps]))
+    for gp, x in zip(gps, result.x):
+        gp.set_parameter_vector(x)
+    return result
+
+
 @attr.s
 class BaseEmulator(object):
     ordering: Optional[List[Hashable]] = None

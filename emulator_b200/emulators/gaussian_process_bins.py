@@ -15,7 +15,7 @@ import attr
 import numpy as np
 
 from .. import dist
-from .base import BaseEmulator, build_gp, default_kernel, optimise_gp
+from .base import BaseEmulator, build_gp, default_kernel, optimise_gp, optimise_gps_lockstep
 
 
 @attr.s
@@ -26,6 +26,11 @@ class GaussianProcessEmulatorBins(BaseEmulator):
     #: independent per-bin fits run concurrently from this many host threads; every GP owns its
     #: device handle and stream, and the C ABI calls release the GIL (results do not depend on it)
     workers: int = attr.ib(default=8)
+    #: "scipy": every bin is fitted by scipy's BFGS, as in the reference (from `workers` host threads);
+    #: "lockstep": all bins advance together through emulator_b200.optimise (one batched device call per
+    #: round; a different line search, so iterates differ while optima agree to the optimiser's tolerance)
+    fit_mode: str = attr.ib(default="scipy")
+    lockstep_result = None
 
     n_bins: int = None
     bin_centers: List[float] = None
@@ -88,7 +93,18 @@ class GaussianProcessEmulatorBins(BaseEmulator):
             optimise_gp(gp, values["dependent"])
             return b, gp
 
-        if self.mean_model is not None or self.workers <= 1 or len(mine) <= 1:
+        if self.fit_mode not in ("scipy", "lockstep"):
+            raise ValueError("fit_mode must be 'scipy' or 'lockstep'")
+        if self.fit_mode == "lockstep" and self.mean_model is None and len(mine) > 0:
+            # all bins of this rank advance together: one batched device call per optimiser round
+            mine_gps = [
+                build_gp(self.kernel, None, self.bin_model_values[b]["independent"], self.bin_model_values[b]["dependent"],
+                         self.bin_model_values[b]["dependent_errors"], device=self.device)
+                for b in mine
+            ]
+            self.lockstep_result = optimise_gps_lockstep(mine_gps, [self.bin_model_values[b]["dependent"] for b in mine])
+            results = list(zip(mine, mine_gps))
+        elif self.mean_model is not None or self.workers <= 1 or len(mine) <= 1:
             # mean_model.train mutates the shared mean-model object: keep the reference's sequential order
             results = [fit_bin(b) for b in mine]
         else:

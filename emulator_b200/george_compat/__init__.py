@@ -5,4 +5,4 @@ the reference side.
 """
 
 from . import kernels, modeling  # noqa: F401
-from .gp import GP, TINY  # noqa: F401
+from .gp import GP, TINY, pinned_evaluator  # noqa: F401

@@ -28,7 +28,7 @@ import weakref
 import numpy as np
 
 from .. import _lib
-from ..device import DeviceProblem
+from ..device import DeviceProblem, evaluate_many
 from . import kernels as _kernels
 from .modeling import CallableModel, ConstantModel, Model
 
@@ -380,3 +380,30 @@ class GP:
 
     def __deepcopy__(self, memo):
         raise TypeError("a device-resident GP cannot be deep-copied; copy the kernel and build a new GP")
+
+
+@contextlib.contextmanager
+def pinned_evaluator(gps, ys):
+    """
+    Context for optimisers that advance many GPs together (emulator_b200/optimise.py): pins the device
+    handles of `gps`, uploads their residuals (y - mean) once, and yields
+    ``evaluate(indices, vectors, want_grad=True) -> (lml, grad, info)``, which evaluates GP ``indices[k]``
+    at ``vectors[k]`` in ONE native call (the evaluations overlap on the device).  The GPs' own parameter
+    vectors are not touched; their cached values are dropped.
+    """
+    with contextlib.ExitStack() as stack:
+        for gp, y in zip(gps, ys):
+            gp._residual(y)
+            stack.enter_context(gp._using_device())
+            gp._sync_residual()
+        problems = [gp._problem for gp in gps]
+
+        def evaluate(indices, vectors, want_grad=True):
+            lml, grad, info = evaluate_many([problems[i] for i in indices], vectors, want_grad=want_grad)
+            for i in indices:
+                g = gps[i]
+                g.n_device_evaluations += 1
+                g._device_p = g._cache_key = g._cache = None
+            return lml, grad, info
+
+        yield evaluate

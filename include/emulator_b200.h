@@ -68,6 +68,13 @@ int eb200_gp_set_residual_device(eb200_gp* gp, const double* r_dev, void* stream
 int eb200_gp_eval_host(eb200_gp* gp, const double* p_host, int mode, double* result_host);
 int eb200_gp_eval_device(eb200_gp* gp, const double* p_dev, int mode, double* result_dev, void* stream);
 
+/* One evaluation (any mode) on each of nb handles -- e.g. the per-bin GPs of GaussianProcessEmulatorBins
+ * (gaussian_process_bins.py:206-262), which the reference fits one after the other -- enqueued on the
+ * handles' own streams and collected afterwards, so that small problems overlap on the device.
+ * Problem b reads p_host + b * p_stride and writes result_host + b * result_stride. */
+int eb200_gp_eval_multi_host(eb200_gp** gps, int nb, const double* p_host, int p_stride, int mode, double* result_host,
+                             int result_stride);
+
 /* nb value-only evaluations (EB200_EVAL_VALUE_ONLY semantics) at the parameter vectors p_host[nb][d+1];
  * result_host[nb][EB200_RESULT_LEN(d)].  A value-only factorisation is bound by its dependency chain
  * and leaves most SMs idle, so up to four share one launch.  This is the half-ensemble of proposals

@@ -176,3 +176,31 @@ def test_device_handles_are_released_and_recreated_within_the_memory_budget():
         res.RESERVE = old_reserve
         for g in gps:
             g.close()
+
+
+def test_bins_lockstep_fit_reaches_the_optima_of_the_scipy_fit():
+    """fit_mode="lockstep": all bins advance together (one batched device call per round).  The line
+    search is not scipy's, so iterates differ; the optima and the predictions must agree."""
+    from emulator_b200 import synthetic
+
+    spec, params, values = synthetic.make_config("C3", seed_offset=3)
+    # a small slice of C3: 6 bins, 48 simulations
+    keep = list(values.model_values.keys())[:48]
+    from emulator_b200.backend import ModelParameters, ModelValues
+    vals = ModelValues({k: {kk: np.asarray(vv)[:6] for kk, vv in values.model_values[k].items()} for k in keep})
+    pars = ModelParameters({k: params.model_parameters[k] for k in keep})
+    a = GaussianProcessEmulatorBins(fit_mode="scipy", workers=1)
+    a.fit_model(spec, pars, vals)
+    b = GaussianProcessEmulatorBins(fit_mode="lockstep")
+    b.fit_model(spec, pars, vals)
+    assert b.lockstep_result is not None and b.lockstep_result.rounds < 400
+    theta = pars.model_parameters[keep[5]]
+    ind = np.asarray(vals.model_values[keep[0]]["independent"])
+    for gp_a, gp_b, data in zip(a.bin_gaussian_process, b.bin_gaussian_process, a.bin_model_values):
+        la, lb = gp_a.log_likelihood(data["dependent"]), gp_b.log_likelihood(data["dependent"])
+        assert abs(la - lb) <= 1e-5 * max(1.0, abs(la))  # same optimum of the likelihood
+    mu_a, var_a = a.predict_values(ind, theta)
+    mu_b, var_b = b.predict_values(ind, theta)
+    assert np.allclose(mu_a, mu_b, rtol=1e-3, atol=1e-5) and np.allclose(var_a, var_b, rtol=5e-2, atol=1e-8)
+    with pytest.raises(ValueError):
+        GaussianProcessEmulatorBins(fit_mode="other").fit_model(spec, pars, vals)

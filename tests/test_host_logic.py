@@ -344,3 +344,59 @@ def test_gp_handle_residency_logic_with_a_fake_device(monkeypatch):
     for g in gps:
         g.close()
     assert live["count"] == 0
+
+
+def test_lockstep_bfgs_minimises_many_problems_together():
+    """The vectorised BFGS of emulator_b200.optimise against known minima and scipy's BFGS."""
+    from scipy.optimize import minimize
+    from emulator_b200.optimise import minimise_lockstep
+
+    rng = np.random.default_rng(0)
+    nb, P = 12, 5
+    mats = []
+    for _ in range(nb):
+        m = rng.standard_normal((P, P))
+        mats.append(m @ m.T + np.eye(P))
+    centres = rng.standard_normal((nb, P))
+    calls = []
+
+    def quartic(indices, points):
+        calls.append(len(indices))
+        f, g = [], []
+        for i, x in zip(indices, points):
+            z = x - centres[i]
+            f.append(0.5 * z @ mats[i] @ z + 0.1 * np.sum(z ** 4))
+            g.append(mats[i] @ z + 0.4 * z ** 3)
+        return np.array(f), np.array(g)
+
+    res = minimise_lockstep(quartic, np.zeros((nb, P)))
+    assert np.all(res.status == 0) and np.max(np.abs(res.x - centres)) < 1e-4
+    assert res.rounds == len(calls) and calls[0] == nb and min(calls) >= 1  # finished problems drop out
+    assert np.all(np.max(np.abs(res.jac), axis=1) < 1e-5)
+
+    def rosenbrock(indices, points):
+        f, g = [], []
+        for x in points:
+            f.append(np.sum(100.0 * (x[1:] - x[:-1] ** 2) ** 2 + (1 - x[:-1]) ** 2))
+            gg = np.zeros_like(x)
+            gg[:-1] += -400.0 * x[:-1] * (x[1:] - x[:-1] ** 2) - 2.0 * (1 - x[:-1])
+            gg[1:] += 200.0 * (x[1:] - x[:-1] ** 2)
+            g.append(gg)
+        return np.array(f), np.array(g)
+
+    x0 = 0.5 * rng.standard_normal((6, 4))
+    res = minimise_lockstep(rosenbrock, x0)
+    assert np.all(res.status == 0) and np.max(np.abs(res.x - 1.0)) < 1e-5
+    ref = minimize(lambda x: rosenbrock([0], [x])[0][0], x0[0], jac=lambda x: rosenbrock([0], [x])[1][0], method="BFGS")
+    # (the 4-d Rosenbrock function has a second, local minimum that scipy's line search may fall into)
+    assert res.fun[0] <= ref.fun + 1e-10 and np.all(res.nfev < 200)
+
+    # a failed evaluation (non-finite value) is a step that was too long, not an error
+    def walled(indices, points):
+        f, g = quartic(indices, points)
+        return np.where(np.max(np.abs(points), axis=1) > 6.0, np.inf, f), g
+
+    res = minimise_lockstep(walled, np.zeros((nb, P)))
+    assert np.all(res.status == 0) and np.max(np.abs(res.x - centres)) < 1e-4
+    with pytest.raises(ValueError):
+        minimise_lockstep(walled, np.full((nb, P), 7.0))
