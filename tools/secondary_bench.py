@@ -51,6 +51,13 @@ def fit(name, cls, cfg):
 fit("fit_C1_gpe_N1000", GaussianProcessEmulator, "C1")
 fit("fit_C2_gpe_N4096", GaussianProcessEmulator, "C2")
 fit("fit_C3_bins_64xN256", GaussianProcessEmulatorBins, "C3")
+# the same with all bins advancing in lock step (emulator_b200/optimise.py)
+spec3, params3, values3 = synthetic.make_config("C3")
+GaussianProcessEmulatorBins(fit_mode="lockstep").fit_model(spec3, params3, values3)  # warm-up
+emu3 = GaussianProcessEmulatorBins(fit_mode="lockstep")
+t0 = time.perf_counter(); emu3.fit_model(spec3, params3, values3); dt3 = time.perf_counter() - t0
+out["fit_C3_bins_64xN256_lockstep"] = {"seconds": dt3, "rounds": int(emu3.lockstep_result.rounds),
+                                       "device_evals": int(emu3.lockstep_result.nfev.sum())}
 # ---- one C4-sized evaluation (N = 8176) ----
 x, y, yerr = synthetic.design_arrays(8176, 9, seed=1238)
 noise = np.sqrt(np.ascontiguousarray(yerr ** 2, dtype=np.float64) + 1.25e-12) ** 2
