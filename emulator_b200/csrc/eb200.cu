@@ -126,6 +126,7 @@ struct eb200_gp {
   // prediction scratch
   double *T_dev = nullptr, *mu_dev = nullptr, *var_dev = nullptr, *rowss = nullptr, *T_in = nullptr;
   double *h_pred = nullptr;  // pinned staging for predict (np * (d + 2) doubles)
+  char *arena = nullptr, *pinned = nullptr;  // one device / one pinned allocation behind the small arrays above
   // grow-only device buffers of the grid prediction (parameter rows, independent values, results)
   double *grid_theta = nullptr, *grid_ind = nullptr, *grid_mu = nullptr, *grid_var = nullptr;
   size_t grid_theta_cap = 0, grid_ind_cap = 0, grid_out_cap = 0;
@@ -462,35 +463,52 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   const size_t mat_a = mat + (size_t)TB * np * sizeof(double);  // + the residual tile row of value-only evaluations
   CK(cudaMalloc(&h->A, mat_a));
   CK(cudaMalloc(&h->W, mat));
-  CK(cudaMalloc(&h->X, (size_t)np * dp * sizeof(double)));
-  CK(cudaMalloc(&h->noise, np * sizeof(double)));
-  CK(cudaMalloc(&h->r, np * sizeof(double)));
-  CK(cudaMalloc(&h->z, np * sizeof(double)));
-  CK(cudaMalloc(&h->alpha, np * sizeof(double)));
-  CK(cudaMalloc(&h->logdet_part, h->nt * sizeof(double)));
-  CK(cudaMalloc(&h->tpartial, (size_t)h->nT * np * sizeof(double)));
-  CK(cudaMalloc(&h->p_dev, (MAXD + 1) * sizeof(double)));
-  CK(cudaMalloc(&h->out_dev, (MAXD + 8) * sizeof(double)));
-  CK(cudaMalloc(&h->kp, sizeof(KernelParams)));
-  CK(cudaMalloc(&h->info, sizeof(int)));
-  CK(cudaMallocHost(&h->h_p, (MAXD + 1) * sizeof(double)));
-  CK(cudaMallocHost(&h->h_out, (MAXD + 8) * sizeof(double)));
-  CK(cudaMalloc(&h->T_dev, (size_t)np * dp * sizeof(double)));
-  CK(cudaMalloc(&h->T_in, (size_t)np * d * sizeof(double)));
-  CK(cudaMalloc(&h->mu_dev, np * sizeof(double)));
-  CK(cudaMalloc(&h->var_dev, np * sizeof(double)));
-  CK(cudaMalloc(&h->rowss, (size_t)h->nT * np * sizeof(double)));
-  CK(cudaMalloc(&h->var_tasks, (size_t)h->nT * h->nT * sizeof(TileTask)));
-  CK(cudaMallocHost(&h->h_pred, (size_t)np * (d + 2) * sizeof(double)));
-  CK(cudaMemset(h->r, 0, np * sizeof(double)));
-  CK(cudaMemset(h->z, 0, np * sizeof(double)));
-  CK(cudaMemset(h->alpha, 0, np * sizeof(double)));
+  // Everything small lives in one device arena and one pinned block: a handle used to cost ~30 cudaMalloc
+  // and as many (synchronising) cudaFree calls, which is what creating and destroying the 64 per-bin GPs
+  // of a binned emulator, or re-creating a released handle, mostly paid for.
+  {
+    struct Want { void** slot; size_t bytes; };
+    std::vector<Want> dev_wants = {
+        {(void**)&h->X, (size_t)np * dp * sizeof(double)},
+        {(void**)&h->noise, np * sizeof(double)},
+        {(void**)&h->r, np * sizeof(double)},
+        {(void**)&h->z, np * sizeof(double)},
+        {(void**)&h->alpha, np * sizeof(double)},
+        {(void**)&h->logdet_part, h->nt * sizeof(double)},
+        {(void**)&h->tpartial, (size_t)h->nT * np * sizeof(double)},
+        {(void**)&h->p_dev, (MAXD + 1) * sizeof(double)},
+        {(void**)&h->out_dev, (MAXD + 8) * sizeof(double)},
+        {(void**)&h->kp, sizeof(KernelParams)},
+        {(void**)&h->info, sizeof(int)},
+        {(void**)&h->T_dev, (size_t)np * dp * sizeof(double)},
+        {(void**)&h->T_in, (size_t)np * d * sizeof(double)},
+        {(void**)&h->mu_dev, np * sizeof(double)},
+        {(void**)&h->var_dev, np * sizeof(double)},
+        {(void**)&h->rowss, (size_t)h->nT * np * sizeof(double)},
+        {(void**)&h->var_tasks, (size_t)h->nT * h->nT * sizeof(TileTask)},
+        {(void**)&h->counter, 8 * sizeof(unsigned)},
+        {(void**)&h->abort_flag, sizeof(int)},
+        {(void**)&h->rdiag, (size_t)np * sizeof(double)},
+    };
+    auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t total = 0;
+    for (const Want& w : dev_wants) total += align(w.bytes);
+    CK(cudaMalloc(&h->arena, total));
+    CK(cudaMemset(h->arena, 0, total));  // (r, z, alpha and the flags start at zero)
+    size_t off = 0;
+    for (const Want& w : dev_wants) {
+      *w.slot = h->arena + off;
+      off += align(w.bytes);
+    }
+    const size_t pinned = align((MAXD + 1) * sizeof(double)) + align((MAXD + 8) * sizeof(double)) +
+                          (size_t)np * (d + 2) * sizeof(double);
+    CK(cudaMallocHost(&h->pinned, pinned));
+    h->h_p = reinterpret_cast<double*>(h->pinned);
+    h->h_out = reinterpret_cast<double*>(h->pinned + align((MAXD + 1) * sizeof(double)));
+    h->h_pred = reinterpret_cast<double*>(h->pinned + align((MAXD + 1) * sizeof(double)) + align((MAXD + 8) * sizeof(double)));
+  }
   CK(cudaMemset(h->W, 0, mat));
   CK(cudaMemset(h->A, 0, mat_a));  // strictly-upper 64-blocks of diagonal 128-tiles must stay zero
-  CK(cudaMalloc(&h->counter, 8 * sizeof(unsigned)));
-  CK(cudaMalloc(&h->abort_flag, sizeof(int)));
-  CK(cudaMalloc(&h->rdiag, (size_t)np * sizeof(double)));
-  CK(cudaMemset(h->abort_flag, 0, sizeof(int)));
   CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device));
   {
     // Queue 0: the Cholesky's chain tasks (diagonal tile, first sub-diagonal tile, inverse of the diagonal
@@ -616,12 +634,9 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
     CK(cudaMemcpy(h->tasks, tasks.data(), tasks.size() * sizeof(TileTask), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&h->trace_partial, (size_t)std::max(1, h->n_lauum) * (dp + 1) * sizeof(double)));
   }
-  if (capture_graph(h, EB200_EVAL_GRAD, &h->g_grad, &h->launches_grad)) return 1;
-  if (capture_graph(h, EB200_EVAL_LML, &h->g_lml, &h->launches_lml)) return 1;
-  if (capture_graph(h, EB200_EVAL_VALUE_ONLY, &h->g_val, &h->launches_val)) return 1;
-  if (capture_graph(h, EB200_EVAL_GRAD, &h->gh_grad, nullptr, true)) return 1;
-  if (capture_graph(h, EB200_EVAL_LML, &h->gh_lml, nullptr, true)) return 1;
-  if (capture_graph(h, EB200_EVAL_VALUE_ONLY, &h->gh_val, nullptr, true)) return 1;
+  // (the six evaluation graphs -- three modes, with and without the host copies -- are captured on first
+  //  use: a handle typically needs one or two of them, and capture + instantiation is most of what
+  //  creating a small handle costs)
   *out = h;
   return 0;
 }
@@ -635,9 +650,8 @@ int eb200_gp_destroy(eb200_gp* h) {
   if (h->g_val) cudaGraphExecDestroy(h->g_val);
   for (cudaGraphExec_t g : {h->gh_grad, h->gh_lml, h->gh_val})
     if (g) cudaGraphExecDestroy(g);
-  void* dev[] = {h->A, h->W, h->X, h->noise, h->r, h->z, h->alpha, h->logdet_part, h->tpartial,
-                 h->trace_partial, h->p_dev, h->out_dev, h->kp, h->info, h->tasks, h->ktiles, h->T_dev, h->T_in,
-                 h->mu_dev, h->var_dev, h->rowss, h->var_tasks, h->grid_theta, h->grid_ind, h->grid_mu, h->grid_var, h->ftasks, h->ftasks_v, h->inv_order, h->counter, h->ready, h->abort_flag, h->rdiag};
+  void* dev[] = {h->A, h->W, h->arena, h->trace_partial, h->tasks, h->ktiles, h->grid_theta, h->grid_ind, h->grid_mu, h->grid_var,
+                 h->ftasks, h->ftasks_v, h->inv_order, h->ready};
   for (void* p : dev)
     if (p) cudaFree(p);
   {
@@ -648,9 +662,7 @@ int eb200_gp_destroy(eb200_gp* h) {
       if (q) cudaFree(q);
     if (bs.h_stage) cudaFreeHost(bs.h_stage);
   }
-  if (h->h_p) cudaFreeHost(h->h_p);
-  if (h->h_out) cudaFreeHost(h->h_out);
-  if (h->h_pred) cudaFreeHost(h->h_pred);
+  if (h->pinned) cudaFreeHost(h->pinned);
   cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -661,7 +673,13 @@ int eb200_gp_dim(const eb200_gp* h) { return h ? h->d : -1; }
 int eb200_gp_padded_n(const eb200_gp* h) { return h ? h->np : -1; }
 int eb200_gp_eval_launches(const eb200_gp* h, int mode) {
   if (!h) return -1;
-  return mode == EB200_EVAL_GRAD ? h->launches_grad : (mode == EB200_EVAL_VALUE_ONLY ? h->launches_val : h->launches_lml);
+  int cnt = 0;  // kernel launches of one evaluation = kernel nodes of its graph
+  for (const Op& op : h->ops) {
+    if (op.debug_only || (op.grad_only && mode != EB200_EVAL_GRAD)) continue;
+    if (mode == EB200_EVAL_VALUE_ONLY && op.stage == 3) continue;
+    cnt += (op.kind == OP_TRMV_T) ? 2 : 1;
+  }
+  return cnt;
 }
 
 int eb200_gp_set_residual_host(eb200_gp* h, const double* r_host) {
@@ -684,12 +702,17 @@ int eb200_gp_set_residual_device(eb200_gp* h, const double* r_dev, void* stream)
   return 0;
 }
 
-static cudaGraphExec_t eval_graph(eb200_gp* h, int mode) {
-  return mode == EB200_EVAL_GRAD ? h->g_grad : (mode == EB200_EVAL_VALUE_ONLY ? h->g_val : h->g_lml);
+// The evaluation graph of a mode, captured on first use (nullptr + error message on failure).
+static cudaGraphExec_t eval_graph(eb200_gp* h, int mode, bool host_copies = false) {
+  cudaGraphExec_t* slot = host_copies ? (mode == EB200_EVAL_GRAD ? &h->gh_grad : (mode == EB200_EVAL_VALUE_ONLY ? &h->gh_val : &h->gh_lml))
+                                      : (mode == EB200_EVAL_GRAD ? &h->g_grad : (mode == EB200_EVAL_VALUE_ONLY ? &h->g_val : &h->g_lml));
+  if (*slot == nullptr) {
+    int* launches = mode == EB200_EVAL_GRAD ? &h->launches_grad : (mode == EB200_EVAL_VALUE_ONLY ? &h->launches_val : &h->launches_lml);
+    if (capture_graph(h, mode, slot, launches, host_copies)) *slot = nullptr;
+  }
+  return *slot;
 }
-static cudaGraphExec_t eval_graph_host(eb200_gp* h, int mode) {
-  return mode == EB200_EVAL_GRAD ? h->gh_grad : (mode == EB200_EVAL_VALUE_ONLY ? h->gh_val : h->gh_lml);
-}
+static cudaGraphExec_t eval_graph_host(eb200_gp* h, int mode) { return eval_graph(h, mode, true); }
 
 int eb200_gp_eval_device(eb200_gp* h, const double* p_dev, int mode, double* result_dev, void* stream) {
   if (!h || !p_dev) return fail("eval: null argument");
@@ -697,7 +720,9 @@ int eb200_gp_eval_device(eb200_gp* h, const double* p_dev, int mode, double* res
   CK(cudaSetDevice(h->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   CK(cudaMemcpyAsync(h->p_dev, p_dev, (h->d + 1) * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  CK(cudaGraphLaunch(eval_graph(h, mode), st));
+  cudaGraphExec_t g = eval_graph(h, mode);
+  if (!g) return 1;
+  CK(cudaGraphLaunch(g, st));
   if (result_dev)
     CK(cudaMemcpyAsync(result_dev, h->out_dev, EB200_RESULT_LEN(h->d) * sizeof(double), cudaMemcpyDeviceToDevice, st));
   h->factor_valid = mode != EB200_EVAL_VALUE_ONLY;  // a value-only evaluation leaves no L^-1 / alpha behind
@@ -710,7 +735,9 @@ int eb200_gp_eval_host(eb200_gp* h, const double* p_host, int mode, double* resu
   CK(cudaSetDevice(h->device));
   const int len = EB200_RESULT_LEN(h->d);
   memcpy(h->h_p, p_host, (h->d + 1) * sizeof(double));
-  CK(cudaGraphLaunch(eval_graph_host(h, mode), h->stream));  // parameters in, kernels, result out: one launch
+  cudaGraphExec_t g = eval_graph_host(h, mode);
+  if (!g) return 1;
+  CK(cudaGraphLaunch(g, h->stream));  // parameters in, kernels, result out: one launch
   CK(cudaStreamSynchronize(h->stream));
   memcpy(result_host, h->h_out, len * sizeof(double));
   if (mode != EB200_EVAL_GRAD)
@@ -732,7 +759,9 @@ int eb200_gp_eval_multi_host(eb200_gp** gps, int nb, const double* p_host, int p
     if (p_stride < h->d + 1 || result_stride < EB200_RESULT_LEN(h->d)) return fail("eval_multi: stride too small");
     CK(cudaSetDevice(h->device));
     memcpy(h->h_p, p_host + (size_t)b * p_stride, (h->d + 1) * sizeof(double));
-    CK(cudaGraphLaunch(eval_graph_host(h, mode), h->stream));
+    cudaGraphExec_t g = eval_graph_host(h, mode);
+    if (!g) return 1;
+    CK(cudaGraphLaunch(g, h->stream));
   }
   for (int b = 0; b < nb; ++b) {
     eb200_gp* h = gps[b];
