@@ -26,4 +26,5 @@ def oracle_backend(monkeypatch):
     import emulator_b200.george_compat as gc
 
     monkeypatch.setattr(gc, "GP", oracle_george.OracleBackedGP)
+    monkeypatch.setattr(gc, "pinned_evaluator", oracle_george.pinned_evaluator)
     return oracle_george.OracleBackedGP

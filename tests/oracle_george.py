@@ -7,6 +7,7 @@ for the device GP in CPU-only host-logic tests.  Never imported by the product.
 
 from __future__ import annotations
 
+import contextlib
 import sys
 import types
 
@@ -89,6 +90,30 @@ class OracleBackedGP:
 
     def close(self):
         pass
+
+
+@contextlib.contextmanager
+def pinned_evaluator(gps, ys):
+    """Oracle counterpart of george_compat.pinned_evaluator (lock-step optimisers)."""
+
+    def evaluate(indices, vectors, want_grad=True):
+        lml, grad, info = [], [], []
+        for i, v in zip(indices, vectors):
+            g = gps[i]
+            keep = g.get_parameter_vector().copy()
+            g.set_parameter_vector(v)
+            try:
+                lml.append(g._gp.log_likelihood(ys[i]))
+                grad.append(g._gp.grad_log_likelihood(ys[i]) if want_grad else np.zeros(len(g)))
+                info.append(0)
+            except np.linalg.LinAlgError:
+                lml.append(np.nan)
+                grad.append(np.zeros(len(g)))
+                info.append(1)
+            g.set_parameter_vector(keep)
+        return np.array(lml), np.array(grad), np.array(info)
+
+    yield evaluate
 
 
 def fake_george_module():

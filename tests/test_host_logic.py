@@ -400,3 +400,19 @@ def test_lockstep_bfgs_minimises_many_problems_together():
     assert np.all(res.status == 0) and np.max(np.abs(res.x - centres)) < 1e-4
     with pytest.raises(ValueError):
         minimise_lockstep(walled, np.full((nb, P), 7.0))
+
+
+def test_bins_lockstep_fit_matches_the_scipy_fit(oracle_backend):
+    """Host logic of fit_mode="lockstep" (all bins advance together) against the per-bin scipy fits."""
+    spec, params, values = synthetic.make_model(2, 14, 4, seed=6)
+    a = GaussianProcessEmulatorBins(fit_mode="scipy", workers=1)
+    a.fit_model(spec, params, values)
+    b = GaussianProcessEmulatorBins(fit_mode="lockstep")
+    b.fit_model(spec, params, values)
+    assert b.lockstep_result.x.shape == (4, 3) and np.all(b.lockstep_result.status >= 0)
+    for ga, gb, data in zip(a.bin_gaussian_process, b.bin_gaussian_process, a.bin_model_values):
+        la, lb = ga.log_likelihood(data["dependent"]), gb.log_likelihood(data["dependent"])
+        assert abs(la - lb) <= 1e-5 * max(1.0, abs(la))
+    theta = params.model_parameters[list(values.model_values.keys())[3]]
+    ind = np.asarray(values.model_values[list(values.model_values.keys())[0]]["independent"])
+    assert np.allclose(a.predict_values(ind, theta)[0], b.predict_values(ind, theta)[0], rtol=1e-3, atol=1e-6)
