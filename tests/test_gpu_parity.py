@@ -454,3 +454,35 @@ def test_empty_and_invalid_inputs():
     assert out[2] != 0 or not np.isfinite(out[0])
     assert gp.evaluate(p, True)[2] == 0  # and the handle recovers
     gp.close()
+
+
+def test_device_against_extended_precision_on_an_ill_conditioned_problem():
+    """Where K is ill conditioned (d = 1, dense design: cond(K) ~ 1e8) the device and the fp64 oracle each
+    differ from the exact answer by ~cond(K) * 2^-53; the longdouble oracle is the yardstick: the device
+    must be as close to it as the CPU path is (within a small factor), and exact to 1e-11 when K is
+    well conditioned."""
+    from oracle import gp_oracle_extended as ext
+
+    rng = np.random.default_rng(58)
+    for n, d, shift, well in ((90, 4, np.zeros(5), True), (144, 1, np.array([0.3, -0.4]), False)):
+        x = rng.random((n, d)).astype(np.float32).astype(np.float64)
+        y = np.sin(3.0 * x.sum(axis=1)) + 0.1 * rng.standard_normal(n)
+        noise = orc.noise_diagonal((0.02 * np.abs(y) + 1e-3).astype(np.float32))
+        p = orc.default_parameter_vector(d) + shift
+        exact = ext.lml_and_grad(p, x, noise, y)
+        e_lml, e_grad = float(exact[0]), np.asarray(exact[1], dtype=np.float64)
+        cpu = orc.lml_and_grad(p, x, noise, y)
+        gp = device_problem(x, noise, y)
+        lml, grad, info, _, _ = gp.evaluate(p, True)
+        assert info == 0
+        dev_l, dev_g = abs(lml - e_lml) / abs(e_lml), np.max(np.abs(grad - e_grad)) / np.max(np.abs(e_grad))
+        cpu_l, cpu_g = abs(cpu[0] - e_lml) / abs(e_lml), np.max(np.abs(cpu[1] - e_grad)) / np.max(np.abs(e_grad))
+        if well:
+            assert dev_l <= 1e-11 and dev_g <= 1e-11
+        else:
+            k = orc.kernel_value(p, x)
+            k[np.diag_indices(n)] += noise
+            floor = np.linalg.cond(k) * 2.0 ** -53
+            assert dev_l <= 50 * floor and dev_g <= 50 * floor
+            assert dev_g <= 10 * max(cpu_g, floor) and dev_l <= 10 * max(cpu_l, floor)
+        gp.close()

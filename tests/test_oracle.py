@@ -134,3 +134,27 @@ def test_golden_likelihoods_reproduce(path):
         got = orc.lml_and_grad(p, x.astype(np.float64), diag, y.astype(np.float64))
         assert got[0] == pytest.approx(lml, rel=1e-13)
         assert np.allclose(got[1], grad, rtol=1e-11, atol=1e-12)
+
+
+def test_fp64_oracle_against_extended_precision():
+    """The fp64 oracle against the longdouble restatement: ~1e-13 when K is well conditioned, and an
+    error that scales with cond(K) * 2^-53 when it is not (the yardstick for the 1e-9 parity band)."""
+    from oracle import gp_oracle_extended as ext
+
+    rng = np.random.default_rng(58)
+    for n, d, shift, bound in ((90, 4, np.zeros(5), 1e-11), (144, 1, np.array([0.3, -0.4]), None)):
+        x = rng.random((n, d)).astype(np.float32).astype(np.float64)
+        y = np.sin(3.0 * x.sum(axis=1)) + 0.1 * rng.standard_normal(n)
+        noise = orc.noise_diagonal((0.02 * np.abs(y) + 1e-3).astype(np.float32))
+        p = orc.default_parameter_vector(d) + shift
+        e = ext.lml_and_grad(p, x, noise, y)
+        o = orc.lml_and_grad(p, x, noise, y)
+        k = orc.kernel_value(p, x)
+        k[np.diag_indices(n)] += noise
+        cond = np.linalg.cond(k)
+        lml_err = abs(float(e[0]) - o[0]) / abs(o[0])
+        grad_err = np.max(np.abs(np.asarray(e[1], dtype=np.float64) - o[1])) / np.max(np.abs(o[1]))
+        limit = bound if bound is not None else 50.0 * cond * 2.0 ** -53
+        assert lml_err <= limit and grad_err <= limit, (n, d, cond, lml_err, grad_err)
+        if bound is None:
+            assert cond > 1e7  # this case is meant to be ill conditioned
