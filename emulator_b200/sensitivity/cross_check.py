@@ -20,7 +20,7 @@ import numpy as np
 
 from .. import dist
 from ..backend import ModelParameters, ModelSpecification, ModelValues
-from ..emulators.base import build_gp, default_kernel
+from ..emulators.base import build_gp, default_kernel, optimise_gps_lockstep
 from ..emulators.gaussian_process import GaussianProcessEmulator
 from ..emulators.gaussian_process_bins import GaussianProcessEmulatorBins
 
@@ -39,6 +39,11 @@ class CrossCheck(object):
     #: owns its device handle and stream; the Cholesky's dependency chain of one refit leaves SMs
     #: idle that another refit's kernels use)
     workers: int = attr.ib(default=2)
+    #: "scipy": every refit is optimised by scipy's BFGS as in the reference; "lockstep": the refits of a rank
+    #: advance together through emulator_b200.optimise (same optima, different iterates; pays for small
+    #: problems, where the per-evaluation Python overhead dominates)
+    fit_mode: str = attr.ib(default="scipy")
+    lockstep_result = None
 
     model_specification: ModelSpecification = None
     model_parameters: ModelParameters = None
@@ -65,7 +70,26 @@ class CrossCheck(object):
             emulator.fit_model(model_specification, model_parameters, _without(model_values, uid))
             return i, uid, emulator
 
-        if self.kernel is None and self.mean_model is None and self.workers > 1 and len(mine) > 1:
+        if self.fit_mode not in ("scipy", "lockstep"):
+            raise ValueError("fit_mode must be 'scipy' or 'lockstep'")
+        if self.fit_mode == "lockstep" and self.kernel is None and self.mean_model is None and len(mine) > 0:
+            # all refits of this rank advance together (emulator_b200/optimise.py): one batched device call
+            # per optimiser round.  Every refit has the same shape (one simulation left out).
+            done = []
+            for i in mine:
+                uid = self.leave_out_order[i]
+                emulator = GaussianProcessEmulator(device=self.device)
+                emulator._build_arrays(model_specification, model_parameters, _without(model_values, uid))
+                emulator.kernel = default_kernel(model_specification.number_of_parameters + 1)
+                emulator.emulator = build_gp(
+                    emulator.kernel, None, emulator.independent_variables, emulator.dependent_variables,
+                    emulator.dependent_variable_errors, device=self.device,
+                )
+                done.append((i, uid, emulator))
+            self.lockstep_result = optimise_gps_lockstep(
+                [e.emulator for _, _, e in done], [e.dependent_variables for _, _, e in done]
+            )
+        elif self.kernel is None and self.mean_model is None and self.workers > 1 and len(mine) > 1:
             with ThreadPoolExecutor(max_workers=self.workers) as pool:
                 done = list(pool.map(refit, mine))
         else:  # shared kernel / mean-model objects are mutated by fit_model: keep it sequential

@@ -204,3 +204,20 @@ def test_bins_lockstep_fit_reaches_the_optima_of_the_scipy_fit():
     assert np.allclose(mu_a, mu_b, rtol=1e-3, atol=1e-5) and np.allclose(var_a, var_b, rtol=5e-2, atol=1e-8)
     with pytest.raises(ValueError):
         GaussianProcessEmulatorBins(fit_mode="other").fit_model(spec, pars, vals)
+
+
+def test_cross_check_lockstep_on_the_device():
+    from emulator_b200 import synthetic
+    from emulator_b200.sensitivity import CrossCheck
+
+    spec, params, values = synthetic.make_model(2, 10, 6, seed=4)
+    a = CrossCheck(fit_mode="scipy", workers=1)
+    a.build_emulators(spec, params, values)
+    b = CrossCheck(fit_mode="lockstep")
+    b.build_emulators(spec, params, values)
+    for uid in a.cross_emulators:
+        ea, eb = a.cross_emulators[uid], b.cross_emulators[uid]
+        la = ea.emulator.log_likelihood(ea.dependent_variables)
+        lb = eb.emulator.log_likelihood(eb.dependent_variables)
+        assert abs(la - lb) <= 1e-5 * max(1.0, abs(la))
+    assert abs(a.get_mean_squared()[0] - b.get_mean_squared()[0]) <= 1e-3 * abs(a.get_mean_squared()[0])

@@ -416,3 +416,23 @@ def test_bins_lockstep_fit_matches_the_scipy_fit(oracle_backend):
     theta = params.model_parameters[list(values.model_values.keys())[3]]
     ind = np.asarray(values.model_values[list(values.model_values.keys())[0]]["independent"])
     assert np.allclose(a.predict_values(ind, theta)[0], b.predict_values(ind, theta)[0], rtol=1e-3, atol=1e-6)
+
+
+def test_cross_check_lockstep_matches_the_scipy_refits(oracle_backend):
+    """CrossCheck(fit_mode="lockstep"): the leave-one-out refits advance together; same optima."""
+    spec, params, values = synthetic.make_model(2, 8, 5, seed=9)
+    a = CrossCheck(fit_mode="scipy", workers=1)
+    a.build_emulators(spec, params, values)
+    b = CrossCheck(fit_mode="lockstep")
+    b.build_emulators(spec, params, values)
+    assert b.lockstep_result is not None and b.cross_fit_parameters.shape == a.cross_fit_parameters.shape
+    for uid in a.cross_emulators:
+        ea, eb = a.cross_emulators[uid], b.cross_emulators[uid]
+        la = ea.emulator.log_likelihood(ea.dependent_variables)
+        lb = eb.emulator.log_likelihood(eb.dependent_variables)
+        assert abs(la - lb) <= 1e-5 * max(1.0, abs(la))
+    ms_a, _ = a.get_mean_squared()
+    ms_b, _ = b.get_mean_squared()
+    assert abs(ms_a - ms_b) <= 1e-3 * abs(ms_a)
+    with pytest.raises(ValueError):
+        CrossCheck(fit_mode="nope").build_emulators(spec, params, values)
