@@ -93,10 +93,11 @@ struct FactorArgs {
   unsigned long long* trace;  // optional [ntasks][TRACE_SLOTS] (diagnostics), or nullptr
 };
 
-// Several independent value-only factorisations (same shapes, different hyperparameters) can share
-// one launch: a value-only evaluation is bound by its 64-step dependency chain and leaves most SMs
-// idle, so the chains of up to MAX_BATCH problems are interleaved (the ensemble sampler proposes
-// half its walkers at once).  CTA c is at home in problem c % nb and helps the others.
+// Several independent factorisations of the same shape can share one launch: a value-only evaluation,
+// and any evaluation of a small problem, is bound by its dependency chain and leaves most SMs idle, so
+// the chains of up to MAX_BATCH problems are interleaved (the ensemble sampler proposes half its walkers
+// at once; lock-step optimisers evaluate many equally shaped GPs per round).  CTA c is at home in
+// problem c % nb and helps the others.
 constexpr int MAX_BATCH = 8;
 struct FactorBatch {
   int nb;
@@ -515,7 +516,8 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
         // %smid -- 6 or 12 SMs, band of 1 or 3 sub-diagonals -- made its tile factorisations 25 %
         // faster but lost more in look-ahead and bulk capacity: 307-314 vs 321 evals/s at N = 4096.)
         const int slot = BATCH ? local : (int)(blockIdx.x % (unsigned)a0.n_sms);
-        const int first_wave = BATCH ? 1 : (blockIdx.x < (unsigned)a0.n_sms);
+        // (batched full evaluations: the CTAs of a problem alternate between its Cholesky and its inverse queues)
+        const int first_wave = BATCH ? ((local & 1) == 0) : (blockIdx.x < (unsigned)a0.n_sms);
         s_role = (slot < a0.n_chain_sms) ? 0 : ((first_wave || a0.value_only) ? 1 : 2);
       }
       __syncwarp();

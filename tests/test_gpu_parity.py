@@ -486,3 +486,36 @@ def test_device_against_extended_precision_on_an_ill_conditioned_problem():
             assert dev_l <= 50 * floor and dev_g <= 50 * floor
             assert dev_g <= 10 * max(cpu_g, floor) and dev_l <= 10 * max(cpu_l, floor)
         gp.close()
+
+
+@pytest.mark.parametrize("n,d,nb", [(256, 8, 11), (1000, 3, 9), (2048, 9, 3), (130, 2, 2)])
+def test_multi_handle_evaluation_equals_single_evaluations(n, d, nb):
+    """evaluate_many: equally shaped chain-bound problems share factorisation launches (chains interleaved);
+    every result must equal the handle's own stand-alone evaluation bit for bit, in every mode."""
+    from emulator_b200.device import evaluate_many
+
+    probs, ps, singles = [], [], []
+    for k in range(nb):
+        x, y, diag = problem(n, d, seed=100 * n + k)
+        gp = device_problem(x, diag, y)
+        p = orc.default_parameter_vector(d) + 0.2 * np.random.default_rng(k).standard_normal(d + 1)
+        probs.append(gp); ps.append(p)
+        singles.append(gp.evaluate(p, True))
+    ps = np.array(ps)
+    for rep in range(3):
+        lml, grad, info = evaluate_many(probs, ps, want_grad=True)
+        assert np.all(info == 0)
+        for k in range(nb):
+            assert lml[k] == singles[k][0] and np.array_equal(grad[k], singles[k][1])
+    lml2, grad2, info2 = evaluate_many(probs, ps, want_grad=False)
+    assert np.array_equal(lml2, lml) and np.all(grad2 == 0.0) and np.all(info2 == 0)
+    # prediction state is valid on every handle afterwards
+    t = problem(n, d, seed=7)[0][:5]
+    mu = probs[nb - 1].predict(t, False)
+    ref = orc.predict(ps[nb - 1], *[problem(n, d, seed=100 * n + nb - 1)[i] for i in (0, 2, 1)], t, False)
+    assert relmax(mu, ref) <= TOL
+    # value-only requests go through the handles' own graphs
+    lml3, _, info3 = evaluate_many(probs, ps, want_grad=False, value_only=True)
+    assert np.all(info3 == 0) and np.max(np.abs(lml3 - lml) / np.abs(lml)) <= 1e-12
+    for gp in probs:
+        gp.close()
