@@ -160,6 +160,27 @@ class GaussianProcessEmulatorBins(BaseEmulator):
             variances.append(var[0])
         return np.array(means), np.array(variances)
 
+    def predict_grid(self, theta_rows: np.ndarray, independent: np.ndarray, want_var: bool = True):
+        """
+        Every parameter row of `theta_rows` (columns in `parameter_order`) at every requested bin: one
+        batched device call per bin instead of one per (parameter row, bin) -- what the sweeps
+        (mocking.mock_hypercube / mock_sweep) would otherwise issue through predict_values.  Returns
+        mean[n_theta, n_bins] (and variance); same values as predict_values row by row.
+        """
+        order = self._bin_indices(independent)
+        theta = np.ascontiguousarray(np.atleast_2d(theta_rows), dtype=np.float64)
+        mean = np.empty((len(theta), len(order)))
+        var = np.empty((len(theta), len(order))) if want_var else None
+        for col, b in enumerate(order):
+            out = self.bin_gaussian_process[b].predict(
+                y=self.bin_model_values[b]["dependent"], t=theta, return_cov=False, return_var=want_var
+            )
+            if want_var:
+                mean[:, col], var[:, col] = out
+            else:
+                mean[:, col] = out
+        return (mean, var) if want_var else mean
+
     def predict_values_no_error(self, independent: np.array, model_parameters: Dict[str, float]):
         order = self._bin_indices(independent)
         t = self._query(model_parameters)

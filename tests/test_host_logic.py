@@ -436,3 +436,22 @@ def test_cross_check_lockstep_matches_the_scipy_refits(oracle_backend):
     assert abs(ms_a - ms_b) <= 1e-3 * abs(ms_a)
     with pytest.raises(ValueError):
         CrossCheck(fit_mode="nope").build_emulators(spec, params, values)
+
+
+def test_mocking_a_binned_emulator_goes_through_its_grid_prediction(oracle_backend):
+    """Sweeps over a GaussianProcessEmulatorBins: one batched call per bin (predict_grid), same values as
+    the per-point predict_values path."""
+    spec, params, values = synthetic.make_model(2, 12, 5, seed=2)
+    emu = GaussianProcessEmulatorBins(workers=1)
+    emu.fit_model(spec, params, values)
+    mocked, new_params = mocking.mock_hypercube(emu, spec, samples=7, rng=np.random.default_rng(1))
+    assert len(mocked) == 7
+    for uid in ("emulated_0", "emulated_6"):
+        mu, var = emu.predict_values(mocked[uid]["independent"], new_params[uid])
+        assert np.allclose(mocked[uid]["dependent"], mu, rtol=1e-12, atol=1e-13)
+        assert np.allclose(mocked[uid]["dependent_error"], var, rtol=1e-9, atol=1e-12)
+    theta = np.array([[new_params[f"emulated_{k}"][name] for name in emu.parameter_order] for k in range(7)])
+    centers = np.array(emu.bin_centers)
+    assert np.array_equal(emu.predict_grid(theta, centers[:2], want_var=False), emu.predict_grid(theta, centers[:2])[0])
+    with pytest.raises(AttributeError):
+        emu.predict_grid(theta, np.array([0.123456]))
