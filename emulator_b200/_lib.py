@@ -44,6 +44,7 @@ SIGNATURES = {
     "eb200_gp_eval_host": (c_int, [c_void_p, _dp, c_int, _dp]),
     "eb200_gp_eval_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "eb200_gp_eval_multi_host": (c_int, [POINTER(c_void_p), c_int, _dp, c_int, c_int, _dp, c_int]),
+    "eb200_gp_eval_multi_device": (c_int, [POINTER(c_void_p), c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "eb200_gp_eval_value_batch_host": (c_int, [c_void_p, c_int, _dp, _dp]),
     "eb200_gp_predict_host": (c_int, [c_void_p, c_int, _dp, c_int, _dp, _dp]),
     "eb200_gp_predict_grid_host": (c_int, [c_void_p, c_int, _dp, c_int, _dp, c_int, c_int, _dp, _dp]),

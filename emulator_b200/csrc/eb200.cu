@@ -2,7 +2,9 @@
 // See include/emulator_b200.h for the contract and DESIGN.md for the algorithm.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -106,6 +108,13 @@ struct eb200_gp {
     double* h_stage = nullptr;  // pinned: MAX_BATCH parameter vectors + results
     int slots = 0;             // matrices allocated so far
   } batch;
+  // State of grouped multi-handle evaluations led by this handle (allocated on first use): parameter vectors
+  // and results of the group's problems, contiguous so that one copy each way serves the whole group.
+  struct GroupState {
+    double *p_dev = nullptr, *out_dev = nullptr;  // [MAX_BATCH][MAXD + 1], [MAX_BATCH][MAXD + 8]
+    double* h_stage = nullptr;                    // pinned: both of the above
+  } group;
+  size_t state_ints = 0;  // ints behind `ready` zeroed before every factorisation: flags, claim marks, counters, info, abort flag
   FactorTask* ftasks_v = nullptr;  // value-only list: Cholesky tiles + the residual row
   int n_ftasks_v = 0;
   int qbase_v[5] = {0, 0, 0, 0, 0};
@@ -245,9 +254,48 @@ void fill_factor_args(eb200_gp* h, bool vo, FactorArgs& fa) {
   fa.n_chain_sms = 1;
 }
 
+// The pointers of the stages after the factorisation for the handle's own state.
+void fill_post_args(eb200_gp* h, int mode, PostArgs& pa) {
+  pa.W = h->W; pa.r = h->r; pa.z = h->z; pa.tpartial = h->tpartial; pa.alpha = h->alpha; pa.Xtr = h->X; pa.kp = h->kp;
+  pa.trace_partial = h->trace_partial; pa.logdet_part = h->logdet_part;
+  // value-only: z = L^-1 r is the residual row of the factorised matrix
+  pa.zfin = mode == EB200_EVAL_VALUE_ONLY ? h->A + (size_t)h->np * h->np : h->z;
+  pa.info = h->info; pa.abort_flag = h->abort_flag; pa.out = h->out_dev;
+}
+
+// Flags, claim marks, queue counters, info and the watchdog's abort flag of one handle: one memset.
+cudaError_t reset_state(eb200_gp* h, cudaStream_t st) { return cudaMemsetAsync(h->ready, 0, h->state_ints * sizeof(int), st); }
+
+// Launch the kernels of one post-factorisation op for the problems of `pb` (all shaped like h).
+int launch_post(eb200_gp* h, const Op& op, const PostBatch& pb, cudaStream_t st, int mode, double* kinv_out) {
+  const int want_grad = mode == EB200_EVAL_GRAD;
+  const int np = h->np, nb = pb.nb;
+  switch (op.kind) {
+    case OP_TRMV:
+      trmv_lower_kernel<<<dim3(np / 8, nb), 256, 0, st>>>(pb, np, np);
+      return 1;
+    case OP_TRMV_T:
+      trmv_t_partial_kernel<<<dim3(h->nT, h->nT, nb), 128, 0, st>>>(pb, np, np);
+      trmv_t_reduce_kernel<<<dim3(h->nT, nb), 128, 0, st>>>(pb, np);
+      return 2;
+    case OP_LAUUM: {
+      // the diagnostics path (K^-1 stored) needs whole tiles; it has no more tasks than the sliced list
+      const int toff = kinv_out ? h->lauum_full_off : op.task_off;
+      const int tcnt = kinv_out ? h->lauum_full_cnt : op.task_cnt;
+      if (kinv_out) cudaMemsetAsync(h->trace_partial, 0, (size_t)h->n_lauum * (h->dp + 1) * sizeof(double), st);
+      DP_SWITCH(h->dp, (lauum_trace_kernel<DP><<<tcnt * nb, 256, LauumSmem<DP>::BYTES, st>>>(h->tasks + toff, pb, np, h->n, kinv_out)));
+      return 1;
+    }
+    case OP_FINALIZE:
+      finalize_kernel<<<nb, 256, 0, st>>>(pb, h->nt, h->n, h->n_lauum, h->dp, h->d, want_grad);
+      return 1;
+    default:
+      return 0;
+  }
+}
+
 // Enqueue one op.  Returns number of kernel launches issued.
 int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int mode, double* kinv_out) {
-  const int want_grad = mode == EB200_EVAL_GRAD;
   const int np = h->np;
   switch (op.kind) {
     case OP_PREP:
@@ -258,10 +306,7 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int mode, double* kinv
       return 1;
     case OP_FACTOR_DF: {
       const bool vo = mode == EB200_EVAL_VALUE_ONLY;
-      const size_t nf = (size_t)(h->nt + 1) * h->nt;  // flags per array (tile row nt: the residual row)
-      cudaMemsetAsync(h->counter, 0, 8 * sizeof(unsigned), st);
-      // ready, xready, pready, cready, lready, sm_chain, claimed
-      cudaMemsetAsync(h->ready, 0, (4 * nf + 8 * h->nt + 512 + (size_t)h->n_ftasks) * sizeof(int), st);
+      reset_state(h, st);
       FactorBatch fb;
       fb.nb = 1;
       FactorArgs& fa = fb.p[0];
@@ -273,35 +318,17 @@ int launch_op(eb200_gp* h, const Op& op, cudaStream_t st, int mode, double* kinv
       DP_SWITCH(h->dp, (factor_dataflow_kernel<DP, false><<<grid, 256, FactorSmem<DP>::BYTES, st>>>(fb)));
       return 1;
     }
-    case OP_TRMV:
-      trmv_lower_kernel<<<np / 8, 256, 0, st>>>(h->W, np, np, h->r, h->z);
-      return 1;
-    case OP_TRMV_T:
-      trmv_t_partial_kernel<<<dim3(h->nT, h->nT), 128, 0, st>>>(h->W, np, np, h->z, h->tpartial);
-      trmv_t_reduce_kernel<<<h->nT, 128, 0, st>>>(h->tpartial, np, h->alpha);
-      return 2;
-    case OP_LAUUM: {
-      // the diagnostics path (K^-1 stored) needs whole tiles; it has no more tasks than the sliced list
-      const int toff = kinv_out ? h->lauum_full_off : op.task_off;
-      const int tcnt = kinv_out ? h->lauum_full_cnt : op.task_cnt;
-      if (kinv_out) cudaMemsetAsync(h->trace_partial, 0, (size_t)h->n_lauum * (h->dp + 1) * sizeof(double), st);
-      DP_SWITCH(h->dp, (lauum_trace_kernel<DP><<<tcnt, 256, LauumSmem<DP>::BYTES, st>>>(
-                           h->tasks + toff, h->W, np, h->X, h->alpha, h->kp, h->n, h->trace_partial, kinv_out)));
-      return 1;
+    default: {
+      PostBatch pb;
+      pb.nb = 1;
+      fill_post_args(h, mode, pb.p[0]);
+      return launch_post(h, op, pb, st, mode, kinv_out);
     }
-    case OP_FINALIZE:
-      // value-only: z = L^-1 r is the residual row of the factorised matrix
-      finalize_kernel<<<1, 256, 0, st>>>(h->logdet_part, h->nt, mode == EB200_EVAL_VALUE_ONLY ? h->A + (size_t)np * np : h->z, h->n, h->trace_partial, h->n_lauum, h->dp, h->d,
-                                         want_grad, h->info, h->abort_flag, h->out_dev);
-      return 1;
   }
-  return 0;
 }
 
 int enqueue_eval(eb200_gp* h, cudaStream_t st, int mode, int max_stage, double* kinv_out, int* launches) {
   int cnt = 0;
-  CK(cudaMemsetAsync(h->info, 0, sizeof(int), st));
-  CK(cudaMemsetAsync(h->abort_flag, 0, sizeof(int), st));
   for (const Op& op : h->ops) {
     if (op.stage > max_stage) continue;
     if (op.grad_only && mode != EB200_EVAL_GRAD) continue;
@@ -315,26 +342,38 @@ int enqueue_eval(eb200_gp* h, cudaStream_t st, int mode, int max_stage, double* 
 }
 
 int capture_graph(eb200_gp* h, int mode, cudaGraphExec_t* exec, int* launches, bool host_copies = false) {
-  cudaGraph_t graph;
   CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
   if (host_copies) cudaMemcpyAsync(h->p_dev, h->h_p, (h->d + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream);
   int rc = enqueue_eval(h, h->stream, mode, 99, nullptr, launches);
   if (host_copies)
     cudaMemcpyAsync(h->h_out, h->out_dev, EB200_RESULT_LEN(h->d) * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
-  if (rc) return rc;
+  if (rc || e != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    if (rc) return rc;
+    CK(e);
+  }
+  e = cudaGraphInstantiate(exec, graph, 0);
+  cudaGraphDestroy(graph);
   CK(e);
-  CK(cudaGraphInstantiate(exec, graph, 0));
-  CK(cudaGraphDestroy(graph));
   return 0;
 }
 
+int set_attrs_impl();
+// Function attributes are per device and set once per device, whichever host thread gets there first.
 int set_attrs() {
+  static std::mutex mu;
   static bool done_dev[64] = {false};
   int dev = 0;
   CK(cudaGetDevice(&dev));
-  bool& done = done_dev[dev & 63];
-  if (done) return 0;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done_dev[dev & 63]) return 0;
+  if (set_attrs_impl()) return 1;
+  done_dev[dev & 63] = true;
+  return 0;
+}
+int set_attrs_impl() {
   CK((set_gemm_attr<Cfg128, KCONTIG, KCONTIG>()));
   CK(cudaFuncSetAttribute(var_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES));
@@ -352,7 +391,6 @@ int set_attrs() {
   SET_LAUUM(2) SET_LAUUM(3) SET_LAUUM(4) SET_LAUUM(5) SET_LAUUM(6) SET_LAUUM(8) SET_LAUUM(9) SET_LAUUM(10)
   SET_LAUUM(12) SET_LAUUM(16)
 #undef SET_LAUUM
-  done = true;
   return 0;
 }
 
@@ -444,13 +482,29 @@ int eb200_device_mem_info(int device, unsigned long long* free_bytes, unsigned l
   return 0;
 }
 
+static int create_impl(eb200_gp* h, int device, int n, int d, const double* x_host, const double* noise_host);
+
 int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_host, const double* noise_host) {
   if (!out || !x_host || !noise_host) return fail("eb200_gp_create: null argument");
+  *out = nullptr;
   if (n < 1) return fail("eb200_gp_create: n must be >= 1");
   if (d < 1 || d > EB200_MAX_DIM) return fail("eb200_gp_create: kernel dimension must be in [1, 16]");
   CK(cudaSetDevice(device));
   if (set_attrs()) return 1;
   eb200_gp* h = new eb200_gp();
+  if (create_impl(h, device, n, d, x_host, noise_host)) {
+    // (typically cudaMalloc out of memory with many live handles: give back whatever this one had got, and
+    //  clear the sticky last-error so that the next call on this thread does not report it again)
+    const std::string why = g_err;
+    eb200_gp_destroy(h);
+    cudaGetLastError();
+    return fail(why);
+  }
+  *out = h;
+  return 0;
+}
+
+static int create_impl(eb200_gp* h, int device, int n, int d, const double* x_host, const double* noise_host) {
   h->device = device;
   h->n = n;
   h->d = d;
@@ -481,15 +535,12 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
         {(void**)&h->p_dev, (MAXD + 1) * sizeof(double)},
         {(void**)&h->out_dev, (MAXD + 8) * sizeof(double)},
         {(void**)&h->kp, sizeof(KernelParams)},
-        {(void**)&h->info, sizeof(int)},
         {(void**)&h->T_dev, (size_t)np * dp * sizeof(double)},
         {(void**)&h->T_in, (size_t)np * d * sizeof(double)},
         {(void**)&h->mu_dev, np * sizeof(double)},
         {(void**)&h->var_dev, np * sizeof(double)},
         {(void**)&h->rowss, (size_t)h->nT * np * sizeof(double)},
         {(void**)&h->var_tasks, (size_t)h->nT * h->nT * sizeof(TileTask)},
-        {(void**)&h->counter, 8 * sizeof(unsigned)},
-        {(void**)&h->abort_flag, sizeof(int)},
         {(void**)&h->rdiag, (size_t)np * sizeof(double)},
     };
     auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
@@ -587,7 +638,17 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
     CK(cudaMemcpy(h->inv_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
     h->n_ftasks = (int)ft.size();
     h->qbase[4] = h->n_ftasks;
-    CK(cudaMalloc(&h->ready, ((size_t)4 * (h->nt + 1) * h->nt + 8 * h->nt + 512 + ft.size()) * sizeof(int)));  // flags + claim marks
+    {
+      // flags + claim marks, then the queue counters (8), info and the watchdog's abort flag: everything one
+      // evaluation starts from zero sits in one block cleared by one memset (reset_state)
+      const size_t flag_ints = (size_t)4 * (h->nt + 1) * h->nt + 8 * h->nt + 512 + ft.size();
+      h->state_ints = flag_ints + 8 + 2;
+      CK(cudaMalloc(&h->ready, h->state_ints * sizeof(int)));
+      CK(cudaMemset(h->ready, 0, h->state_ints * sizeof(int)));
+      h->counter = reinterpret_cast<unsigned*>(h->ready + flag_ints);
+      h->info = h->ready + flag_ints + 8;
+      h->abort_flag = h->info + 1;
+    }
     CK(cudaMalloc(&h->ftasks, ft.size() * sizeof(FactorTask)));
     CK(cudaMemcpy(h->ftasks, ft.data(), ft.size() * sizeof(FactorTask), cudaMemcpyHostToDevice));
     // Value-only list (likelihood without gradient, e.g. ensemble sampling): the Cholesky tasks of
@@ -639,14 +700,13 @@ int eb200_gp_create(eb200_gp** out, int device, int n, int d, const double* x_ho
   // (the six evaluation graphs -- three modes, with and without the host copies -- are captured on first
   //  use: a handle typically needs one or two of them, and capture + instantiation is most of what
   //  creating a small handle costs)
-  *out = h;
   return 0;
 }
 
 int eb200_gp_destroy(eb200_gp* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->g_grad) cudaGraphExecDestroy(h->g_grad);
   if (h->g_lml) cudaGraphExecDestroy(h->g_lml);
   if (h->g_val) cudaGraphExecDestroy(h->g_val);
@@ -664,9 +724,12 @@ int eb200_gp_destroy(eb200_gp* h) {
       if (q) cudaFree(q);
     if (bs.h_stage) cudaFreeHost(bs.h_stage);
   }
+  if (h->group.p_dev) cudaFree(h->group.p_dev);
+  if (h->group.out_dev) cudaFree(h->group.out_dev);
+  if (h->group.h_stage) cudaFreeHost(h->group.h_stage);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->batch_done) cudaEventDestroy(h->batch_done);
-  cudaStreamDestroy(h->stream);
+  if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
 }
@@ -745,76 +808,137 @@ int eb200_gp_eval_host(eb200_gp* h, const double* p_host, int mode, double* resu
   memcpy(result_host, h->h_out, len * sizeof(double));
   if (mode != EB200_EVAL_GRAD)
     for (int i = 0; i <= h->d; ++i) result_host[1 + i] = 0.0;
-  h->factor_valid = mode != EB200_EVAL_VALUE_ONLY;
+  // prediction state (L^-1, alpha) is only there after a successful factorisation that kept it
+  h->factor_valid = mode != EB200_EVAL_VALUE_ONLY && result_host[h->d + 2] == 0.0;
   return 0;
 }
 
-// One factorisation launch for a group of equally shaped handles (chains interleaved, factor_dataflow.cuh),
-// then every handle's remaining stages on its own stream.  Results land in each handle's h_out.
-static int enqueue_group_batched(eb200_gp** g, int m, int mode) {
+// Tunables of grouped launches (development: read once from the environment).
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+static int ensure_group_state(eb200_gp* h) {
+  eb200_gp::GroupState& gs = h->group;
+  if (gs.p_dev) return 0;
+  const size_t PS_ = MAXD + 1, OS_ = MAXD + 8;
+  CK(cudaMalloc(&gs.p_dev, MAX_BATCH * PS_ * sizeof(double)));
+  CK(cudaMalloc(&gs.out_dev, MAX_BATCH * OS_ * sizeof(double)));
+  CK(cudaMallocHost(&gs.h_stage, MAX_BATCH * (PS_ + OS_) * sizeof(double)));
+  return 0;
+}
+
+// One evaluation on each of m equally shaped handles (m <= MAX_BATCH) as ONE sequence of launches on stream
+// `st`: the factorisations share a launch with their dependency chains interleaved (factor_dataflow.cuh: one
+// Cholesky chain cannot feed 148 SMs until it is a few hundred columns long, m of them can), and every later
+// stage is one launch over the problems of the group.  Problem b reads p_dev + b * p_stride and writes its
+// result vector to out_dev + b * out_stride (device pointers).  Results equal stand-alone evaluations bit for
+// bit: every tile and every reduction is computed by the same code in the same order whoever claims it.
+static int enqueue_group(eb200_gp** g, int m, int mode, const double* p_dev, int p_stride, double* out_dev, int out_stride,
+                         cudaStream_t st) {
   eb200_gp* h0 = g[0];
-  cudaStream_t s0 = h0->stream;
   const int nt = h0->nt;
-  const size_t nf = (size_t)(nt + 1) * nt;
+  const bool vo = mode == EB200_EVAL_VALUE_ONLY;
   FactorBatch fb;
   fb.nb = m;
-  const int grid = std::min(2 * h0->n_sms, m * h0->qbase[4]);
+  PostBatch pb;
+  pb.nb = m;
+  PrepBatch prep;
+  const int ntasks = vo ? h0->n_ftasks_v : h0->n_ftasks;
+  const int grid = (int)std::min<long long>(2ll * h0->n_sms, (long long)m * ntasks);
+  // chain CTAs per problem: a CTA of the chain queue claims in order and waits inside its task, so it is a
+  // CTA slot that mostly idles -- as few as keep the chain fed
+  // (measured at N = 4096, ms per evaluation, groups of 4: 1 chain CTA per problem 2.91, 2: 2.80, 3: 2.82, 6: 2.86;
+  //  stand-alone evaluations 2.98)
+  static const int chain_env = env_int("EB200_GROUP_CHAIN", 0);
+  int n_chain = std::max(1, std::min({6, nt / 4, (grid / m) / 4}));
+  if (nt > 32) n_chain = std::min(n_chain, 2);
+  if (chain_env > 0) n_chain = chain_env;
   for (int b = 0; b < m; ++b) {
     eb200_gp* h = g[b];
-    CK(cudaMemcpyAsync(h->p_dev, h->h_p, (h->d + 1) * sizeof(double), cudaMemcpyHostToDevice, s0));
-    CK(cudaMemsetAsync(h->info, 0, sizeof(int), s0));
-    CK(cudaMemsetAsync(h->abort_flag, 0, sizeof(int), s0));
-    CK(cudaMemsetAsync(h->counter, 0, 8 * sizeof(unsigned), s0));
-    CK(cudaMemsetAsync(h->ready, 0, (4 * nf + 8 * nt + 512 + (size_t)h->n_ftasks) * sizeof(int), s0));
-    prep_params_kernel<<<1, 32, 0, s0>>>(h->p_dev, h->d, h->kp);
+    CK(reset_state(h, st));
+    prep.kp[b] = h->kp;
     FactorArgs& fa = fb.p[b];
-    fill_factor_args(h, false, fa);
+    fill_factor_args(h, vo, fa);
     fa.sm_chain = fb.p[0].sm_chain;  // one priority flag per SM for the whole launch
     fa.trace = nullptr;
-    fa.n_chain_sms = std::max(1, std::min({6, nt / 4, (grid / m) / 4}));
+    fa.n_chain_sms = n_chain;
+    fill_post_args(h, mode, pb.p[b]);
+    pb.p[b].out = out_dev + (size_t)b * out_stride;
   }
-  DP_SWITCH(h0->dp, (factor_dataflow_kernel<DP, true><<<grid, 256, FactorSmem<DP>::BYTES, s0>>>(fb)));
-  CK(cudaEventRecord(h0->batch_done, s0));
-  for (int b = 0; b < m; ++b) {
-    eb200_gp* h = g[b];
-    if (b > 0) CK(cudaStreamWaitEvent(h->stream, h0->batch_done, 0));
-    for (const Op& op : h->ops) {
-      if (op.stage < 3 || op.debug_only) continue;
-      if (op.grad_only && mode != EB200_EVAL_GRAD) continue;
-      launch_op(h, op, h->stream, mode, nullptr);
-    }
-    CK(cudaMemcpyAsync(h->h_out, h->out_dev, EB200_RESULT_LEN(h->d) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  prep_params_group_kernel<<<m, 32, 0, st>>>(p_dev, p_stride, h0->d, prep);
+  DP_SWITCH(h0->dp, (factor_dataflow_kernel<DP, true><<<grid, 256, FactorSmem<DP>::BYTES, st>>>(fb)));
+  for (const Op& op : h0->ops) {
+    if (op.stage < 3 || op.debug_only) continue;
+    if (op.grad_only && mode != EB200_EVAL_GRAD) continue;
+    if (vo && op.stage == 3) continue;
+    launch_post(h0, op, pb, st, mode, nullptr);
   }
   CK(cudaGetLastError());
   return 0;
 }
 
-// One evaluation on each of nb handles in ONE native call.  Chain-bound problems (14 to 32 tile rows) of
-// equal shape share factorisation launches, MAX_BATCH at a time; everything else is enqueued on the
-// handles' own streams.  Either way the evaluations overlap on the device and are collected afterwards.
+static bool same_shape(const eb200_gp* a, const eb200_gp* b) {
+  return a->np == b->np && a->dp == b->dp && a->d == b->d && a->n == b->n && a->device == b->device;
+}
+
+// Whether handles shaped like h share factorisation launches when several are evaluated together.
+// (measured, 64 handles, us per evaluation, own graphs vs shared launches: N=256 12 vs 38, N=640 65 vs 77,
+//  N=768 107 vs 99, N=1000 ~430 vs 117: below ~14 tile rows the handles' own graphs overlap well enough)
+// (the same at larger sizes, stand-alone vs groups: N=2048 0.91 vs 0.46 ms (groups of 8), N=4096 2.98 vs 2.80 (groups of 4;
+//  2.93 in groups of 8), N=8176 20.0 vs 20.5: a factorisation of 128 tile rows keeps the device busy by itself)
+static bool groups_pay(const eb200_gp* h, int mode) {
+  static const int lo = env_int("EB200_GROUP_MIN_NT", 14), hi = env_int("EB200_GROUP_MAX_NT", 96);
+  return mode != EB200_EVAL_VALUE_ONLY && h->nt >= lo && h->nt <= hi;
+}
+static int group_size(const eb200_gp* h) {
+  static const int env = env_int("EB200_GROUP_SIZE", 0);
+  const int m = env > 0 ? env : (h->nt <= 32 ? MAX_BATCH : 4);
+  return std::max(1, std::min((int)MAX_BATCH, m));
+}
+
+static int check_distinct(eb200_gp** gps, int nb, const char* who) {
+  std::vector<eb200_gp*> v(gps, gps + nb);
+  std::sort(v.begin(), v.end());
+  for (int b = 0; b < nb; ++b) {
+    if (!v[b]) return fail(std::string(who) + ": null handle");
+    if (b > 0 && v[b] == v[b - 1]) return fail(std::string(who) + ": the same handle appears twice (its matrices would be factorised twice at once)");
+  }
+  return 0;
+}
+
+// One evaluation on each of nb handles in ONE native call.  Equally shaped problems of at least 14 tile rows
+// share launches, MAX_BATCH at a time (enqueue_group); everything else is enqueued on the handles' own streams.
+// Either way the evaluations overlap on the device and are collected afterwards.
 int eb200_gp_eval_multi_host(eb200_gp** gps, int nb, const double* p_host, int p_stride, int mode, double* result_host,
                              int result_stride) {
   if (!gps || !p_host || !result_host || nb < 0) return fail("eval_multi: bad argument");
   if (mode < 0 || mode > 2) return fail("eval: mode must be EB200_EVAL_LML, EB200_EVAL_GRAD or EB200_EVAL_VALUE_ONLY");
-  for (int b = 0; b < nb; ++b) {
-    eb200_gp* h = gps[b];
-    if (!h) return fail("eval_multi: null handle");
-    if (p_stride < h->d + 1 || result_stride < EB200_RESULT_LEN(h->d)) return fail("eval_multi: stride too small");
-    memcpy(h->h_p, p_host + (size_t)b * p_stride, (h->d + 1) * sizeof(double));
-  }
+  if (check_distinct(gps, nb, "eval_multi")) return 1;
+  for (int b = 0; b < nb; ++b)
+    if (p_stride < gps[b]->d + 1 || result_stride < EB200_RESULT_LEN(gps[b]->d)) return fail("eval_multi: stride too small");
+  const int PS_ = MAXD + 1, OS_ = MAXD + 8;
+  std::vector<int> lead(nb, -1);  // for grouped problems: index of the group's first handle
   for (int b = 0; b < nb;) {
     eb200_gp* h = gps[b];
     CK(cudaSetDevice(h->device));
     int m = 1;
-    // (measured, 64 handles, us per evaluation, own graphs vs shared launches: N=256 12 vs 38, N=640 65 vs 77,
-    //  N=768 107 vs 99, N=1000 ~430 vs 117: below ~14 tile rows the handles' own graphs overlap well enough)
-    if (mode != EB200_EVAL_VALUE_ONLY && h->nt <= 32 && h->nt >= 14)
-      while (b + m < nb && m < MAX_BATCH && gps[b + m]->np == h->np && gps[b + m]->dp == h->dp && gps[b + m]->d == h->d &&
-             gps[b + m]->device == h->device && gps[b + m] != h)
-        ++m;
+    if (groups_pay(h, mode))
+      while (b + m < nb && m < group_size(h) && same_shape(gps[b + m], h)) ++m;
     if (m >= 2) {
-      if (enqueue_group_batched(gps + b, m, mode)) return 1;
+      if (ensure_group_state(h)) return 1;
+      double* stage_p = h->group.h_stage;
+      for (int k = 0; k < m; ++k) {
+        memcpy(stage_p + (size_t)k * PS_, p_host + (size_t)(b + k) * p_stride, (h->d + 1) * sizeof(double));
+        lead[b + k] = b;
+      }
+      CK(cudaMemcpyAsync(h->group.p_dev, stage_p, (size_t)m * PS_ * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      if (enqueue_group(gps + b, m, mode, h->group.p_dev, PS_, h->group.out_dev, OS_, h->stream)) return 1;
+      CK(cudaMemcpyAsync(stage_p + (size_t)MAX_BATCH * PS_, h->group.out_dev, (size_t)m * OS_ * sizeof(double), cudaMemcpyDeviceToHost,
+                         h->stream));
     } else {
+      memcpy(h->h_p, p_host + (size_t)b * p_stride, (h->d + 1) * sizeof(double));
       cudaGraphExec_t g = eval_graph_host(h, mode);
       if (!g) return 1;
       CK(cudaGraphLaunch(g, h->stream));
@@ -823,13 +947,53 @@ int eb200_gp_eval_multi_host(eb200_gp** gps, int nb, const double* p_host, int p
   }
   for (int b = 0; b < nb; ++b) {
     eb200_gp* h = gps[b];
-    CK(cudaSetDevice(h->device));
-    CK(cudaStreamSynchronize(h->stream));
+    const int len = EB200_RESULT_LEN(h->d);
     double* dst = result_host + (size_t)b * result_stride;
-    memcpy(dst, h->h_out, EB200_RESULT_LEN(h->d) * sizeof(double));
+    CK(cudaSetDevice(h->device));
+    if (lead[b] >= 0) {
+      eb200_gp* h0 = gps[lead[b]];
+      if (lead[b] == b) CK(cudaStreamSynchronize(h0->stream));
+      memcpy(dst, h0->group.h_stage + (size_t)MAX_BATCH * PS_ + (size_t)(b - lead[b]) * OS_, len * sizeof(double));
+    } else {
+      CK(cudaStreamSynchronize(h->stream));
+      memcpy(dst, h->h_out, len * sizeof(double));
+    }
     if (mode != EB200_EVAL_GRAD)
       for (int i = 0; i <= h->d; ++i) dst[1 + i] = 0.0;
-    h->factor_valid = mode != EB200_EVAL_VALUE_ONLY;
+    // prediction state (L^-1, alpha) is only there after a successful factorisation that kept it
+    h->factor_valid = mode != EB200_EVAL_VALUE_ONLY && dst[h->d + 2] == 0.0;
+  }
+  return 0;
+}
+
+// The same with device pointers: parameter vectors p_dev[nb][p_stride] and result vectors
+// result_dev[nb][result_stride] live in HBM, everything is enqueued on `stream` (NULL: the first handle's own)
+// and nothing synchronises.  All handles must be on the current device of `stream`.
+int eb200_gp_eval_multi_device(eb200_gp** gps, int nb, const double* p_dev, int p_stride, int mode, double* result_dev,
+                               int result_stride, void* stream) {
+  if (!gps || !p_dev || !result_dev || nb < 0) return fail("eval_multi_device: bad argument");
+  if (mode < 0 || mode > 2) return fail("eval: mode must be EB200_EVAL_LML, EB200_EVAL_GRAD or EB200_EVAL_VALUE_ONLY");
+  if (nb == 0) return 0;
+  if (check_distinct(gps, nb, "eval_multi_device")) return 1;
+  for (int b = 0; b < nb; ++b) {
+    if (p_stride < gps[b]->d + 1 || result_stride < EB200_RESULT_LEN(gps[b]->d)) return fail("eval_multi_device: stride too small");
+    if (gps[b]->device != gps[0]->device) return fail("eval_multi_device: handles on different devices");
+  }
+  CK(cudaSetDevice(gps[0]->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : gps[0]->stream;
+  for (int b = 0; b < nb;) {
+    eb200_gp* h = gps[b];
+    int m = 1;
+    if (groups_pay(h, mode))
+      while (b + m < nb && m < group_size(h) && same_shape(gps[b + m], h)) ++m;
+    if (m >= 2) {
+      if (enqueue_group(gps + b, m, mode, p_dev + (size_t)b * p_stride, p_stride, result_dev + (size_t)b * result_stride, result_stride, st))
+        return 1;
+      for (int k = 0; k < m; ++k) gps[b + k]->factor_valid = mode != EB200_EVAL_VALUE_ONLY;
+    } else {
+      if (eb200_gp_eval_device(h, p_dev + (size_t)b * p_stride, mode, result_dev + (size_t)b * result_stride, st)) return 1;
+    }
+    b += m;
   }
   return 0;
 }
@@ -1052,7 +1216,6 @@ int eb200_gp_profile_stages(eb200_gp* h, const double* p_host, int reps, float* 
   for (auto& e : ev) CK(cudaEventCreate(&e));
   for (int s = 0; s < 5; ++s) ms_out[s] = 0.f;
   for (int rep = 0; rep <= reps; ++rep) {  // rep 0 is a warm-up
-    CK(cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
     CK(cudaEventRecord(ev[0], h->stream));
     for (int stage = 1; stage <= 5; ++stage) {
       for (const Op& op : h->ops)

@@ -98,7 +98,6 @@ struct FactorArgs {
 // the chains of up to MAX_BATCH problems are interleaved (the ensemble sampler proposes half its walkers
 // at once; lock-step optimisers evaluate many equally shaped GPs per round).  CTA c is at home in
 // problem c % nb and helps the others.
-constexpr int MAX_BATCH = 8;
 struct FactorBatch {
   int nb;
   FactorArgs p[MAX_BATCH];

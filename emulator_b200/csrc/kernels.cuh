@@ -22,6 +22,10 @@ struct KernelParams {
   double inv_m[MAXD];   // 1 / exp(p_{i+1}); zero for padded dimensions
 };
 
+// Several independent problems of one shape can share launches (factor_dataflow.cuh; the stages after
+// the factorisation below): block index -> problem through a pointer table passed by value.
+constexpr int MAX_BATCH = 8;
+
 // One block per problem of a batch: problem b reads p + b * p_stride and writes out[b].
 __global__ void prep_params_kernel(const double* __restrict__ p, int d, KernelParams* __restrict__ out, int p_stride = 0) {
   if (threadIdx.x == 0) {
@@ -31,6 +35,40 @@ __global__ void prep_params_kernel(const double* __restrict__ p, int d, KernelPa
     for (int i = 0; i < MAXD; ++i) out->inv_m[i] = (i < d) ? 1.0 / exp(p[i + 1]) : 0.0;
   }
 }
+
+// The same for problems whose parameter blocks live in different handles.
+struct PrepBatch {
+  KernelParams* kp[MAX_BATCH];
+};
+__global__ void prep_params_group_kernel(const double* __restrict__ p, int p_stride, int d, const PrepBatch out) {
+  if (threadIdx.x == 0) {
+    p += (size_t)blockIdx.x * p_stride;
+    KernelParams* o = out.kp[blockIdx.x];
+    o->amp = (double)d * exp(p[0]);
+    for (int i = 0; i < MAXD; ++i) o->inv_m[i] = (i < d) ? 1.0 / exp(p[i + 1]) : 0.0;
+  }
+}
+
+// Per-problem pointers of the stages that follow the factorisation (alpha, K^-1 traces, final sum).
+struct PostArgs {
+  const double* W;        // X = L^-1
+  const double* r;        // residual
+  double* z;              // z = X r
+  double* tpartial;       // [nT][np] partial sums of alpha = X^T z
+  double* alpha;
+  const double* Xtr;      // [np][DP] padded training inputs
+  const KernelParams* kp;
+  double* trace_partial;  // [n_lauum][DP+1]
+  const double* logdet_part;
+  const double* zfin;     // the z the final sum reads (value-only: the residual row of the factorised matrix)
+  const int* info;
+  const int* abort_flag;
+  double* out;            // [d + 5] result vector
+};
+struct PostBatch {
+  int nb;
+  PostArgs p[MAX_BATCH];
+};
 
 // ---------------------------------------------------------------------------------------
 // K1: kernel-matrix build.  One CTA per 64x64 tile of the lower triangle (tile list from the
@@ -154,8 +192,11 @@ __global__ void __launch_bounds__(Cfg::THREADS) tile_gemm_kernel(const TileTask*
 // ---------------------------------------------------------------------------------------
 // z = X r  (X lower triangular, row-major): one warp per row, coalesced.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restrict__ X, int ld, int np,
-                                                          const double* __restrict__ r, double* __restrict__ z) {
+__global__ void __launch_bounds__(256) trmv_lower_kernel(const PostBatch pb, int ld, int np) {
+  const PostArgs& a = pb.p[blockIdx.y];
+  const double* __restrict__ X = a.W;
+  const double* __restrict__ r = a.r;
+  double* __restrict__ z = a.z;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= np) return;
@@ -168,9 +209,11 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restric
 }
 
 // alpha = X^T z, stage 1: partial[rc][j] = sum_{i in row chunk rc, i >= j} X[i][j] z[i].
-__global__ void __launch_bounds__(128) trmv_t_partial_kernel(const double* __restrict__ X, int ld, int np,
-                                                              const double* __restrict__ z,
-                                                              double* __restrict__ partial) {
+__global__ void __launch_bounds__(128) trmv_t_partial_kernel(const PostBatch pb, int ld, int np) {
+  const PostArgs& a = pb.p[blockIdx.z];
+  const double* __restrict__ X = a.W;
+  const double* __restrict__ z = a.z;
+  double* __restrict__ partial = a.tpartial;
   const int cb = blockIdx.x, rc = blockIdx.y;  // 128-column block, 128-row chunk
   const int j = cb * 128 + threadIdx.x;
   double s = 0.0;
@@ -190,8 +233,10 @@ __global__ void __launch_bounds__(128) trmv_t_partial_kernel(const double* __res
   partial[(size_t)rc * np + j] = s;
 }
 // stage 2: alpha[j] = sum over row chunks in fixed order.
-__global__ void __launch_bounds__(128) trmv_t_reduce_kernel(const double* __restrict__ partial, int np,
-                                                             double* __restrict__ alpha) {
+__global__ void __launch_bounds__(128) trmv_t_reduce_kernel(const PostBatch pb, int np) {
+  const PostArgs& a = pb.p[blockIdx.y];
+  const double* __restrict__ partial = a.tpartial;
+  double* __restrict__ alpha = a.alpha;
   const int j = blockIdx.x * 128 + threadIdx.x;
   if (j >= np) return;
   double s = 0.0;
@@ -226,17 +271,23 @@ struct LauumSmem {
 };
 
 template <int DP>
-__global__ void __launch_bounds__(256) lauum_trace_kernel(const TileTask* __restrict__ tasks, const double* X, int ld,
-                                                           const double* __restrict__ Xtr,
-                                                           const double* __restrict__ alpha,
-                                                           const KernelParams* __restrict__ kp, int n,
-                                                           double* __restrict__ partial, double* kinv_out) {
+__global__ void __launch_bounds__(256) lauum_trace_kernel(const TileTask* __restrict__ tasks, const PostBatch pb, int ld,
+                                                           int n, double* kinv_out) {
   extern __shared__ __align__(16) double gsm[];
   using Cfg = Cfg128;
   using E = Engine<Cfg, MCONTIG, MCONTIG, false>;  // plain k order: see OperandSmem
   using SM = LauumSmem<DP>;
   constexpr int XS = SM::XS;
-  const TileTask tk = tasks[blockIdx.x];
+  // block b works on task b / nb of problem b % nb: the task list is sorted longest first, so the blocks of
+  // a batch still start in that order (and the many short tiles of all problems fill the tail together)
+  const unsigned task_id = blockIdx.x / (unsigned)pb.nb;
+  const PostArgs& a = pb.p[blockIdx.x % (unsigned)pb.nb];
+  const double* X = a.W;
+  const double* __restrict__ Xtr = a.Xtr;
+  const double* __restrict__ alpha = a.alpha;
+  const KernelParams* __restrict__ kp = a.kp;
+  double* __restrict__ partial = a.trace_partial;
+  const TileTask tk = tasks[task_id];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM;
   const int wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
@@ -345,7 +396,7 @@ __global__ void __launch_bounds__(256) lauum_trace_kernel(const TileTask* __rest
   if (threadIdx.x <= DP) {
     double v = 0.0;
     for (int w = 0; w < 8; ++w) v += sRed[w * (DP + 1) + threadIdx.x];
-    partial[(size_t)blockIdx.x * (DP + 1) + threadIdx.x] = v;
+    partial[(size_t)task_id * (DP + 1) + threadIdx.x] = v;
   }
 }
 
@@ -353,12 +404,15 @@ __global__ void __launch_bounds__(256) lauum_trace_kernel(const TileTask* __rest
 // Final scalar assembly (one CTA):  out = [lml, grad_0..grad_{P-1}, info, logdet, quad].
 //   lml = -1/2 (N log 2pi + 2 sum log L_jj) - 1/2 z^T z      (george GP.log_likelihood)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ logdet_part, int nt,
-                                                        const double* __restrict__ z, int n,
-                                                        const double* __restrict__ partial, int ntask, int dp,
-                                                        int d, int want_grad, const int* __restrict__ info,
-                                                        const int* __restrict__ abort_flag,
-                                                        double* __restrict__ out) {
+__global__ void __launch_bounds__(256) finalize_kernel(const PostBatch pb, int nt, int n, int ntask, int dp, int d,
+                                                        int want_grad) {
+  const PostArgs& a = pb.p[blockIdx.x];
+  const double* __restrict__ logdet_part = a.logdet_part;
+  const double* __restrict__ z = a.zfin;
+  const double* __restrict__ partial = a.trace_partial;
+  const int* __restrict__ info = a.info;
+  const int* __restrict__ abort_flag = a.abort_flag;
+  double* __restrict__ out = a.out;
   __shared__ double red[256];
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) s = fma(z[i], z[i], s);

@@ -94,7 +94,7 @@ class DeviceProblem:
     def evaluate_value_batch(self, ps: np.ndarray):
         """Value-only evaluations at the rows of ps[nb, P]; returns (lml[nb], info[nb], logdet[nb], quad[nb]).
 
-        The factorisations share launches (up to four at a time): a value-only evaluation is bound by
+        The factorisations share launches (up to eight at a time): a value-only evaluation is bound by
         its dependency chain, not by throughput.  Leaves no prediction state."""
         ps = np.ascontiguousarray(ps, dtype=np.float64)
         if ps.ndim != 2 or ps.shape[1] != self.d + 1:
@@ -205,6 +205,8 @@ def evaluate_many(problems, ps, want_grad: bool = True, value_only: bool = False
     d = problems[0].d
     if ps.shape != (nb, d + 1) or any(q.d != d for q in problems):
         raise ValueError(f"need one parameter vector of {d + 1} entries per problem, all of kernel dimension {d}")
+    if len({id(q) for q in problems}) != nb:
+        raise ValueError("a problem appears twice: its matrices would be factorised twice at once")
     lib = problems[0]._lib
     length = _lib.result_len(d)
     out = np.zeros((nb, length))
@@ -215,3 +217,21 @@ def evaluate_many(problems, ps, want_grad: bool = True, value_only: bool = False
         "eb200_gp_eval_multi_host",
     )
     return out[:, 0].copy(), out[:, 1 : d + 2].copy(), out[:, d + 2].astype(np.int64)
+
+
+def evaluate_many_device(problems, p_ptr: int, p_stride: int, want_grad: bool, result_ptr: int, result_stride: int,
+                         stream: int = 0, value_only: bool = False):
+    """Device-pointer sibling of `evaluate_many`: parameter vectors [nb][p_stride] and result vectors
+    [nb][result_stride] live in HBM; everything is enqueued on `stream`, nothing synchronises."""
+    nb = len(problems)
+    if nb == 0:
+        return
+    if len({id(q) for q in problems}) != nb:
+        raise ValueError("a problem appears twice: its matrices would be factorised twice at once")
+    lib = problems[0]._lib
+    handles = (c_void_p * nb)(*[q._h for q in problems])
+    _lib.check(
+        lib.eb200_gp_eval_multi_device(handles, nb, c_void_p(p_ptr), p_stride, _mode(want_grad, value_only),
+                                       c_void_p(result_ptr), result_stride, c_void_p(stream)),
+        "eb200_gp_eval_multi_device",
+    )

@@ -41,6 +41,15 @@ def local_device() -> int:
     return int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def resolve_device(device=None) -> int:
+    """The CUDA device an emulator / GP uses when the caller names none: this rank's own GPU (LOCAL_RANK)
+    when a process group is initialised -- so that code written against the reference's API, which has no
+    device argument, spreads over the GPUs under torchrun -- and GPU 0 otherwise."""
+    if device is not None:
+        return int(device)
+    return local_device() if _pg() is not None else 0
+
+
 def indices_of(rank_: int, world: int, count: int) -> List[int]:
     """Round-robin assignment: unit i -> rank i mod world."""
     return list(range(rank_, count, world))

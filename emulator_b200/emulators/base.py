@@ -24,7 +24,7 @@ def default_kernel(ndim: int):
     return 1**2 * george.kernels.ExpSquaredKernel(np.ones(ndim), ndim=ndim)
 
 
-def build_gp(kernel, mean_model, x, y, yerr, device: int = 0):
+def build_gp(kernel, mean_model, x, y, yerr, device: Optional[int] = None):
     """Create the GP the way the reference does: deep copy of the kernel, frozen mean."""
     if mean_model is not None:
         mean_model.train(independent=x, dependent=y)

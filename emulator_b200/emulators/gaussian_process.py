@@ -18,7 +18,7 @@ from .base import BaseEmulator, build_gp, default_kernel, flatten_model_values, 
 class GaussianProcessEmulator(BaseEmulator):
     kernel = attr.ib(default=None)
     mean_model = attr.ib(default=None)
-    device: int = attr.ib(default=0)
+    device: Optional[int] = attr.ib(default=None)  # None: this rank's GPU under torchrun, else GPU 0 (dist.resolve_device)
 
     def _build_arrays(self, model_specification, model_parameters, model_values):
         self.model_specification = model_specification

@@ -22,7 +22,7 @@ from .base import BaseEmulator, build_gp, default_kernel, optimise_gp, optimise_
 class GaussianProcessEmulatorBins(BaseEmulator):
     kernel = attr.ib(default=None)
     mean_model = attr.ib(default=None)
-    device: int = attr.ib(default=0)
+    device: Optional[int] = attr.ib(default=None)  # None: this rank's GPU under torchrun, else GPU 0 (dist.resolve_device)
     #: independent per-bin fits run concurrently from this many host threads; every GP owns its
     #: device handle and stream, and the C ABI calls release the GIL (results do not depend on it)
     workers: int = attr.ib(default=8)

@@ -33,7 +33,7 @@ class GaussianProcessEmulatorMCMC(BaseEmulator):
     use_hyperparameter_error: bool = attr.ib(default=False)
     samples_for_error: int = attr.ib(default=100)
     seed: Optional[int] = attr.ib(default=None)
-    device: int = attr.ib(default=0)
+    device: Optional[int] = attr.ib(default=None)  # None: this rank's GPU under torchrun, else GPU 0 (dist.resolve_device)
 
     hyperparameter_samples: Optional[np.ndarray] = None
     hyperparameter_best_fit: Optional[np.ndarray] = None

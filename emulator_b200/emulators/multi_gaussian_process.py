@@ -35,7 +35,7 @@ class MultipleGaussianProcessEmulator(BaseEmulator):
     kernel = attr.ib(default=None)
     mean_model = attr.ib(default=None)
     independent_regions: List[List[Optional[float]]] = attr.ib(default=None)
-    device: int = attr.ib(default=0)
+    device: Optional[int] = attr.ib(default=None)  # None: this rank's GPU under torchrun, else GPU 0 (dist.resolve_device)
 
     model_values_regions: Optional[List[ModelValues]] = None
     emulators: Optional[List[GaussianProcessEmulator]] = None

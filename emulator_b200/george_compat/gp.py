@@ -24,10 +24,12 @@ import contextlib
 import ctypes
 import threading
 import weakref
+from typing import Optional
 
 import numpy as np
 
 from .. import _lib
+from .. import dist as _dist
 from ..device import DeviceProblem, evaluate_many
 from . import kernels as _kernels
 from .modeling import CallableModel, ConstantModel, Model
@@ -87,6 +89,13 @@ class _Residency:
                 other._release_locked()
                 if self.free_bytes(device) >= need + self.RESERVE:
                     return
+            # nothing (more) to release: let a request that cannot possibly fit fail here, clearly, instead of
+            # inside cudaMalloc (RESERVE is head-room, not part of the need)
+            if self.free_bytes(device) < need:
+                raise MemoryError(
+                    f"GPU {device}: {need >> 20} MiB needed for a GP handle, {self.free_bytes(device) >> 20} MiB free and "
+                    "every other handle is in use"
+                )
 
 
 _residency = _Residency()
@@ -102,7 +111,7 @@ class GP:
         white_noise=None,
         fit_white_noise=None,
         solver=None,
-        device: int = 0,
+        device: Optional[int] = None,
         **kwargs,
     ):
         if kernel is None:
@@ -125,7 +134,7 @@ class GP:
             self.mean = CallableModel(mean)
         else:
             self.mean = ConstantModel(float(mean))
-        self.device = device
+        self.device = _dist.resolve_device(device)
         #: evaluate the gradient together with every likelihood value (what BFGS wants);
         #: the ensemble sampler switches this off: its evaluations then go through the Cholesky
         #: factor alone (EB200_EVAL_VALUE_ONLY, a third of the flops).
@@ -259,6 +268,10 @@ class GP:
     def _evaluate(self, want_grad: bool, value_only: bool = False, need_state: bool = False):
         p = np.ascontiguousarray(self.get_parameter_vector(), dtype=np.float64)
         key = p.tobytes()
+        if self._cache_key == key and self._cache[2] != 0:
+            # a failed factorisation fails again, every time it is asked for (as george does); nothing on the
+            # device is valid at these parameters
+            raise np.linalg.LinAlgError(self._failure_text(self._cache[2]))
         cached = self._cache_key == key and (self._cache[1] is not None or not want_grad)
         if cached and not (need_state and self._device_p != key):
             return self._cache
@@ -266,14 +279,26 @@ class GP:
             self._sync_residual()
             lml, grad, info, _logdet, _quad = self._problem.evaluate(p, want_grad, value_only=value_only)
         self.n_device_evaluations += 1
+        if info < 0:
+            # the device watchdog fired (a dependency was not published within its budget): not a property of
+            # the matrix -- never reported as "not positive definite", never cached
+            self._cache_key = self._cache = self._device_p = None
+            raise RuntimeError("device watchdog: the factorisation kernel gave up waiting for a tile (device oversubscribed?)")
+        if info != 0:
+            self._cache_key = key
+            self._cache = (-np.inf, None, info)
+            self._device_p = None  # L^-1 / alpha of an aborted factorisation must never be predicted from
+            raise np.linalg.LinAlgError(self._failure_text(info))
         # a value-only evaluation (Cholesky factor alone) leaves no prediction state behind
         self._device_p = None if value_only else key
         if not (cached and not want_grad):  # keep a cached gradient when only the device state was refreshed
             self._cache_key = key
             self._cache = (lml, grad if want_grad else None, info)
-        if info != 0:
-            raise np.linalg.LinAlgError(f"{info}-th leading minor of the array is not positive definite")
         return self._cache
+
+    @staticmethod
+    def _failure_text(info):
+        return f"{info}-th leading minor of the array is not positive definite"
 
     # ---- likelihood ------------------------------------------------------------------------------
     def log_likelihood(self, y, quiet=False):

@@ -34,7 +34,7 @@ class CrossCheck(object):
     kernel = attr.ib(default=None)
     mean_model = attr.ib(default=None)
     hide_progress: bool = attr.ib(default=True)
-    device: int = attr.ib(default=0)
+    device: Optional[int] = attr.ib(default=None)  # None: this rank's GPU under torchrun, else GPU 0 (dist.resolve_device)
     #: leave-one-out refits of this rank run concurrently from this many host threads (each refit
     #: owns its device handle and stream; the Cholesky's dependency chain of one refit leaves SMs
     #: idle that another refit's kernels use)
@@ -171,7 +171,7 @@ class CrossCheckBins(object):
     kernel = attr.ib(default=None)
     mean_model = attr.ib(default=None)
     hide_progress: bool = attr.ib(default=True)
-    device: int = attr.ib(default=0)
+    device: Optional[int] = attr.ib(default=None)  # None: this rank's GPU under torchrun, else GPU 0 (dist.resolve_device)
 
     model_specification: ModelSpecification = None
     model_parameters: ModelParameters = None

@@ -68,16 +68,25 @@ int eb200_gp_set_residual_device(eb200_gp* gp, const double* r_dev, void* stream
 int eb200_gp_eval_host(eb200_gp* gp, const double* p_host, int mode, double* result_host);
 int eb200_gp_eval_device(eb200_gp* gp, const double* p_dev, int mode, double* result_dev, void* stream);
 
-/* One evaluation (any mode) on each of nb handles -- e.g. the per-bin GPs of GaussianProcessEmulatorBins
- * (gaussian_process_bins.py:206-262), which the reference fits one after the other -- enqueued on the
- * handles' own streams and collected afterwards, so that small problems overlap on the device.
- * Problem b reads p_host + b * p_stride and writes result_host + b * result_stride. */
+/* One evaluation (any mode) on each of nb DISTINCT handles -- the per-bin GPs of GaussianProcessEmulatorBins
+ * (gaussian_process_bins.py:206-262), the leave-one-out refits of CrossCheck (sensitivity/cross_check.py:98-114),
+ * optimiser restarts: problems the reference works through one after the other.  Equally shaped problems of
+ * 14 or more 64-row tile rows share launches, up to 8 at a time: their Cholesky dependency chains are
+ * interleaved in one factorisation launch (one chain cannot feed 148 SMs, several can) and every later stage is
+ * one launch over the group; smaller problems are enqueued on the handles' own streams.  Results are
+ * bit-identical to eb200_gp_eval_host on each handle.  Problem b reads p_host + b * p_stride and writes
+ * result_host + b * result_stride.  A handle listed twice is an error. */
 int eb200_gp_eval_multi_host(eb200_gp** gps, int nb, const double* p_host, int p_stride, int mode, double* result_host,
                              int result_stride);
+/* The same with the parameter vectors and the result vectors in device memory; everything is enqueued on
+ * `stream` (NULL = the first handle's own stream) and nothing synchronises.  All handles on one device.
+ * As with eb200_gp_eval_device the caller reads `info` from the result vector before predicting. */
+int eb200_gp_eval_multi_device(eb200_gp** gps, int nb, const double* p_dev, int p_stride, int mode, double* result_dev,
+                               int result_stride, void* stream);
 
 /* nb value-only evaluations (EB200_EVAL_VALUE_ONLY semantics) at the parameter vectors p_host[nb][d+1];
  * result_host[nb][EB200_RESULT_LEN(d)].  A value-only factorisation is bound by its dependency chain
- * and leaves most SMs idle, so up to four share one launch.  This is the half-ensemble of proposals
+ * and leaves most SMs idle, so up to eight share one launch.  This is the half-ensemble of proposals
  * the ensemble sampler evaluates per move (gaussian_process_mcmc.py:259-265; emcee's `vectorize`). */
 int eb200_gp_eval_value_batch_host(eb200_gp* gp, int nb, const double* p_host, double* result_host);
 
