@@ -1,25 +1,36 @@
 #!/usr/bin/env python
 """
-Headline benchmark: GP log-marginal-likelihood + gradient evaluations per second at
-BASELINE.json configuration C2 (N = 4096 training rows, n_par = 8 -> kernel dimension d = 9,
-P = 10 hyperparameters, fp64), synthetic seeded data.
+Benchmark of the GP hot path on BASELINE.json's configurations, synthetic seeded data.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--skip-secondary]
 
-One "step" = one pass of the hot path over a batch of BATCH hyperparameter vectors (kernel
-matrix build, Cholesky, triangular inverse, alpha, K^-1 tiles fused with the gradient
-traces, final reduction) -- what the reference does as one `fun(p)` + one `jac(p)` call per
-vector (swiftemulator/emulators/gaussian_process.py:208-221).
+HEADLINE (the JSON line's metric/value/e2e): log-marginal-likelihood + gradient evaluations per second at
+configuration C2 (N = 4096 training rows, n_par = 8 -> kernel dimension d = 9, P = 10 hyperparameters, fp64).
+One "step" = one pass of the hot path over a batch of BATCH independent hyperparameter vectors (kernel matrix
+build, Cholesky, triangular inverse, alpha, K^-1 tiles fused with the gradient traces, final reduction) -- what
+the reference does as one `fun(p)` + one `jac(p)` call per vector
+(swiftemulator/emulators/gaussian_process.py:208-221).  The vectors of a step are independent (optimiser
+restarts, leave-one-out refits): they are evaluated on BATCH GP handles holding the same data, four at a time
+sharing launches (eb200_gp_eval_multi_*: interleaved factorisations; bit-identical to stand-alone evaluations,
+asserted below).
 
-value  : whole-job evals/s with inputs resident in HBM (hyperparameter vectors on the device,
-         results left on the device), timed with CUDA events on the launching stream.
-e2e    : the same metric through the host-buffer C ABI call (eb200_gp_eval_host): every
-         evaluation copies its hyperparameter vector host->device from pinned memory and reads
-         the result vector device->host inside the timed region.
-N > 1  : one process per GPU (torchrun); every rank owns an independent problem of the same
-         shape (optimiser restarts / leave-one-out refits shard like this) -- weak scaling, no
-         data-path collective; the timed region is bracketed by barriers and the max over
-         ranks is taken.
+value  : whole-job evals/s with inputs resident in HBM (hyperparameter vectors on the device, results left on
+         the device), timed with CUDA events on the launching stream.
+e2e    : the same metric through the host-buffer C ABI call (eb200_gp_eval_multi_host): every step copies its
+         hyperparameter vectors host->device from pinned memory and reads the result vectors device->host inside
+         the timed region.
+N > 1  : one process per GPU (torchrun); every rank owns independent problems of the same shape -- weak scaling,
+         no data-path collective; barriers on both sides, max over ranks.
+
+SECONDARY BLOCKS in the same JSON line (BASELINE.json's other two metrics, the sharded configurations; both are
+STRONG scaling: the same total work at every N, through the product's drivers, collectives inside the timed
+region, max over ranks):
+sweep_c5 : configuration C5, the Sobol sweep -- 2^20 parameter rows x 32 independent values predicted (mean +
+           variance) against the C2 emulator through `sensitivity.sobol.sweep_predict` (rows split over ranks,
+           results all-gathered from device memory over NCCL, one copy to the host).
+loo_c4   : configuration C4, leave-one-out cross check at N = 8176 -- `CrossCheck.build_emulators` over a fixed
+           subset of the 512 simulations (refits handed out dynamically to ranks, scipy BFGS per refit, likelihood
+           evaluations of concurrent refits combined into shared launches).
 """
 from __future__ import annotations
 
@@ -43,9 +54,18 @@ sys.path.insert(0, ROOT)
 
 N_TRAIN, N_PAR = 4096, 8
 DIM = N_PAR + 1
-BATCH = 8  # evaluations per step
+BATCH = 8  # independent evaluations per step
 WORKLOAD = "C2: LML+grad, N=4096 (256 sims x 16 points), n_par=8 (kernel d=9, P=10), fp64"
 METRIC = "GP LML+grad evals/s (N=4096, d=8, fp64)"
+# identical in both arms (the driver compares the dicts); what an arm samples of it is in its cpu_baseline.sample
+CONFIG = {
+    "workload": WORKLOAD,
+    "batch": "8 independent hyperparameter vectors per step, drawn N(x0, 0.5^2), seed 7",
+    "per_gpu": "independent problems of this shape on every rank (weak scaling)",
+    "cache": "working set 2 x 134 MB per problem exceeds the 126 MB L2 (inputs larger than L2)",
+}
+SWEEP_LOG2_ROWS, SWEEP_IND = 20, 32
+LOO_REFITS = 32
 
 
 def make_inputs(seed_offset=0):
@@ -54,12 +74,12 @@ def make_inputs(seed_offset=0):
     x, y, yerr = synthetic.design_arrays(N_TRAIN, DIM, seed=1235 + seed_offset)
     yerr2 = np.ascontiguousarray(yerr ** 2, dtype=np.float64)  # squared in float32, as george does
     noise = np.sqrt(yerr2 + 1.25e-12) ** 2
-    ps = synthetic.perturbed_parameter_vectors(DIM, count=32, seed=7)
+    ps = synthetic.perturbed_parameter_vectors(DIM, count=32, seed=7)[1:]  # 32 vectors around x0
     return x.astype(np.float64), y.astype(np.float64), noise, yerr, ps
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clock / throttle-reason samples while the timed region runs."""
+    """nvidia-smi clock / throttle-reason samples while a timed region runs."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -135,13 +155,189 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "evals_per_step": 1, "note": "george is not installable here; oracle/gp_oracle.py restates it"},
-        "cpu_baseline": {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(CONFIG),
+        "cpu_baseline": {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "george is not installable here; oracle/gp_oracle.py restates it (checked against scikit-learn, tests/test_oracle_vs_sklearn.py)"},
         "e2e": {"value": rate, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
     }
     emit(line)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def dgemm_peak(torch, dev):
+    """cuBLAS DGEMM 8192^3 on this GPU, TFLOP/s (MEASURED_PEAKS.json has no fp64 entry)."""
+    a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    c = torch.empty(8192, 8192, dtype=torch.float64, device=dev)
+    best = 1e30
+    for it in range(4):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(); torch.matmul(a, b, out=c); s1.record(); torch.cuda.synchronize()
+        if it:
+            best = min(best, s0.elapsed_time(s1))
+    del a, b, c
+    return 2 * 8192.0 ** 3 / best / 1e9
+
+
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of a kernel from the committed ncu --set full summary (None if absent)."""
+    import csv
+
+    for name in ("r02_top_kernels_ncu.csv", "r01_top_kernels_ncu.csv"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                rows = list(csv.DictReader(fh))
+            for row in rows[1:]:
+                if kernel_key in row["Kernel Name"]:
+                    return (float(row["dram__bytes_read.sum"]) + float(row["dram__bytes_write.sum"])) * 1e6, name
+        except Exception:
+            continue
+    return None, None
+
+
+def timed_collective_region(torch, td, world, dev, fn):
+    """Run fn() between barriers; returns (result, device milliseconds by CUDA events on the current stream, wall
+    milliseconds), both as the max over ranks."""
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    out = fn()
+    e1.record()
+    barrier()
+    wall = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e0.elapsed_time(e1), wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    ev_ms, wall_ms = (float(v) for v in t.cpu())
+    return out, ev_ms, wall_ms
+
+
+def block_sweep_c5(torch, td, world, rank, local, dev, peak_tflops, log2_rows):
+    """BASELINE.json configuration C5 through the product's sweep driver (strong scaling)."""
+    from emulator_b200 import synthetic
+    from emulator_b200.emulators import GaussianProcessEmulator
+    from emulator_b200.emulators.base import build_gp, default_kernel
+    from emulator_b200.sensitivity import sobol
+
+    spec, params, values = synthetic.make_config("C2")
+    emu = GaussianProcessEmulator(device=local)
+    emu._build_arrays(spec, params, values)
+    emu.kernel = default_kernel(spec.number_of_parameters + 1)
+    gp = build_gp(emu.kernel, None, emu.independent_variables, emu.dependent_variables, emu.dependent_variable_errors, device=local)
+    p_star = synthetic.perturbed_parameter_vectors(DIM, 1)[1]  # the same hyperparameters on every rank: bitwise-equal replicas
+    gp.set_parameter_vector(p_star)
+    emu.emulator = gp
+    rows = 1 << log2_rows
+    base = max(1, min(1 << 16, rows // (spec.number_of_parameters + 2)))
+    design = sobol.saltelli_design(spec, base, seed=11)  # A, B and the 8 AB_i blocks: 10 * base rows
+    top_up = rows - len(design)
+    if top_up > 0:  # further rows of the same kind up to exactly 2^k (SURVEY.md section 8d)
+        extra = sobol.saltelli_design(spec, -(-top_up // (spec.number_of_parameters + 2)), seed=12)[:top_up]
+        design = np.vstack([design, extra])
+    theta = np.ascontiguousarray(design[:rows])
+    ind = np.linspace(0.0, 1.0, SWEEP_IND)
+    sobol.sweep_predict(emu, theta[: 1 << 12], ind, want_var=True)  # warm-up: factorisation, allocations, NCCL
+    sampler = ClockSampler(local)
+    sampler.start()
+    (mean, var), ev_ms, wall_ms = timed_collective_region(torch, td, world, dev, lambda: sobol.sweep_predict(emu, theta, ind, want_var=True))
+    clocks = sampler.stop()
+    m = rows * SWEEP_IND
+    n = N_TRAIN
+    flops = float(n) * n * m  # variance: one triangular product per query row (SURVEY.md section 8d)
+    out = {
+        "workload": f"C5: Sobol sweep, 2^{log2_rows} parameter rows x {SWEEP_IND} independent values (mean+var) against the C2 GP (N=4096, d=9)",
+        "metric": "predictions/s (mean+var)", "value": m / (ev_ms / 1e3), "unit": "query rows/s", "seconds": ev_ms / 1e3,
+        "wall_seconds": wall_ms / 1e3, "query_rows": m, "scaling": "strong", "n_gpus": world,
+        "timed": "sensitivity.sobol.sweep_predict between barriers: H2D of this rank's parameter rows, query rows formed on the device, "
+                 "mean + variance kernels, NCCL all-gather of both results from device memory, one D2H copy each; CUDA events, max over ranks",
+        "h2d_bytes": int(theta.nbytes // world + ind.nbytes), "d2h_bytes": int(2 * m * 8),
+        "roofline": {"bound": "tensor", "kernel": "var_gemm_kernel (V = K* L^-T reduced to row norms; DMMA.8x8x4 128x128 tiles)",
+                     "flops": flops, "achieved": flops / ev_ms / 1e9 / world, "peak": peak_tflops, "unit": "TFLOP/s per GPU",
+                     "frac": flops / ev_ms / 1e9 / world / peak_tflops},
+        "checksum": float(mean.sum() + var.sum()), "clocks": clocks,
+    }
+    if world == 1 and rank == 0:
+        from oracle import gp_oracle
+
+        x = emu.independent_variables.astype(np.float64)
+        y = emu.dependent_variables.astype(np.float64)
+        diag = gp_oracle.noise_diagonal(emu.dependent_variable_errors)
+        sl = 128  # theta rows -> 4096 query rows
+        t_rows = np.empty((sl * SWEEP_IND, DIM), dtype=np.float32)
+        t_rows[:, 0] = np.tile(ind, sl)
+        t_rows[:, 1:] = np.repeat(theta[:sl], SWEEP_IND, axis=0)
+        t0 = time.perf_counter()
+        ref_mu, ref_var = gp_oracle.predict(p_star, x, diag, y, t_rows.astype(np.float64))
+        dt = time.perf_counter() - t0
+        amp = gp_oracle.amplitude(p_star, DIM)
+        out["cpu_baseline"] = {"value": sl * SWEEP_IND / dt, "unit": "query rows/s", "cores": blas_threads(), "kind": "port",
+                               "sample": f"{sl * SWEEP_IND} query rows (the first {sl} parameter rows) through oracle predict, factorisation included; {dt:.2f} s"}
+        out["parity_on_cpu_sample"] = {
+            "mean_rel": float(np.max(np.abs(mean[:sl].ravel() - ref_mu)) / np.max(np.abs(ref_mu))),
+            "var_rel_amp": float(np.max(np.abs(var[:sl].ravel() - ref_var)) / amp),
+        }
+        assert out["parity_on_cpu_sample"]["mean_rel"] <= 1e-9 and out["parity_on_cpu_sample"]["var_rel_amp"] <= 1e-9
+    gp.close()
+    return out
+
+
+def block_loo_c4(torch, td, world, rank, local, dev, peak_tflops, refits):
+    """BASELINE.json configuration C4 (a fixed subset of its 512 refits) through CrossCheck (strong scaling)."""
+    from emulator_b200 import dist, synthetic
+    from emulator_b200.sensitivity import CrossCheck
+
+    spec, params, values = synthetic.make_config("C4")
+    uids = list(values.model_values.keys())[:refits]
+    cc = CrossCheck(device=local, leave_out=uids)
+    sampler = ClockSampler(local)
+    sampler.start()
+    _, ev_ms, wall_ms = timed_collective_region(torch, td, world, dev, lambda: cc.build_emulators(spec, params, values))
+    clocks = sampler.stop()
+    stats = cc.build_stats
+    totals = dist.all_reduce_sum(np.array([stats["device_evaluations"], stats["combined_calls"], stats["refits"]], dtype=np.float64))
+    per_rank = dist.all_reduce_sum(np.eye(world)[rank] * stats["refits"])
+    n_loo = len(next(iter(cc.cross_emulators.values())).independent_variables)
+    flops = totals[0] * float(n_loo) ** 3
+    out = {
+        "workload": f"C4: CrossCheck.build_emulators, {refits} of the 512 leave-one-out refits at N={n_loo} (d=9), scipy BFGS each",
+        "metric": "LOO refits/s", "value": refits / (ev_ms / 1e3), "unit": "refits/s", "seconds": ev_ms / 1e3, "wall_seconds": wall_ms / 1e3,
+        "scaling": "strong", "n_gpus": world, "refits": refits, "refits_per_rank": [int(v) for v in per_rank],
+        "device_evaluations": int(totals[0]), "combined_native_calls": int(totals[1]),
+        "timed": "CrossCheck.build_emulators between barriers: array building, handle creation, BFGS (host), likelihood evaluations "
+                 "(device, concurrent refits share launches), all-reduce of the optima; CUDA events on an idle stream = wall clock, max over ranks",
+        "roofline": {"bound": "tensor", "flops": flops, "achieved": flops / ev_ms / 1e9 / world, "peak": peak_tflops, "unit": "TFLOP/s per GPU",
+                     "frac": flops / ev_ms / 1e9 / world / peak_tflops, "note": "N^3 flop per LML+grad evaluation, host time included"},
+        "projected_512_refits_s": 512.0 / (refits / (ev_ms / 1e3)),
+        "checksum": float(cc.cross_fit_parameters.sum()), "clocks": clocks,
+    }
+    if world == 1 and rank == 0:
+        from oracle import gp_oracle
+
+        emu = next(iter(cc.cross_emulators.values()))
+        x, y = emu.independent_variables.astype(np.float64), emu.dependent_variables.astype(np.float64)
+        diag = gp_oracle.noise_diagonal(emu.dependent_variable_errors)
+        p = emu.emulator.get_parameter_vector()
+        t0 = time.perf_counter()
+        ref_lml, ref_grad, _, _ = gp_oracle.lml_and_grad_lean(p, x, diag, y)
+        dt = time.perf_counter() - t0
+        evals_per_refit = totals[0] / refits
+        out["cpu_baseline"] = {"value": 1.0 / (dt * evals_per_refit), "unit": "refits/s", "cores": blas_threads(), "kind": "port",
+                               "sample": f"1 LML+grad evaluation of the lean oracle (the GPU path's algorithm; the george-faithful one needs a 5.3 GB "
+                                         f"gradient tensor here) at N={n_loo}: {dt:.1f} s, times the {evals_per_refit:.1f} evaluations BFGS took per refit"}
+        lml = emu.emulator.log_likelihood(emu.dependent_variables)
+        grad = emu.emulator.grad_log_likelihood(emu.dependent_variables)
+        out["parity_on_cpu_sample"] = {"lml_rel": float(abs(lml - ref_lml) / abs(ref_lml)),
+                                       "grad_rel": float(np.max(np.abs(grad - ref_grad)) / np.max(np.abs(ref_grad)))}
+    for e in cc.cross_emulators.values():
+        e.emulator.close()
+    return out
 
 
 def run_ours(args):
@@ -149,7 +345,7 @@ def run_ours(args):
     import torch.distributed as td
 
     from emulator_b200 import _lib
-    from emulator_b200.device import DeviceProblem
+    from emulator_b200.device import DeviceProblem, evaluate_many, evaluate_many_device, profile_group_stages
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -161,29 +357,32 @@ def run_ours(args):
     dev = torch.device("cuda", local)
 
     x, y, noise, _, ps = make_inputs(seed_offset=rank)
-    gp = DeviceProblem(x, noise, device=local)
-    gp.set_residual(y)
-    P = DIM + 1
+    gps = []
+    for _ in range(BATCH):
+        gp = DeviceProblem(x, noise, device=local)
+        gp.set_residual(y)
+        gps.append(gp)
+    P, L = DIM + 1, DIM + 5
     n_ps = len(ps)
+    assert n_ps % BATCH == 0
     p_dev = torch.from_numpy(ps).to(dev)
-    out_dev = torch.zeros((n_ps, DIM + 5), dtype=torch.float64, device=dev)
+    out_dev = torch.zeros((n_ps, L), dtype=torch.float64, device=dev)
     stream = torch.cuda.Stream(device=dev)  # explicit stream: handle 0 would select the GP's own stream
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
 
     def step_device(step):
-        for b in range(BATCH):
-            i = (step * BATCH + b) % n_ps
-            gp.evaluate_device(p_dev[i].data_ptr(), True, out_dev[i].data_ptr(), sptr)
+        i = (step * BATCH) % n_ps
+        evaluate_many_device(gps, p_dev[i].data_ptr(), P, True, out_dev[i].data_ptr(), L, sptr)
 
-    host_results = np.zeros((n_ps, DIM + 5))
+    host_results = np.zeros((n_ps, L))
 
     def step_host(step):
-        for b in range(BATCH):
-            i = (step * BATCH + b) % n_ps
-            lml, grad, info, _, _ = gp.evaluate(ps[i], True)
-            host_results[i, 0] = lml
-            host_results[i, 1 : P + 1] = grad
+        i = (step * BATCH) % n_ps
+        lml, grad, info = evaluate_many(gps, ps[i : i + BATCH], want_grad=True)
+        host_results[i : i + BATCH, 0] = lml
+        host_results[i : i + BATCH, 1 : P + 1] = grad
+        host_results[i : i + BATCH, P + 1] = info
 
     def barrier():
         if world > 1:
@@ -220,52 +419,43 @@ def run_ours(args):
     dev_ms, e2e_ms = (float(v) for v in times.cpu())
     evals = args.steps * BATCH * world
 
-    # sanity: device and host paths agree bit for bit with each other
+    # sanity: the device- and host-pointer paths agree bit for bit, and a grouped evaluation equals a stand-alone one
     res = out_dev.cpu().numpy()
     used = sorted({(s * BATCH + b) % n_ps for s in range(args.steps) for b in range(BATCH)})
     assert all(res[i, DIM + 2] == 0 for i in used), "Cholesky failed in the timed region"
-    assert np.array_equal(res[used, : P + 1], host_results[used, : P + 1]), "device/host entry points disagree"
+    assert np.array_equal(res[used, : P + 2], host_results[used, : P + 2]), "device/host entry points disagree"
+    alone = gps[3].evaluate(ps[used[3]], True)
+    assert alone[0] == res[used[3], 0] and np.array_equal(alone[1], res[used[3], 1 : P + 1]), "grouped != stand-alone evaluation"
 
+    line = None
+    peak_tflops = dgemm_peak(torch, dev) if rank == 0 else 0.0
+    pk = torch.tensor([peak_tflops], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(pk, op=td.ReduceOp.MAX)
+    peak_tflops = float(pk.cpu()[0])
     if rank == 0:
-        # ---- roofline of the dominant stage, live: per-stage CUDA-event times + cuBLAS DGEMM peak ----
-        stage_ms = gp.profile_stages(ps[0], reps=3)
+        # ---- roofline of the dominant stage, live: per-stage CUDA-event times of one group + cuBLAS DGEMM peak ----
+        group = 4
+        stage_ms = profile_group_stages(gps[:group], ps[:group], reps=3) / group  # per evaluation
+        single_ms = gps[0].profile_stages(ps[0], reps=3)
         names = ["params", "kbuild_cholesky_inverse", "alpha", "kinv_traces", "finalize"]
         n3 = float(N_TRAIN) ** 3
         stage_flops = [0.0, 2 * n3 / 3, 4.0 * N_TRAIN * N_TRAIN, n3 / 3, 0.0]
         dominant = int(np.argmax(stage_ms))
-        a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
-        b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
-        c = torch.empty(8192, 8192, dtype=torch.float64, device=dev)
-        best = 1e30
-        for it in range(4):
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record(); torch.matmul(a, b, out=c); s1.record(); torch.cuda.synchronize()
-            if it:
-                best = min(best, s0.elapsed_time(s1))
-        peak_tflops = 2 * 8192.0 ** 3 / best / 1e9
-        del a, b, c
         eval_ms = dev_ms / (args.steps * BATCH)
         achieved_eval = n3 / eval_ms / 1e9
         achieved_stage = stage_flops[dominant] / stage_ms[dominant] / 1e9 if stage_ms[dominant] > 0 else 0.0
-        traffic = None
-        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-            import csv
-            with open(os.path.join(ROOT, "profiles", "r01_top_kernels_ncu.csv")) as fh:
-                rows = list(csv.DictReader(fh))
-            key = "factor_dataflow" if dominant == 1 else "lauum_trace"
-            for row in rows[1:]:
-                if key in row["Kernel Name"]:
-                    traffic = (float(row["dram__bytes_read.sum"]) + float(row["dram__bytes_write.sum"])) * 1e6
-        except Exception:
-            traffic = None
-        kernel_names = {1: "factor_dataflow_kernel (K build + Cholesky + triangular inverse)", 3: "lauum_trace_kernel (K^-1 tiles + traces)"}
+        traffic, traffic_src = ncu_traffic("factor_dataflow" if dominant == 1 else "lauum_trace")
+        kernel_names = {1: "factor_dataflow_kernel<9,true> (K build + Cholesky + triangular inverse of 4 interleaved problems)",
+                        3: "lauum_trace_kernel (K^-1 tiles + traces)"}
         roofline = {
-            "bound": "tensor", "kernel": kernel_names.get(dominant, names[dominant]) + " -- DMMA.8x8x4 tile engine, one launch per eval",
+            "bound": "tensor", "kernel": kernel_names.get(dominant, names[dominant]) + " -- DMMA.8x8x4 tile engine, one launch per group of 4 evaluations",
             "achieved": achieved_stage, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_stage / peak_tflops,
-            "traffic": traffic, "traffic_source": "profiles/r01_top_kernels_ncu.csv (ncu --set full, bytes per launch)",
+            "traffic": traffic, "traffic_source": f"profiles/{traffic_src} (ncu --set full, bytes per launch)" if traffic_src else None,
             "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; MEASURED_PEAKS.json has no fp64 entry",
             "whole_eval": {"flops": n3, "ms": eval_ms, "achieved": achieved_eval, "frac": achieved_eval / peak_tflops},
-            "stage_ms": {k: float(v) for k, v in zip(names, stage_ms)},
+            "stage_ms_per_eval_grouped": {k: float(v) for k, v in zip(names, stage_ms)},
+            "stage_ms_stand_alone": {k: float(v) for k, v in zip(names, single_ms)},
         }
         # ---- CPU baseline on this box's host cores (bounded sample) ----
         cpu_baseline = None
@@ -279,20 +469,29 @@ def run_ours(args):
                 # also the CPU running the GPU path's algorithm (no N x N x P tensor, one triangular inverse)
                 "optimised_cpu_value": lean_rate, "optimised_cpu_sample": f"2 evals of the lean oracle, {np.mean(lean_times):.2f} s each",
             }
-        launches = gp.launches_per_eval(True)
+        kernels_per_group = 7  # parameters, factorisations, z, alpha (2), K^-1 + traces, final sums
+        groups_per_step = BATCH // group
         line = {
             "metric": METRIC, "value": evals / (dev_ms / 1e3), "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "evals_per_step": BATCH, "per_gpu": "one independent problem per rank",
-                       "cache": "working set 2 x 134 MB per problem exceeds the 126 MB L2 (inputs larger than L2)"},
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(CONFIG),
             "e2e": {"value": evals / (e2e_ms / 1e3), "unit": "evals/s", "h2d_bytes_per_step": BATCH * P * 8,
-                    "d2h_bytes_per_step": BATCH * (DIM + 5) * 8, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": launches * args.steps * BATCH, "launches_per_eval": launches,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                    "d2h_bytes_per_step": BATCH * L * 8, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": kernels_per_group * groups_per_step * args.steps, "launches_per_step": kernels_per_group * groups_per_step,
+            "evals_per_step": BATCH, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
+    for gp in gps:
+        gp.close()
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
+    # ---- the sharded configurations (strong scaling; collectives inside the timed regions) ----
+    if not args.skip_secondary:
+        sweep = block_sweep_c5(torch, td, world, rank, local, dev, peak_tflops, args.sweep_log2_rows)
+        loo = block_loo_c4(torch, td, world, rank, local, dev, peak_tflops, args.loo_refits)
+        if rank == 0:
+            line["sweep_c5"] = sweep
+            line["loo_c4"] = loo
+    if rank == 0:
         emit(line)
-    gp.close()
     if world > 1:
         td.barrier()
         td.destroy_process_group()
@@ -318,6 +517,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-secondary", action="store_true", help="headline metric only (no sweep_c5 / loo_c4 blocks)")
+    ap.add_argument("--sweep-log2-rows", type=int, default=SWEEP_LOG2_ROWS)
+    ap.add_argument("--loo-refits", type=int, default=LOO_REFITS)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

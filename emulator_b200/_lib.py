@@ -48,6 +48,7 @@ SIGNATURES = {
     "eb200_gp_eval_value_batch_host": (c_int, [c_void_p, c_int, _dp, _dp]),
     "eb200_gp_predict_host": (c_int, [c_void_p, c_int, _dp, c_int, _dp, _dp]),
     "eb200_gp_predict_grid_host": (c_int, [c_void_p, c_int, _dp, c_int, _dp, c_int, c_int, _dp, _dp]),
+    "eb200_gp_predict_grid_device": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "eb200_gp_predict_device": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "eb200_gp_synchronize": (c_int, [c_void_p]),
     "eb200_gp_debug_stage": (c_int, [c_void_p, _dp, c_int]),
@@ -60,6 +61,7 @@ SIGNATURES = {
     "eb200_gp_debug_value_trace": (c_int, [c_void_p, _dp, POINTER(ctypes.c_ulonglong), POINTER(c_int)]),
     "eb200_gp_value_tasks": (c_int, [c_void_p]),
     "eb200_gp_profile_stages": (c_int, [c_void_p, _dp, c_int, POINTER(ctypes.c_float)]),
+    "eb200_gp_profile_group_stages": (c_int, [POINTER(c_void_p), c_int, _dp, c_int, c_int, POINTER(ctypes.c_float)]),
     "eb200_bench_accumulate": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "eb200_bench_gemm_nt": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

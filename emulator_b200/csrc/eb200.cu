@@ -32,6 +32,12 @@ int fail(const std::string& msg) {
     }                                                                                                 \
   } while (0)
 
+// Tunables (development: read once from the environment).
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
 int pad_dim(int d) {
   static const int buckets[] = {2, 3, 4, 5, 6, 8, 9, 10, 12, 16};
   for (int b : buckets)
@@ -142,6 +148,14 @@ struct eb200_gp {
   size_t grid_theta_cap = 0, grid_ind_cap = 0, grid_out_cap = 0;
   TileTask* var_tasks = nullptr;
   int var_tasks_mt = -1, var_tasks_cnt = 0;
+  // Grow-only scratch of predictions with more query rows than training rows (sweeps): K* rows, padded query
+  // rows, per-tile row sums and the variance GEMM's task list for chunks of up to `rows` query rows.  Smaller
+  // predictions use the handle's resident buffers (K* goes to matrix A, dead once X = L^-1 exists).
+  struct PredictScratch {
+    double *ks = nullptr, *T = nullptr, *rowss = nullptr;
+    TileTask* tasks = nullptr;
+    int rows = 0, tasks_mt = -1, tasks_cnt = 0;
+  } big;
 };
 
 namespace {
@@ -430,33 +444,94 @@ int grow(double** buf, size_t* cap, size_t need) {
   return 0;
 }
 
-int ensure_var_tasks(eb200_gp* h, int mt) {
-  if (h->var_tasks_mt == mt) return 0;
+// Task list of the variance GEMM for mt 128-row blocks of query rows: tile (M, I) contracts over k < (I+1)*128.
+// Blocks of query rows are taken in groups of VAR_GROUP (their K* rows, 4 MB per block at N = 4096, stay in L2
+// while the group's tiles read them), longest contraction first within a group.
+int build_var_tasks(eb200_gp* h, int mt, TileTask* dst, int* cnt, cudaStream_t st) {
+  static const int group = std::max(1, env_int("EB200_VAR_GROUP", 1 << 20));
   std::vector<TileTask> v;
-  for (int M = 0; M < mt; ++M)
-    for (int I = 0; I < h->nT; ++I) v.push_back({M * 128, I * 128, M * 128, 0, I * 128, 0, (I + 1) * 128 / KC, 0});
-  sort_tasks(v, 0);
-  CK(cudaMemcpyAsync(h->var_tasks, v.data(), v.size() * sizeof(TileTask), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaStreamSynchronize(h->stream));  // v goes out of scope
-  h->var_tasks_mt = mt;
-  h->var_tasks_cnt = (int)v.size();
+  for (int M0 = 0; M0 < mt; M0 += group) {
+    const size_t off = v.size();
+    for (int M = M0; M < std::min(mt, M0 + group); ++M)
+      for (int I = 0; I < h->nT; ++I) v.push_back({M * 128, I * 128, M * 128, 0, I * 128, 0, (I + 1) * 128 / KC, 0});
+    sort_tasks(v, off);
+  }
+  CK(cudaMemcpyAsync(dst, v.data(), v.size() * sizeof(TileTask), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // v goes out of scope
+  *cnt = (int)v.size();
   return 0;
 }
 
-// Predict one chunk (mc <= np query rows) whose padded coordinates already sit in h->T_dev.
-int predict_chunk(eb200_gp* h, int mc, int want_var, double* mu_dev, double* var_dev, cudaStream_t st) {
+// Largest number of query rows one pass of the prediction kernels takes.
+int predict_chunk_rows(const eb200_gp* h, size_t m) {
+  if (m <= (size_t)h->np) return h->np;
+  static const int max_rows = env_int("EB200_PREDICT_CHUNK", 16384);
+  const size_t want = std::min<size_t>((m + 127) / 128 * 128, (size_t)std::max(max_rows, h->np));
+  return (int)want;
+}
+
+// Buffers for chunks of `rows` query rows (rows > np: the grow-only scratch).
+int ensure_predict_scratch(eb200_gp* h, int rows, int want_var) {
+  if (rows <= h->np) return 0;
+  eb200_gp::PredictScratch& ps = h->big;
+  if (ps.rows < rows || (want_var && !ps.ks)) {
+    for (void* q : {(void*)ps.ks, (void*)ps.T, (void*)ps.rowss, (void*)ps.tasks})
+      if (q) CK(cudaFree(q));
+    ps = eb200_gp::PredictScratch();
+    CK(cudaMalloc(&ps.T, (size_t)rows * h->dp * sizeof(double)));
+    if (want_var) {
+      CK(cudaMalloc(&ps.ks, (size_t)rows * h->np * sizeof(double)));
+      CK(cudaMalloc(&ps.rowss, (size_t)h->nT * rows * sizeof(double)));
+      CK(cudaMalloc(&ps.tasks, (size_t)(rows / 128) * h->nT * sizeof(TileTask)));
+    }
+    ps.rows = rows;
+  }
+  return 0;
+}
+
+// Padded query rows of the next chunk go here.
+double* predict_rows_buffer(eb200_gp* h, int chunk_rows) { return chunk_rows <= h->np ? h->T_dev : h->big.T; }
+
+// Predict one chunk (mc <= chunk_rows query rows) whose padded coordinates already sit in predict_rows_buffer().
+int predict_chunk(eb200_gp* h, int chunk_rows, int mc, int want_var, double* mu_dev, double* var_dev, cudaStream_t st) {
   const int np = h->np;
+  const bool small = chunk_rows <= np;
   const int blocks = (mc + 31) / 32;
-  double* ks = want_var ? h->A : nullptr;  // L is no longer needed once X = L^-1 exists: reuse as K* scratch
-  DP_SWITCH(h->dp, (predict_mean_kernel<DP><<<blocks, 256, 0, st>>>(h->T_dev, mc, h->X, h->alpha, h->kp, h->n, np, mu_dev, ks, np)));
+  const double* T = small ? h->T_dev : h->big.T;
+  // small chunks: L is no longer needed once X = L^-1 exists, so matrix A doubles as K* scratch
+  double* ks = want_var ? (small ? h->A : h->big.ks) : nullptr;
+  DP_SWITCH(h->dp, (predict_mean_kernel<DP><<<blocks, 256, 0, st>>>(T, mc, h->X, h->alpha, h->kp, h->n, np, mu_dev, ks, np)));
   if (want_var) {
     const int mt = (mc + 127) / 128;
-    if (ensure_var_tasks(h, mt)) return 1;
-    var_gemm_kernel<<<h->var_tasks_cnt, 256, Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES, st>>>(h->var_tasks, h->A, np, h->W, np,
-                                                                                                 h->rowss, np);
-    var_finish_kernel<<<(mc + 255) / 256, 256, 0, st>>>(h->rowss, np, h->nT, h->kp, mc, var_dev);
+    TileTask* tasks = small ? h->var_tasks : h->big.tasks;
+    int& have_mt = small ? h->var_tasks_mt : h->big.tasks_mt;
+    int& cnt = small ? h->var_tasks_cnt : h->big.tasks_cnt;
+    if (have_mt != mt) {
+      if (build_var_tasks(h, mt, tasks, &cnt, st)) return 1;
+      have_mt = mt;
+    }
+    double* rowss = small ? h->rowss : h->big.rowss;
+    const int ld_rowss = small ? np : h->big.rows;
+    var_gemm_kernel<<<cnt, 256, Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES, st>>>(tasks, ks, np, h->W, np, rowss, ld_rowss);
+    var_finish_kernel<<<(mc + 255) / 256, 256, 0, st>>>(rowss, ld_rowss, h->nT, h->kp, mc, var_dev);
   }
   CK(cudaGetLastError());
+  return 0;
+}
+
+// Grid prediction with everything in device memory (see eb200_gp_predict_grid_host).
+int predict_grid_impl(eb200_gp* h, size_t n_theta, const double* theta_dev, int n_ind, const double* ind_dev, int round_f32,
+                      int want_var, double* mu_dev, double* var_dev, cudaStream_t st) {
+  const size_t m = n_theta * (size_t)n_ind;
+  const int chunk = predict_chunk_rows(h, m);
+  if (ensure_predict_scratch(h, chunk, want_var)) return 1;
+  double* rows = predict_rows_buffer(h, chunk);
+  for (size_t q0 = 0; q0 < m; q0 += chunk) {
+    const int mc = (int)std::min<size_t>(chunk, m - q0);
+    const size_t tot = (size_t)mc * h->dp;
+    grid_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(theta_dev, ind_dev, q0, mc, n_ind, h->d, h->dp, round_f32, rows);
+    if (predict_chunk(h, chunk, mc, want_var, mu_dev + q0, want_var ? var_dev + q0 : nullptr, st)) return 1;
+  }
   return 0;
 }
 
@@ -724,6 +799,8 @@ int eb200_gp_destroy(eb200_gp* h) {
       if (q) cudaFree(q);
     if (bs.h_stage) cudaFreeHost(bs.h_stage);
   }
+  for (void* q : {(void*)h->big.ks, (void*)h->big.T, (void*)h->big.rowss, (void*)h->big.tasks})
+    if (q) cudaFree(q);
   if (h->group.p_dev) cudaFree(h->group.p_dev);
   if (h->group.out_dev) cudaFree(h->group.out_dev);
   if (h->group.h_stage) cudaFreeHost(h->group.h_stage);
@@ -813,12 +890,6 @@ int eb200_gp_eval_host(eb200_gp* h, const double* p_host, int mode, double* resu
   return 0;
 }
 
-// Tunables of grouped launches (development: read once from the environment).
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
-}
-
 static int ensure_group_state(eb200_gp* h) {
   eb200_gp::GroupState& gs = h->group;
   if (gs.p_dev) return 0;
@@ -836,7 +907,7 @@ static int ensure_group_state(eb200_gp* h) {
 // result vector to out_dev + b * out_stride (device pointers).  Results equal stand-alone evaluations bit for
 // bit: every tile and every reduction is computed by the same code in the same order whoever claims it.
 static int enqueue_group(eb200_gp** g, int m, int mode, const double* p_dev, int p_stride, double* out_dev, int out_stride,
-                         cudaStream_t st) {
+                         cudaStream_t st, cudaEvent_t* stage_events = nullptr) {
   eb200_gp* h0 = g[0];
   const int nt = h0->nt;
   const bool vo = mode == EB200_EVAL_VALUE_ONLY;
@@ -867,13 +938,18 @@ static int enqueue_group(eb200_gp** g, int m, int mode, const double* p_dev, int
     fill_post_args(h, mode, pb.p[b]);
     pb.p[b].out = out_dev + (size_t)b * out_stride;
   }
+  // (stage_events, diagnostics: [0] before the parameters, [s] after the last kernel of stage s = 1..5)
+  if (stage_events) CK(cudaEventRecord(stage_events[0], st));
   prep_params_group_kernel<<<m, 32, 0, st>>>(p_dev, p_stride, h0->d, prep);
+  if (stage_events) CK(cudaEventRecord(stage_events[1], st));
   DP_SWITCH(h0->dp, (factor_dataflow_kernel<DP, true><<<grid, 256, FactorSmem<DP>::BYTES, st>>>(fb)));
+  if (stage_events) CK(cudaEventRecord(stage_events[2], st));
   for (const Op& op : h0->ops) {
     if (op.stage < 3 || op.debug_only) continue;
     if (op.grad_only && mode != EB200_EVAL_GRAD) continue;
     if (vo && op.stage == 3) continue;
     launch_post(h0, op, pb, st, mode, nullptr);
+    if (stage_events) CK(cudaEventRecord(stage_events[op.stage], st));  // (re-recorded by a stage's later kernels: the last stands)
   }
   CK(cudaGetLastError());
   return 0;
@@ -1073,11 +1149,14 @@ int eb200_gp_predict_device(eb200_gp* h, int m, const double* t_dev, int want_va
   if (!h->factor_valid) return fail("predict: no factorisation resident (evaluate with EB200_EVAL_LML or EB200_EVAL_GRAD first)");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-  for (int q0 = 0; q0 < m; q0 += h->np) {
-    const int mc = std::min(h->np, m - q0);
+  const int chunk = predict_chunk_rows(h, (size_t)std::max(m, 0));
+  if (ensure_predict_scratch(h, chunk, want_var)) return 1;
+  double* rows = predict_rows_buffer(h, chunk);
+  for (int q0 = 0; q0 < m; q0 += chunk) {
+    const int mc = std::min(chunk, m - q0);
     const size_t tot = (size_t)mc * h->dp;
-    pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(t_dev + (size_t)q0 * h->d, mc, h->d, h->dp, h->T_dev);
-    if (predict_chunk(h, mc, want_var, mu_dev + q0, want_var ? var_dev + q0 : nullptr, st)) return 1;
+    pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(t_dev + (size_t)q0 * h->d, mc, h->d, h->dp, rows);
+    if (predict_chunk(h, chunk, mc, want_var, mu_dev + q0, want_var ? var_dev + q0 : nullptr, st)) return 1;
   }
   return 0;
 }
@@ -1097,7 +1176,7 @@ int eb200_gp_predict_host(eb200_gp* h, int m, const double* t_host, int want_var
     CK(cudaMemcpyAsync(h->T_in, stage_t, (size_t)mc * d * sizeof(double), cudaMemcpyHostToDevice, st));
     const size_t tot = (size_t)mc * h->dp;
     pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->T_in, mc, d, h->dp, h->T_dev);
-    if (predict_chunk(h, mc, want_var, h->mu_dev, h->var_dev, st)) return 1;
+    if (predict_chunk(h, h->np, mc, want_var, h->mu_dev, h->var_dev, st)) return 1;
     CK(cudaMemcpyAsync(stage_mu, h->mu_dev, mc * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (want_var) CK(cudaMemcpyAsync(stage_var, h->var_dev, mc * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1105,6 +1184,17 @@ int eb200_gp_predict_host(eb200_gp* h, int m, const double* t_host, int want_var
     if (want_var) memcpy(var_host + q0, stage_var, mc * sizeof(double));
   }
   return 0;
+}
+
+int eb200_gp_predict_grid_device(eb200_gp* h, long long n_theta, const double* theta_dev, int n_ind, const double* ind_dev,
+                                 int round_f32, int want_var, double* mu_dev, double* var_dev, void* stream) {
+  if (!h || !theta_dev || !ind_dev || !mu_dev || (want_var && !var_dev)) return fail("predict_grid: null argument");
+  if (n_theta < 0 || n_ind < 1 || h->d < 2) return fail("predict_grid: needs n_ind >= 1 and a kernel dimension >= 2");
+  if (!h->factor_valid) return fail("predict: no factorisation resident (evaluate with EB200_EVAL_LML or EB200_EVAL_GRAD first)");
+  if (n_theta == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  return predict_grid_impl(h, (size_t)n_theta, theta_dev, n_ind, ind_dev, round_f32, want_var, mu_dev, var_dev, st);
 }
 
 int eb200_gp_predict_grid_host(eb200_gp* h, int n_theta, const double* theta_host, int n_ind, const double* ind_host,
@@ -1129,13 +1219,7 @@ int eb200_gp_predict_grid_host(eb200_gp* h, int n_theta, const double* theta_hos
   }
   CK(cudaMemcpyAsync(h->grid_theta, theta_host, (size_t)n_theta * (h->d - 1) * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->grid_ind, ind_host, (size_t)n_ind * sizeof(double), cudaMemcpyHostToDevice, st));
-  for (size_t q0 = 0; q0 < m; q0 += h->np) {
-    const int mc = (int)std::min<size_t>(h->np, m - q0);
-    const size_t tot = (size_t)mc * h->dp;
-    grid_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->grid_theta, h->grid_ind, q0, mc, n_ind, h->d, h->dp,
-                                                                      round_f32, h->T_dev);
-    if (predict_chunk(h, mc, want_var, h->grid_mu + q0, want_var ? h->grid_var + q0 : nullptr, st)) return 1;
-  }
+  if (predict_grid_impl(h, (size_t)n_theta, h->grid_theta, n_ind, h->grid_ind, round_f32, want_var, h->grid_mu, h->grid_var, st)) return 1;
   CK(cudaMemcpyAsync(mu_host, h->grid_mu, m * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (want_var) CK(cudaMemcpyAsync(var_host, h->grid_var, m * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -1233,6 +1317,35 @@ int eb200_gp_profile_stages(eb200_gp* h, const double* p_host, int reps, float* 
   }
   for (auto& e : ev) cudaEventDestroy(e);
   h->factor_valid = true;
+  return 0;
+}
+
+int eb200_gp_profile_group_stages(eb200_gp** gps, int nb, const double* p_host, int p_stride, int reps, float* ms_out) {
+  if (!gps || !p_host || !ms_out || reps < 1 || nb < 1 || nb > MAX_BATCH) return fail("profile_group_stages: bad argument");
+  if (check_distinct(gps, nb, "profile_group_stages")) return 1;
+  eb200_gp* h = gps[0];
+  for (int b = 0; b < nb; ++b)
+    if (!same_shape(gps[b], h) || p_stride < h->d + 1) return fail("profile_group_stages: the handles must share one shape");
+  CK(cudaSetDevice(h->device));
+  if (ensure_group_state(h)) return 1;
+  const int PS_ = MAXD + 1, OS_ = MAXD + 8;
+  for (int b = 0; b < nb; ++b) memcpy(h->group.h_stage + (size_t)b * PS_, p_host + (size_t)b * p_stride, (h->d + 1) * sizeof(double));
+  CK(cudaMemcpyAsync(h->group.p_dev, h->group.h_stage, (size_t)nb * PS_ * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  cudaEvent_t ev[6];
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  for (int s = 0; s < 5; ++s) ms_out[s] = 0.f;
+  for (int rep = 0; rep <= reps; ++rep) {  // rep 0 is a warm-up
+    if (enqueue_group(gps, nb, EB200_EVAL_GRAD, h->group.p_dev, PS_, h->group.out_dev, OS_, h->stream, ev)) return 1;
+    CK(cudaStreamSynchronize(h->stream));
+    if (rep == 0) continue;
+    for (int s = 0; s < 5; ++s) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, ev[s], ev[s + 1]));
+      ms_out[s] += ms / reps;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  for (int b = 0; b < nb; ++b) gps[b]->factor_valid = true;
   return 0;
 }
 

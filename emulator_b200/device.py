@@ -162,6 +162,17 @@ class DeviceProblem:
             "eb200_gp_predict_device",
         )
 
+    def predict_grid_device(self, n_theta: int, theta_ptr: int, n_ind: int, ind_ptr: int, want_var: bool, mu_ptr: int,
+                            var_ptr: int, stream: int = 0, round_f32: bool = True):
+        """Grid prediction with theta[n_theta, d-1], independent[n_ind] and the results [n_theta * n_ind] in HBM."""
+        _lib.check(
+            self._lib.eb200_gp_predict_grid_device(
+                self._h, n_theta, c_void_p(theta_ptr), n_ind, c_void_p(ind_ptr), int(bool(round_f32)), int(bool(want_var)),
+                c_void_p(mu_ptr), c_void_p(var_ptr), c_void_p(stream),
+            ),
+            "eb200_gp_predict_grid_device",
+        )
+
     def synchronize(self):
         _lib.check(self._lib.eb200_gp_synchronize(self._h), "synchronize")
 
@@ -235,3 +246,15 @@ def evaluate_many_device(problems, p_ptr: int, p_stride: int, want_grad: bool, r
                                        c_void_p(result_ptr), result_stride, c_void_p(stream)),
         "eb200_gp_eval_multi_device",
     )
+
+
+def profile_group_stages(problems, ps, reps: int = 3) -> np.ndarray:
+    """Device milliseconds per stage of ONE grouped LML+grad evaluation of `problems` (up to 8, one shape) at the
+    rows of ps: [params, factorisations (shared launch), alpha, K^-1 + traces, final sums]."""
+    nb = len(problems)
+    ps = np.ascontiguousarray(ps, dtype=np.float64)
+    handles = (c_void_p * nb)(*[q._h for q in problems])
+    out = (ctypes.c_float * 5)()
+    _lib.check(problems[0]._lib.eb200_gp_profile_group_stages(handles, nb, _lib.as_double_ptr(ps), ps.shape[1], reps, out),
+               "profile_group_stages")
+    return np.array(list(out), dtype=np.float64)

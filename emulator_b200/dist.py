@@ -133,6 +133,106 @@ def all_gather_concat(block: np.ndarray, count: int) -> np.ndarray:
     return out.reshape((count,) + block.shape[1:])
 
 
+def all_reduce_sum(array: np.ndarray) -> np.ndarray:
+    """Element-wise sum over ranks of a small float64 array (every rank gets the result)."""
+    td = _pg()
+    array = np.ascontiguousarray(array, dtype=np.float64)
+    if td is None or td.get_world_size() == 1:
+        return array
+    import torch
+
+    use_cuda = td.get_backend() == "nccl"
+    dev = torch.device("cuda", local_device()) if use_cuda else torch.device("cpu")
+    t = torch.from_numpy(array.copy()).to(dev)
+    td.all_reduce(t, op=td.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+class WorkClaimer:
+    """
+    Hands out the unit indices 0 .. count-1 to whoever asks next -- host threads of this rank and, through a
+    counter in the process group's store, the other ranks: a rank whose units finish early takes more
+    (leave-one-out refits take 60 to 80 likelihood evaluations each, so a fixed i mod world split leaves ranks
+    idle at the end).  `claimer.next()` returns an index or None; `claimer.taken` lists what this rank got.
+    Collective: every rank constructs the claimers of a program in the same order.  Without a store
+    (single process) or with dynamic=False the split is the round-robin one.
+    """
+
+    _serial = 0
+    _serial_lock = None
+
+    def __init__(self, count: int, dynamic: bool = True):
+        import threading
+
+        if WorkClaimer._serial_lock is None:
+            WorkClaimer._serial_lock = threading.Lock()
+        with WorkClaimer._serial_lock:
+            WorkClaimer._serial += 1
+            self._key = f"emulator_b200/claim/{WorkClaimer._serial}"
+        self.count = count
+        self.taken: List[int] = []
+        self._lock = threading.Lock()
+        self._store = None
+        td = _pg()
+        if dynamic and td is not None and td.get_world_size() > 1:
+            try:
+                self._store = td.distributed_c10d._get_default_store()
+            except Exception:  # pragma: no cover - private API moved: fall back to the static split
+                self._store = None
+        self._static = iter(my_indices(count)) if self._store is None else None
+
+    def next(self):
+        with self._lock:
+            if self._static is not None:
+                i = next(self._static, None)
+            else:
+                i = int(self._store.add(self._key, 1)) - 1  # atomic fetch-and-add in the store
+                if i >= self.count:
+                    i = None
+            if i is not None:
+                self.taken.append(i)
+            return i
+
+
+def device_collectives() -> bool:
+    """True when results can stay in device memory until they are gathered: a CUDA device is there and the process
+    group (if any) is NCCL."""
+    try:
+        import torch
+    except Exception:  # pragma: no cover
+        return False
+    if not torch.cuda.is_available():
+        return False
+    td = _pg()
+    return td is None or td.get_world_size() == 1 or td.get_backend() == "nccl"
+
+
+def all_gather_concat_device(block, count: int):
+    """
+    `all_gather_concat` for a CUDA tensor: `block` holds this rank's rows [start, stop) of a [count, width]
+    result, padded to ceil(count / world) rows.  The slices are gathered over NVLink from where they are
+    and the result crosses the bus to the host ONCE; returns a numpy array [count, width].
+    """
+    import torch
+
+    td = _pg()
+    world = td.get_world_size() if td is not None else 1
+    per_rank = (count + world - 1) // world
+    assert block.shape[0] == per_rank and block.is_cuda
+    if world == 1:
+        return block[:count].cpu().numpy()
+    gathered = torch.empty((world * per_rank,) + tuple(block.shape[1:]), dtype=block.dtype, device=block.device)
+    td.all_gather_into_tensor(gathered, block.contiguous())
+    host = gathered.cpu().numpy()
+    if count == world * per_rank:
+        return host
+    parts = []
+    for r in range(world):
+        start, stop = contiguous_slice(count, r, world)
+        parts.append(host[r * per_rank : r * per_rank + (stop - start)])
+    return np.concatenate(parts, axis=0)
+
+
 def barrier():
     td = _pg()
     if td is not None:

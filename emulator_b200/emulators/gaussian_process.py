@@ -68,6 +68,16 @@ class GaussianProcessEmulator(BaseEmulator):
         self._require_trained()
         return self.emulator.predict_grid(self.dependent_variables, theta_rows, independent, return_var=want_var)
 
+    def predict_grid_device(self, theta_t, independent_t, mean_out, var_out=None):
+        """`predict_grid` on CUDA tensors, results left in device memory (see `GP.predict_grid_device`)."""
+        self._require_trained()
+        self.emulator.predict_grid_device(self.dependent_variables, theta_t, independent_t, mean_out, var_out)
+
+    @property
+    def supports_device_grid(self) -> bool:
+        """Whether `predict_grid_device` applies: a zero-mean GP (mean models are host callables)."""
+        return self.emulator is not None and self.mean_model is None and hasattr(self.emulator, "predict_grid_device")
+
     def predict_batch(self, query_rows: np.ndarray, want_var: bool = True):
         """
         Batched prediction at arbitrary rows [independent, theta...] in ONE device call (the

@@ -19,6 +19,7 @@ from typing import Dict, Optional
 import attr
 import numpy as np
 
+from .. import dist
 from .base import BaseEmulator, build_gp, default_kernel, flatten_model_values, optimise_gp, query_matrix
 from .ensemble import EnsembleSampler
 
@@ -33,6 +34,9 @@ class GaussianProcessEmulatorMCMC(BaseEmulator):
     use_hyperparameter_error: bool = attr.ib(default=False)
     samples_for_error: int = attr.ib(default=100)
     seed: Optional[int] = attr.ib(default=None)
+    #: under torchrun the walkers' likelihood evaluations are split over the ranks (needs a seed: every rank runs the
+    #: same sampler); off: every rank evaluates all walkers itself
+    shard_walkers: bool = attr.ib(default=True)
     device: Optional[int] = attr.ib(default=None)  # None: this rank's GPU under torchrun, else GPU 0 (dist.resolve_device)
 
     hyperparameter_samples: Optional[np.ndarray] = None
@@ -64,10 +68,22 @@ class GaussianProcessEmulatorMCMC(BaseEmulator):
         start = self.fit_result.x
 
         def log_likelihood(positions):  # a block of walker positions per call (value-only, batched on the device)
-            return gp.log_likelihood_batch(y, positions, quiet=True)
+            world = dist.world_size()
+            if world == 1 or not self.shard_walkers or len(positions) < world:
+                return gp.log_likelihood_batch(y, positions, quiet=True)
+            # every rank runs the same seeded sampler, evaluates its slice of the proposals, and one all-gather per
+            # half-step gives every rank all values (deterministic kernels: bitwise-equal replicas, same decisions)
+            start, stop = dist.contiguous_slice(len(positions))
+            mine = gp.log_likelihood_batch(y, positions[start:stop], quiet=True)
+            return dist.all_gather_concat(mine.reshape(-1, 1), len(positions)).ravel()
 
         ndim = len(gp)
-        rng = np.random.default_rng(self.seed)
+        seed = self.seed
+        if seed is None and self.shard_walkers and dist.world_size() > 1:
+            # unseeded run on several ranks: rank 0 draws the seed, everyone uses it (the ranks must propose alike)
+            drawn = float(np.random.SeedSequence().entropy % (1 << 52)) if dist.rank() == 0 else 0.0
+            seed = int(dist.all_reduce_sum(np.array([drawn]))[0])
+        rng = np.random.default_rng(seed)
         gp.eager_gradient = False  # value-only evaluations while sampling
         try:
             sampler = EnsembleSampler(self.walkers, ndim, log_likelihood, seed=rng, vectorize=True)
@@ -100,11 +116,15 @@ class GaussianProcessEmulatorMCMC(BaseEmulator):
         model, variance = self.emulator.predict(y=y, t=t, return_cov=False, return_var=True)
         if self.use_hyperparameter_error:
             picks = self._rng.choice(len(self.hyperparameter_samples), self.samples_for_error, replace=False)
-            spread = np.empty((len(independent), self.samples_for_error), dtype=np.float64)
-            for column, sample in enumerate(picks):
-                self.emulator.set_parameter_vector(self.hyperparameter_samples[sample, :])
-                spread[:, column] = self.emulator.predict(y=y, t=t, return_cov=False, return_var=False)
-            self.emulator.set_parameter_vector(self.hyperparameter_best_fit)
+            if hasattr(self.emulator, "predict_mean_batch"):
+                # the samples are factorised in groups on sibling handles (one native call per group)
+                spread = self.emulator.predict_mean_batch(y, t, self.hyperparameter_samples[picks, :]).T
+            else:
+                spread = np.empty((len(independent), self.samples_for_error), dtype=np.float64)
+                for column, sample in enumerate(picks):
+                    self.emulator.set_parameter_vector(self.hyperparameter_samples[sample, :])
+                    spread[:, column] = self.emulator.predict(y=y, t=t, return_cov=False, return_var=False)
+                self.emulator.set_parameter_vector(self.hyperparameter_best_fit)
             variance = variance + np.var(spread, axis=1)
         return model, variance
 

@@ -29,6 +29,7 @@ from typing import Optional
 import numpy as np
 
 from .. import _lib
+from .. import combine as _combine
 from .. import dist as _dist
 from ..device import DeviceProblem, evaluate_many
 from . import kernels as _kernels
@@ -277,7 +278,12 @@ class GP:
             return self._cache
         with self._using_device():
             self._sync_residual()
-            lml, grad, info, _logdet, _quad = self._problem.evaluate(p, want_grad, value_only=value_only)
+            combiner = None if value_only else _combine.current()
+            if combiner is not None:
+                # several optimiser threads share launches (emulator_b200/combine.py); same numbers, bit for bit
+                lml, grad, info = combiner.evaluate(self._problem, p, want_grad)
+            else:
+                lml, grad, info, _logdet, _quad = self._problem.evaluate(p, want_grad, value_only=value_only)
         self.n_device_evaluations += 1
         if info < 0:
             # the device watchdog fired (a dependency was not published within its budget): not a property of
@@ -390,6 +396,79 @@ class GP:
             rows[:, 1:] = np.repeat(theta, len(independent), axis=0)
             mu = mu + self._call_mean(rows.astype(np.float64)).reshape(mu.shape)
         return (mu, out[1]) if return_var else mu
+
+    def predict_mean_batch(self, y, t, vectors, siblings: int = 8):
+        """
+        Predictive mean at the rows of `t` for EACH hyperparameter vector in `vectors`: returns [len(vectors), len(t)].
+        The loop swiftemulator's MCMC emulator runs one sample at a time to estimate the hyperparameter error
+        (gaussian_process_mcmc.py:410-431: set_parameter_vector + predict per sample, each a full
+        re-factorisation).  Here the samples are factorised in groups on sibling handles holding the same data
+        (`eb200_gp_eval_multi_host`: shared launches for chain-bound sizes) and each sibling predicts its own.
+        Does not change the GP's parameter vector.
+        """
+        self._residual(y)
+        xs = np.asarray(t)
+        if xs.ndim == 1:
+            xs = xs[:, None]
+        if xs.ndim != 2 or xs.shape[1] != self.ndim:
+            raise ValueError("Dimension mismatch")
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        vectors = np.atleast_2d(np.asarray(vectors, dtype=np.float64))
+        if vectors.shape[1] != len(self):
+            raise ValueError("Dimension mismatch")
+        mean_t = self._call_mean(xs)
+        out = np.empty((len(vectors), len(xs)))
+        count = max(1, min(int(siblings), len(vectors)))
+        with self._using_device():
+            self._sync_residual()
+            _residency.make_room(self.device, (count - 1) * _Residency.needed_bytes(len(self._x)), keep=self)
+            extra = []
+            try:
+                for _ in range(count - 1):
+                    q = DeviceProblem(self._x, self._noise, device=self.device)
+                    q.set_residual(self._r)
+                    extra.append(q)
+                group = [self._problem] + extra
+                for g0 in range(0, len(vectors), count):
+                    part = vectors[g0 : g0 + count]
+                    _, _, info = evaluate_many(group[: len(part)], part, want_grad=False)
+                    self.n_device_evaluations += len(part)
+                    if np.any(info != 0):
+                        raise np.linalg.LinAlgError(self._failure_text(int(info[np.nonzero(info)[0][0]])))
+                    for j in range(len(part)):
+                        out[g0 + j] = group[j].predict(xs, want_var=False) + mean_t
+            finally:
+                for q in extra:
+                    q.close()
+                self._device_p = None  # the handle's factorisation now belongs to one of `vectors`
+        return out
+
+    def predict_grid_device(self, y, theta_t, independent_t, mean_out, var_out=None, round_f32=True):
+        """
+        `predict_grid` with everything in device memory: `theta_t` [n_theta, ndim-1], `independent_t` [n_ind] and
+        the outputs `mean_out` / `var_out` [n_theta, n_ind] are CUDA float64 tensors on this GP's device; the work
+        is enqueued on torch's current stream and nothing is copied to the host (sharded sweeps all-gather the
+        results from where they are, emulator_b200/dist.py).  Zero-mean GPs only (a mean model is a host callable).
+        """
+        import torch
+
+        if not (isinstance(self.mean, ConstantModel) and self.mean.value == 0.0):
+            raise NotImplementedError("device-resident grid prediction needs a zero mean (mean models are host callables)")
+        self._residual(y)
+        n_theta, n_ind = int(theta_t.shape[0]), int(independent_t.shape[0])
+        for t in (theta_t, independent_t, mean_out) + ((var_out,) if var_out is not None else ()):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.device.index == self.device):
+                raise ValueError("device-resident grid prediction needs contiguous float64 CUDA tensors on the GP's device")
+        if theta_t.shape[1] != self.ndim - 1 or mean_out.numel() != n_theta * n_ind or (var_out is not None and var_out.numel() != n_theta * n_ind):
+            raise ValueError("Dimension mismatch")
+        with self._using_device():
+            self._evaluate(want_grad=False, need_state=True)
+            stream = torch.cuda.current_stream(theta_t.device).cuda_stream
+            self._problem.predict_grid_device(
+                n_theta, theta_t.data_ptr(), n_ind, independent_t.data_ptr(), var_out is not None, mean_out.data_ptr(),
+                var_out.data_ptr() if var_out is not None else 0, stream=stream, round_f32=round_f32,
+            )
+            torch.cuda.current_stream(theta_t.device).synchronize()  # the handle may be released once unpinned
 
     # ---- lifetime ---------------------------------------------------------------------------------
     def close(self):

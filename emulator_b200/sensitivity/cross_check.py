@@ -12,7 +12,7 @@ the one simulation removed and the caller's container is never mutated.
 
 from __future__ import annotations
 
-from concurrent.futures import ThreadPoolExecutor
+import threading
 from typing import Dict, Hashable, List, Optional
 
 import attr
@@ -20,6 +20,7 @@ import numpy as np
 
 from .. import dist
 from ..backend import ModelParameters, ModelSpecification, ModelValues
+from ..combine import EvaluationCombiner
 from ..emulators.base import build_gp, default_kernel, optimise_gps_lockstep
 from ..emulators.gaussian_process import GaussianProcessEmulator
 from ..emulators.gaussian_process_bins import GaussianProcessEmulatorBins
@@ -35,15 +36,24 @@ class CrossCheck(object):
     mean_model = attr.ib(default=None)
     hide_progress: bool = attr.ib(default=True)
     device: Optional[int] = attr.ib(default=None)  # None: this rank's GPU under torchrun, else GPU 0 (dist.resolve_device)
-    #: leave-one-out refits of this rank run concurrently from this many host threads (each refit
-    #: owns its device handle and stream; the Cholesky's dependency chain of one refit leaves SMs
-    #: idle that another refit's kernels use)
-    workers: int = attr.ib(default=2)
+    #: leave-one-out refits of this rank run from this many host threads, each with scipy's BFGS on its own GP;
+    #: their likelihood evaluations are combined into shared device launches (emulator_b200/combine.py): the
+    #: Cholesky dependency chain of one refit leaves SMs idle that the other refits' tiles use.  Iterates and
+    #: optima are those of a sequential run, bit for bit.
+    workers: int = attr.ib(default=4)
     #: "scipy": every refit is optimised by scipy's BFGS as in the reference; "lockstep": the refits of a rank
     #: advance together through emulator_b200.optimise (same optima, different iterates; pays for small
     #: problems, where the per-evaluation Python overhead dominates)
     fit_mode: str = attr.ib(default="scipy")
+    #: restrict the cross check to these unique identifiers (extension: the reference always leaves out every
+    #: simulation in turn, cross_check.py:98)
+    leave_out: Optional[List[Hashable]] = attr.ib(default=None)
+    #: refits are handed out one at a time to whichever rank / thread asks next (a counter in the process group's
+    #: store) instead of i mod world: BFGS takes 60-80 evaluations per refit, a fixed split leaves ranks idle
+    dynamic_claim: bool = attr.ib(default=True)
     lockstep_result = None
+    #: diagnostics of the last build: refits done by this rank, their device evaluations, combined native calls
+    build_stats: Optional[Dict[str, float]] = None
 
     model_specification: ModelSpecification = None
     model_parameters: ModelParameters = None
@@ -58,12 +68,18 @@ class CrossCheck(object):
         self.model_parameters = model_parameters
         self.model_values = model_values
         self.leave_out_order = list(model_values.model_values.keys())
+        if self.leave_out is not None:
+            wanted = set(self.leave_out)
+            missing = wanted - set(self.leave_out_order)
+            if missing:
+                raise KeyError(f"leave_out names unknown simulations: {sorted(missing, key=str)}")
+            self.leave_out_order = [uid for uid in self.leave_out_order if uid in wanted]
         count = len(self.leave_out_order)
         n_hyper = model_specification.number_of_parameters + 2 if self.kernel is None else len(self.kernel)
 
-        mine = dist.my_indices(count)
         fitted = np.zeros((count, n_hyper))
         emulators = {}
+
         def refit(i):
             uid = self.leave_out_order[i]
             emulator = GaussianProcessEmulator(kernel=self.kernel, mean_model=self.mean_model, device=self.device)
@@ -72,9 +88,11 @@ class CrossCheck(object):
 
         if self.fit_mode not in ("scipy", "lockstep"):
             raise ValueError("fit_mode must be 'scipy' or 'lockstep'")
-        if self.fit_mode == "lockstep" and self.kernel is None and self.mean_model is None and len(mine) > 0:
+        stats = {"combined_calls": 0, "combined_evaluations": 0}
+        if self.fit_mode == "lockstep" and self.kernel is None and self.mean_model is None:
             # all refits of this rank advance together (emulator_b200/optimise.py): one batched device call
             # per optimiser round.  Every refit has the same shape (one simulation left out).
+            mine = dist.my_indices(count)
             done = []
             for i in mine:
                 uid = self.leave_out_order[i]
@@ -86,18 +104,52 @@ class CrossCheck(object):
                     emulator.dependent_variable_errors, device=self.device,
                 )
                 done.append((i, uid, emulator))
-            self.lockstep_result = optimise_gps_lockstep(
-                [e.emulator for _, _, e in done], [e.dependent_variables for _, _, e in done]
-            )
-        elif self.kernel is None and self.mean_model is None and self.workers > 1 and len(mine) > 1:
-            with ThreadPoolExecutor(max_workers=self.workers) as pool:
-                done = list(pool.map(refit, mine))
-        else:  # shared kernel / mean-model objects are mutated by fit_model: keep it sequential
-            done = [refit(i) for i in mine]
+            if done:
+                self.lockstep_result = optimise_gps_lockstep(
+                    [e.emulator for _, _, e in done], [e.dependent_variables for _, _, e in done]
+                )
+        else:
+            claimer = dist.WorkClaimer(count, dynamic=self.dynamic_claim)
+            # shared kernel / mean-model objects are mutated by fit_model: those refits stay sequential
+            threads = max(1, self.workers) if (self.kernel is None and self.mean_model is None) else 1
+            threads = min(threads, max(1, count))
+            done, errors = [], []
+            combiner = EvaluationCombiner(threads)
+
+            def work():
+                try:
+                    with combiner:
+                        while True:
+                            i = claimer.next()
+                            if i is None:
+                                break
+                            done.append(refit(i))
+                except BaseException as exc:  # surfaced on the calling thread below
+                    errors.append(exc)
+
+            if threads == 1:
+                work()
+            else:
+                pool = [threading.Thread(target=work, daemon=True) for _ in range(threads)]
+                for t in pool:
+                    t.start()
+                for t in pool:
+                    t.join()
+            if errors:
+                raise errors[0]
+            stats["combined_calls"], stats["combined_evaluations"] = combiner.calls, combiner.evaluations
+        owner = np.zeros(count)
         for i, uid, emulator in done:
             fitted[i] = emulator.emulator.get_parameter_vector()
+            owner[i] = 1.0
             emulators[uid] = emulator
-        fitted = dist.all_gather_rows(fitted, mine, count)
+        stats["refits"] = len(done)
+        stats["device_evaluations"] = int(sum(getattr(e.emulator, "n_device_evaluations", 0) for _, _, e in done))
+        self.build_stats = stats
+        # every refit was done by exactly one rank, the others hold zeros: a sum collects them all
+        fitted = dist.all_reduce_sum(fitted)
+        if not np.all(dist.all_reduce_sum(owner) == 1.0):
+            raise RuntimeError("leave-one-out refits were not each done exactly once")
         self.cross_fit_parameters = fitted
         # refits done on other ranks: rebuild the GP at the gathered optimum (no optimisation)
         for i, uid in enumerate(self.leave_out_order):
@@ -123,7 +175,7 @@ class CrossCheck(object):
     def build_mocked_model_values_original_independent(self) -> ModelValues:
         self._require_built()
         out = {}
-        for uid in self.model_values.keys():
+        for uid in self.leave_out_order:
             independent = self.model_values[uid]["independent"]
             emulated, variance = self.cross_emulators[uid].predict_values(
                 independent=independent, model_parameters=self.model_parameters[uid]
@@ -134,7 +186,7 @@ class CrossCheck(object):
     def build_mocked_model_values(self, emulate_at: np.array) -> ModelValues:
         self._require_built()
         out = {}
-        for uid in self.model_values.keys():
+        for uid in self.leave_out_order:
             emulated, variance = self.cross_emulators[uid].predict_values(
                 independent=emulate_at, model_parameters=self.model_parameters[uid]
             )

@@ -39,6 +39,30 @@ def saltelli_design(model_specification: ModelSpecification, base_samples: int, 
     return np.vstack(blocks)
 
 
+def _sweep_predict_device(emulator, theta_rows, independent, want_var):
+    """The sweep with the results kept in HBM until they are gathered: this rank's parameter rows go to the device
+    once, the (theta x independent) query rows are formed there, mean and variance are written to device buffers,
+    all-gathered over NVLink (NCCL) and copied to the host once."""
+    import torch
+
+    n_theta, n_ind = len(theta_rows), len(independent)
+    world = dist.world_size()
+    per_rank = (n_theta + world - 1) // world
+    start, stop = dist.contiguous_slice(n_theta)
+    dev = torch.device("cuda", emulator.emulator.device)
+    with torch.cuda.device(dev):
+        theta_t = torch.from_numpy(np.ascontiguousarray(theta_rows[start:stop], dtype=np.float64)).to(dev)
+        ind_t = torch.from_numpy(np.ascontiguousarray(independent, dtype=np.float64)).to(dev)
+        mean_t = torch.zeros((per_rank, n_ind), dtype=torch.float64, device=dev)
+        var_t = torch.zeros((per_rank, n_ind), dtype=torch.float64, device=dev) if want_var else None
+        if stop > start:
+            emulator.predict_grid_device(theta_t, ind_t, mean_t[: stop - start], var_t[: stop - start] if want_var else None)
+        mean = dist.all_gather_concat_device(mean_t, n_theta)
+        if want_var:
+            return mean, dist.all_gather_concat_device(var_t, n_theta)
+        return mean
+
+
 def sweep_predict(emulator, theta_rows: np.ndarray, independent: np.ndarray, want_var: bool = True,
                   chunk_rows: int = 1 << 20):
     """
@@ -47,6 +71,8 @@ def sweep_predict(emulator, theta_rows: np.ndarray, independent: np.ndarray, wan
     all-gathered.
     """
     n_theta, n_ind = len(theta_rows), len(independent)
+    if getattr(emulator, "supports_device_grid", False) and dist.device_collectives():
+        return _sweep_predict_device(emulator, np.asarray(theta_rows), np.asarray(independent, dtype=np.float64), want_var)
     start, stop = dist.contiguous_slice(n_theta)
     mine = theta_rows[start:stop]
     mean = np.empty((len(mine), n_ind))

@@ -108,6 +108,12 @@ int eb200_gp_predict_device(eb200_gp* gp, int m, const double* t_dev, int want_v
 int eb200_gp_predict_grid_host(eb200_gp* gp, int n_theta, const double* theta_host, int n_ind, const double* ind_host,
                                int round_f32, int want_var, double* mu_host, double* var_host);
 
+/* The same with theta, ind and the results in device memory (enqueued on `stream`, no synchronisation): what a
+ * sharded sweep uses, whose per-rank results are all-gathered over NVLink from where they are
+ *  and copied to the host once. */
+int eb200_gp_predict_grid_device(eb200_gp* gp, long long n_theta, const double* theta_dev, int n_ind, const double* ind_dev,
+                                 int round_f32, int want_var, double* mu_dev, double* var_dev, void* stream);
+
 int eb200_gp_synchronize(eb200_gp* gp);
 
 /* Test / diagnostics hooks (not used by the product path).
@@ -138,6 +144,10 @@ int eb200_gp_value_tasks(const eb200_gp* gp);
  * ms_out[0] = parameter prep, [1] = dataflow factorisation (kernel-matrix build + Cholesky +
  * triangular inverse), [2] = alpha, [3] = K^-1 tiles + gradient traces, [4] = final reduction. */
 int eb200_gp_profile_stages(eb200_gp* gp, const double* p_host, int reps, float* ms_out);
+
+/* The same for one grouped LML+grad evaluation of nb equally shaped handles (eb200_gp_eval_multi_host's shared
+ * launches); ms_out as above, each figure covering the whole group. */
+int eb200_gp_profile_group_stages(eb200_gp** gps, int nb, const double* p_host, int p_stride, int reps, float* ms_out);
 
 /* Micro-benchmark of the dataflow kernel's 64x64 main loop in isolation: C[m][n] = A[m][k] * B[n][k]^T
  * (b_mcontig = 0) or A[m][k] * B[k][n] (b_mcontig = 1) with `grid` persistent CTAs. */

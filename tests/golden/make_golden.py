@@ -146,7 +146,79 @@ def golden_cross_check(name, n_par, sims, bins, seed):
     print(name, "mean squared =", total)
 
 
+class MinimizeRecorder:
+    """Stands in for `scipy.optimize.minimize` inside a reference module (they do `from scipy.optimize import minimize`):
+    the same call plus a callback that records the iterates x_k -- a callback does not change what BFGS does."""
+
+    def __init__(self):
+        self.results, self.iterates = [], []
+
+    def __call__(self, fun, x0, jac=None, **kwargs):
+        from scipy.optimize import minimize
+
+        its = [np.array(x0, dtype=np.float64)]
+        res = minimize(fun, x0, jac=jac, callback=lambda xk: its.append(np.array(xk, dtype=np.float64)), **kwargs)
+        self.results.append(res)
+        self.iterates.append(np.array(its))
+        return res
+
+
+def golden_trajectory(name, n_par, sims, bins, seed):
+    """The BFGS run of the reference's GaussianProcessEmulator.fit_model (gaussian_process.py:217-224), iterate by
+    iterate: what "identical hyperparameter optima for the same optimiser" is checked against on the device."""
+    import swiftemulator.emulators.gaussian_process as ref_module
+
+    spec, params, values = synthetic.make_model(n_par, sims, bins, seed=seed)
+    rspec, rparams, rvalues = to_reference(spec, params, values)
+    recorder = MinimizeRecorder()
+    keep = ref_module.minimize
+    ref_module.minimize = recorder
+    try:
+        emu = RefGPE()
+        emu.fit_model(rspec, rparams, rvalues)
+    finally:
+        ref_module.minimize = keep
+    res = recorder.results[0]
+    np.savez(
+        os.path.join(HERE, name + ".npz"), n_par=n_par, sims=sims, bins=bins, seed=seed, iterates=recorder.iterates[0],
+        nit=res.nit, nfev=res.nfev, njev=res.njev, status=res.status, fun=res.fun, p_fit=res.x,
+    )
+    print(name, "N =", len(emu.dependent_variables), "nit", res.nit, "nfev", res.nfev, "njev", res.njev, "status", res.status)
+
+
+def golden_bins_trajectories(name, n_par, sims, bins, seed):
+    """A binned emulator at BASELINE configuration C3's shape: 64 per-bin GPs of N = 256, d = 8."""
+    import swiftemulator.emulators.gaussian_process_bins as ref_module
+
+    spec, params, values = synthetic.make_model(n_par, sims, bins, seed=seed)
+    rspec, rparams, rvalues = to_reference(spec, params, values)
+    recorder = MinimizeRecorder()
+    keep = ref_module.minimize
+    ref_module.minimize = recorder
+    try:
+        emu = RefBins()
+        emu.fit_model(rspec, rparams, rvalues)
+    finally:
+        ref_module.minimize = keep
+    p_fit = np.array([gp.get_parameter_vector() for gp in emu.bin_gaussian_process])
+    theta = {nm: 0.41 + 0.05 * i for i, nm in enumerate(spec.parameter_names)}
+    centers = np.array(emu.bin_centers)
+    mu, var = emu.predict_values(centers, theta)
+    np.savez(
+        os.path.join(HERE, name + ".npz"), n_par=n_par, sims=sims, bins=bins, seed=seed, p_fit=p_fit, centers=centers,
+        theta=np.array([theta[nm] for nm in spec.parameter_names]), mu=mu, var=var,
+        nit=np.array([r.nit for r in recorder.results]), nfev=np.array([r.nfev for r in recorder.results]),
+        fun=np.array([r.fun for r in recorder.results]),
+    )
+    print(name, "bins =", len(centers), "nit", [r.nit for r in recorder.results][:8], "...")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":  # the vectors added in round 2 only
+        golden_trajectory("trajectory_c1", 2, 50, 20, seed=1235)       # BASELINE configuration C1: N = 1000, d = 3
+        golden_trajectory("trajectory_c2_shape", 8, 64, 16, seed=201)  # C2's shape at a quarter of its rows: N = 1024, d = 9
+        golden_bins_trajectories("bins_c3", 8, 256, 64, seed=1237)     # BASELINE configuration C3 in full
+        sys.exit(0)
     golden_gpe("gpe_small", 2, 12, 10, seed=101)
     golden_gpe("gpe_noerr", 2, 3, 10, seed=102, fixture=True)
     golden_gpe("gpe_linear_mean", 3, 20, 8, seed=103, mean_model=RefLinear())

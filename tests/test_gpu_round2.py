@@ -1,0 +1,448 @@
+"""
+Round-2 parity cases on the GPU (through the C ABI): BASELINE configurations that had no oracle check yet
+(C2-size prediction, a slice of the C5 grid, the full C3 binned emulator), trajectory-level "identical optima",
+grouped evaluations at full size, the device-pointer siblings, device-resident sweeps, combined leave-one-out
+refits, and the MCMC / multi-region emulators against the oracle-backed flow on the same inputs.
+
+Tolerances are those of tests/test_gpu_parity.py (1e-9; BASELINE.json north_star).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from emulator_b200 import synthetic
+from oracle import gp_oracle as orc
+from test_gpu_parity import device_problem, problem, relmax
+from test_host_logic import golden_inputs, load, theta_dict
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _record(name, payload):
+    """Keep the measured agreement next to the other GPU artefacts when the directory is there (gpurun)."""
+    out = os.path.join(ROOT, "gpurun_out", "r2")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, f"parity_{name}.json"), "w") as fh:
+            json.dump(payload, fh)
+    except OSError:
+        pass
+
+
+class RecordingMinimize:
+    """scipy.optimize.minimize plus a callback recording the iterates (tests/golden/make_golden.py does the same
+    around the reference's call)."""
+
+    def __init__(self):
+        self.results, self.iterates = [], []
+
+    def __call__(self, fun, x0, jac=None, **kwargs):
+        from scipy.optimize import minimize
+
+        its = [np.array(x0, dtype=np.float64)]
+        res = minimize(fun, x0, jac=jac, callback=lambda xk: its.append(np.array(xk, dtype=np.float64)), **kwargs)
+        self.results.append(res)
+        self.iterates.append(np.array(its))
+        return res
+
+
+# ---------------------------------------------------------------------------------------------------------
+# "identical hyperparameter optima for the same optimiser seed": iterate by iterate
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["trajectory_c1", "trajectory_c2_shape"])
+def test_bfgs_trajectory_matches_reference_golden(name, monkeypatch):
+    """The same scipy BFGS, driven by device values instead of the oracle's, must walk the same path as the
+    reference's fit_model did (golden: the reference's own code, iterates recorded).  Values agree to ~1e-12, so
+    the iterates agree far below the optimiser's own tolerance until the run ends; a run that ends on "precision
+    loss" (status 2, which the reference ignores) does so inside a line search whose last function differences are
+    at rounding level, so there the step count may differ by a step or two and the end point at 1e-3."""
+    import emulator_b200.emulators.base as base
+    from emulator_b200.emulators import GaussianProcessEmulator
+
+    g = load(name)
+    spec, params, values = golden_inputs(g)
+    recorder = RecordingMinimize()
+    monkeypatch.setattr(base, "minimize", recorder)
+    emu = GaussianProcessEmulator()
+    emu.fit_model(spec, params, values)
+    res, its = recorder.results[0], recorder.iterates[0]
+    ref_its = g["iterates"]
+    ref_nit, ref_nfev, status = int(g["nit"]), int(g["nfev"]), int(g["status"])
+    common = min(len(its), len(ref_its))
+    step_diff = np.max(np.abs(its[:common] - ref_its[:common]), axis=1)
+    _record(name, {"nit": int(res.nit), "ref_nit": ref_nit, "nfev": int(res.nfev), "ref_nfev": ref_nfev, "status": int(res.status),
+                   "ref_status": status, "iterate_diff": step_diff.tolist(), "end_diff": float(np.max(np.abs(res.x - g["p_fit"])))})
+    if status == 0:  # converged on the gradient tolerance: everything must coincide
+        assert res.status == 0 and res.nit == ref_nit and res.nfev == ref_nfev
+        assert np.max(step_diff) <= 1e-6
+        assert np.max(np.abs(res.x - g["p_fit"])) <= 1e-6
+    else:
+        # every iterate before the terminating line search
+        settled = max(1, min(res.nit, ref_nit) - 1)
+        assert np.max(step_diff[: settled + 1]) <= 1e-6, step_diff
+        assert abs(res.nit - ref_nit) <= 2
+        assert np.allclose(res.x, g["p_fit"], rtol=1e-3, atol=1e-3)
+    # and the likelihood reached is the reference's
+    assert abs(res.fun - float(g["fun"])) <= 1e-7 * abs(float(g["fun"]))
+
+
+def test_bins_emulator_at_c3_size_matches_reference_golden():
+    """BASELINE configuration C3 in full: 64 per-bin GPs (N = 256, d = 8), fitted and predicted."""
+    from emulator_b200.emulators import GaussianProcessEmulatorBins
+
+    g = load("bins_c3")
+    spec, params, values = golden_inputs(g)
+    emu = GaussianProcessEmulatorBins()
+    emu.fit_model(spec, params, values)
+    assert emu.bin_fit_parameters.shape == g["p_fit"].shape == (64, 9)
+    # optima at the optimiser's resolution (see the trajectory test), likelihood values reached equal
+    worst = float(np.max(np.abs(emu.bin_fit_parameters - g["p_fit"])))
+    funs = []
+    for gp, p, yb in zip(emu.bin_gaussian_process, emu.bin_fit_parameters, emu.bin_model_values):
+        funs.append(-gp.log_likelihood(yb["dependent"]))
+    funs = np.array(funs)
+    _record("bins_c3", {"max_abs_p_diff": worst, "max_rel_fun_diff": float(np.max(np.abs(funs - g["fun"]) / np.abs(g["fun"])))})
+    assert np.max(np.abs(funs - g["fun"]) / np.abs(g["fun"])) <= 1e-6
+    assert worst <= 2e-2  # (flat valleys: the trajectory test above is the sharp statement)
+    # predictions at the golden optima: identical parameters, 1e-9
+    for gp, p in zip(emu.bin_gaussian_process, g["p_fit"]):
+        gp.set_parameter_vector(p)
+    mu, var = emu.predict_values(g["centers"], theta_dict(spec, g))
+    assert np.max(np.abs(mu - g["mu"])) <= TOL * np.max(np.abs(g["mu"]))
+    assert np.max(np.abs(var - g["var"])) <= TOL * np.max(8 * np.exp(g["p_fit"][:, 0]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# prediction at full size
+# ---------------------------------------------------------------------------------------------------------
+def test_prediction_at_c2_size_and_c5_grid_slice_match_oracle():
+    """N = 4096, d = 9: 4096 query rows, and a 2^10-theta x 32 slice of the C5 grid (32768 rows: the large-chunk
+    path), mean and variance against the oracle at 1e-9 of max|mu| and of amp."""
+    n, d = 4096, 9
+    x, y, diag = problem(n, d, seed=1235)
+    gp = device_problem(x, diag, y)
+    p = synthetic.perturbed_parameter_vectors(d, 1)[1]
+    gp.evaluate(p, False)
+    amp = orc.amplitude(p, d)
+    rng = np.random.default_rng(3)
+    t = rng.random((4096, d)).astype(np.float32).astype(np.float64)
+    t[:64] = x[rng.integers(n, size=64)]  # training rows: variance near the noise level
+    mu, var = gp.predict(t, True)
+    ref_mu, ref_var = orc.predict(p, x, diag, y, t)
+    assert relmax(mu, ref_mu) <= TOL
+    assert np.max(np.abs(var - ref_var)) <= TOL * amp
+    # C5 slice: Saltelli-style parameter rows x linspace(0, 1, 32)
+    spec, _, _ = synthetic.make_config("C2")
+    from emulator_b200.sensitivity.sobol import saltelli_design
+
+    theta = saltelli_design(spec, 128, seed=11)[: 1 << 10]
+    ind = np.linspace(0.0, 1.0, 32)
+    gmu, gvar = gp.predict_grid(theta, ind, want_var=True)
+    rows = np.empty((len(theta) * 32, d), dtype=np.float32)
+    rows[:, 0] = np.tile(ind, len(theta))
+    rows[:, 1:] = np.repeat(theta, 32, axis=0)
+    rows = rows.astype(np.float64)
+    ref_mu, ref_var = orc.predict(p, x, diag, y, rows)
+    assert relmax(gmu.ravel(), ref_mu) <= TOL
+    assert np.max(np.abs(gvar.ravel() - ref_var)) <= TOL * amp
+    # the large-chunk path computes every tile as the row-by-row path does
+    mu_rows, var_rows = gp.predict(rows[:3000], True)
+    assert np.array_equal(mu_rows, gmu.ravel()[:3000]) and np.array_equal(var_rows, gvar.ravel()[:3000])
+    _record("predict_c2", {"mean_rel": float(relmax(gmu.ravel(), ref_mu)), "var_rel_amp": float(np.max(np.abs(gvar.ravel() - ref_var)) / amp)})
+    gp.close()
+
+
+def test_grid_prediction_in_device_memory_equals_host_path():
+    import torch
+
+    n, d = 700, 5
+    x, y, diag = problem(n, d, seed=5)
+    gp = device_problem(x, diag, y)
+    p = orc.default_parameter_vector(d) + 0.1
+    gp.evaluate(p, False)
+    theta = np.random.default_rng(1).random((300, d - 1))
+    ind = np.linspace(0.0, 1.0, 7)
+    mu, var = gp.predict_grid(theta, ind, want_var=True)
+    dev = torch.device("cuda", 0)
+    theta_t, ind_t = torch.from_numpy(theta).to(dev), torch.from_numpy(ind).to(dev)
+    mu_t = torch.zeros((300, 7), dtype=torch.float64, device=dev)
+    var_t = torch.zeros_like(mu_t)
+    stream = torch.cuda.current_stream(dev)
+    gp.predict_grid_device(300, theta_t.data_ptr(), 7, ind_t.data_ptr(), True, mu_t.data_ptr(), var_t.data_ptr(), stream=stream.cuda_stream)
+    stream.synchronize()
+    assert np.array_equal(mu_t.cpu().numpy(), mu) and np.array_equal(var_t.cpu().numpy(), var)
+    gp.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# grouped evaluations
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,nb", [(4096, 5), (8176, 2)])
+def test_multi_handle_evaluation_equals_single_evaluations_at_full_size(n, nb):
+    """C2 size: groups of four share launches (five handles: one group plus a stand-alone evaluation); C4 size: a
+    factorisation of 128 tile rows keeps the device busy alone, the handles' own graphs are used.  Bit-identical."""
+    import torch
+
+    from emulator_b200.device import evaluate_many, evaluate_many_device
+
+    d = 9
+    probs, ps, singles = [], [], []
+    for k in range(nb):
+        x, y, diag = problem(n, d, seed=1235 + k)
+        gp = device_problem(x, diag, y)
+        p = synthetic.perturbed_parameter_vectors(d, 8)[1 + k]
+        probs.append(gp); ps.append(p)
+        singles.append(gp.evaluate(p, True))
+    ps = np.array(ps)
+    for rep in range(2):
+        lml, grad, info = evaluate_many(probs, ps, want_grad=True)
+        assert np.all(info == 0)
+        for k in range(nb):
+            assert lml[k] == singles[k][0] and np.array_equal(grad[k], singles[k][1])
+    # the device-pointer sibling
+    dev = torch.device("cuda", 0)
+    p_t = torch.from_numpy(ps).to(dev)
+    out_t = torch.zeros((nb, d + 5), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    evaluate_many_device(probs, p_t.data_ptr(), d + 1, True, out_t.data_ptr(), d + 5, stream.cuda_stream)
+    stream.synchronize()
+    out = out_t.cpu().numpy()
+    assert np.array_equal(out[:, 0], lml) and np.array_equal(out[:, 1 : d + 2], grad) and np.all(out[:, d + 2] == 0)
+    # prediction state of a grouped evaluation
+    t = problem(n, d, seed=1235)[0][:8] + 0.01
+    mu, var = probs[1].predict(t, True)
+    xk, yk, dk = problem(n, d, seed=1236)
+    if n <= 4096:
+        ref_mu, ref_var = orc.predict(ps[1], xk, dk, yk, t)
+        assert relmax(mu, ref_mu) <= TOL and np.max(np.abs(var - ref_var)) <= TOL * orc.amplitude(ps[1], d)
+    for gp in probs:
+        gp.close()
+
+
+def test_duplicate_handles_are_rejected():
+    from emulator_b200.device import evaluate_many
+
+    x, y, diag = problem(1000, 3, seed=2)
+    gp = device_problem(x, diag, y)
+    other = device_problem(x, diag, y)
+    ps = np.tile(orc.default_parameter_vector(3), (3, 1))
+    with pytest.raises(ValueError):
+        evaluate_many([gp, other, gp], ps)
+    # and below the Python guard, in the C ABI itself
+    import ctypes
+
+    from emulator_b200 import _lib
+
+    lib = _lib.load()
+    handles = (ctypes.c_void_p * 3)(gp._h, other._h, gp._h)
+    out = np.zeros((3, 8))
+    assert lib.eb200_gp_eval_multi_host(handles, 3, _lib.as_double_ptr(ps), 4, 1, _lib.as_double_ptr(out), 8) != 0
+    assert "twice" in _lib.last_error()
+    gp.close(); other.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# failed factorisations through the george-shaped object
+# ---------------------------------------------------------------------------------------------------------
+def test_failed_factorisation_is_reported_every_time_and_never_predicted_from():
+    """george raises (or returns -inf / zeros when quiet) on EVERY call at parameters whose matrix is not positive
+    definite; nothing of the aborted factorisation may be served from a cache.  The error surfaces at the first
+    likelihood / predict call, not in compute() (documented deviation: the factorisation is deferred)."""
+    from emulator_b200 import george_compat as george
+
+    x = np.zeros((40, 2))
+    x[:, 0] = np.repeat(np.arange(20), 2) * 0.05  # duplicated rows, no noise: K is exactly singular
+    y = np.ones(40)
+    kernel = 1**2 * george.kernels.ExpSquaredKernel(np.ones(2), ndim=2)
+    gp = george.GP(kernel)
+    gp.compute(x, 0.0)  # does not raise: deferred
+    # (george's white-noise jitter of 1.25e-12 is far below one rounding unit of an amplitude of 2e13: the pivots of
+    #  the twenty duplicated rows cancel to rounding noise, and at least one of them is not positive)
+    bad = np.array([30.0, 3.0, 3.0])
+    gp.set_parameter_vector(bad)
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.log_likelihood(y)
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.log_likelihood(y)  # again: not served from a cache
+    assert gp.log_likelihood(y, quiet=True) == -np.inf
+    assert np.array_equal(gp.grad_log_likelihood(y, quiet=True), np.zeros(3))
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.grad_log_likelihood(y)
+    assert gp.nll(bad, y) == np.inf
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.predict(y, x[:3], return_cov=False, return_var=True)
+    # the C ABI refuses to predict from the aborted factorisation as well
+    with pytest.raises(RuntimeError):
+        gp._problem.predict(x[:3], True)
+    # and the object recovers at parameters where the matrix is fine
+    gp.compute(x, 0.1)
+    gp.set_parameter_vector(orc.default_parameter_vector(2))
+    ref = orc.lml_and_grad(orc.default_parameter_vector(2), x, orc.noise_diagonal(np.full(40, 0.1)), y)[0]
+    assert abs(gp.log_likelihood(y) - ref) <= TOL * abs(ref)
+    gp.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# leave-one-out refits with combined evaluations
+# ---------------------------------------------------------------------------------------------------------
+def test_cross_check_with_combined_evaluations_equals_sequential_refits():
+    """Four scipy BFGS runs at a time whose likelihood evaluations share launches (emulator_b200/combine.py): the
+    optima are those of one refit after the other, bit for bit; restricted to a subset of the simulations."""
+    from emulator_b200.sensitivity import CrossCheck
+
+    spec, params, values = synthetic.make_model(2, 60, 16, seed=41)  # refits of N = 944: 15 tile rows, grouped
+    uids = list(values.model_values.keys())[:8]
+    together = CrossCheck(workers=4, leave_out=uids)
+    together.build_emulators(spec, params, values)
+    alone = CrossCheck(workers=1, leave_out=uids)
+    alone.build_emulators(spec, params, values)
+    assert together.leave_out_order == uids and list(together.cross_emulators.keys()) == uids
+    assert np.array_equal(together.cross_fit_parameters, alone.cross_fit_parameters)
+    stats = together.build_stats
+    assert stats["refits"] == 8 and stats["combined_evaluations"] == stats["device_evaluations"]
+    assert stats["combined_calls"] < stats["combined_evaluations"]  # launches really were shared
+    assert alone.build_stats["combined_calls"] == alone.build_stats["combined_evaluations"]
+    a, _ = together.get_mean_squared()
+    b, _ = alone.get_mean_squared()
+    assert a == b
+    mocked = together.build_mocked_model_values_original_independent()
+    assert list(mocked.model_values.keys()) == uids
+    for cc in (together, alone):
+        for e in cc.cross_emulators.values():
+            e.emulator.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# MCMC and multi-region emulators against the oracle-backed flow
+# ---------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def oracle_gp(monkeypatch):
+    """Context: george_compat.GP replaced by the oracle-backed GP (the checker), restored afterwards."""
+    import oracle_george
+    import emulator_b200.george_compat as gc
+
+    class Switch:
+        def __enter__(self_inner):
+            self_inner.keep = gc.GP
+            gc.GP = oracle_george.OracleBackedGP
+            return self_inner
+
+        def __exit__(self_inner, *exc):
+            gc.GP = self_inner.keep
+            return False
+
+    return Switch
+
+
+def test_ensemble_chain_on_device_values_equals_chain_on_oracle_values(oracle_gp):
+    """The sampler is deterministic given the likelihood values: with the same seed and start, the chain driven by
+    device values (batched value-only evaluations) must make the same accept/reject decisions as the chain driven
+    by the oracle, i.e. identical positions, with log-probabilities equal to 1e-9."""
+    import oracle_george
+    from emulator_b200 import george_compat as george
+    from emulator_b200.emulators.ensemble import EnsembleSampler
+
+    n, d = 400, 3
+    x, y, yerr = synthetic.design_arrays(n, d, seed=9)
+    kernel = 1**2 * george.kernels.ExpSquaredKernel(np.ones(d), ndim=d)
+    dev_gp = george.GP(kernel)
+    dev_gp.compute(x, yerr)
+    ref_gp = oracle_george.OracleBackedGP(1**2 * george.kernels.ExpSquaredKernel(np.ones(d), ndim=d))
+    ref_gp.compute(x, yerr)
+    start = orc.default_parameter_vector(d) + np.array([1.0, 0.5, -0.5, 0.3])
+    walkers, steps = 12, 12
+    chains = []
+    for gp in (dev_gp, ref_gp):
+        rng = np.random.default_rng(17)
+        sampler = EnsembleSampler(walkers, d + 1, lambda pos, gp=gp: gp.log_likelihood_batch(y, pos, quiet=True), seed=rng, vectorize=True)
+        p0 = start + 1e-2 * rng.standard_normal((walkers, d + 1))
+        sampler.run_mcmc(p0, steps)
+        chains.append((sampler.get_chain(), sampler.get_log_prob(), sampler.naccepted.copy()))
+    (c_dev, lp_dev, acc_dev), (c_ref, lp_ref, acc_ref) = chains
+    assert np.array_equal(acc_dev, acc_ref) and acc_dev.sum() > 0
+    assert np.array_equal(c_dev, c_ref)  # positions depend on the values only through the decisions
+    assert np.max(np.abs(lp_dev - lp_ref) / np.abs(lp_ref)) <= TOL
+    dev_gp.close()
+
+
+def test_mcmc_emulator_matches_oracle_backed_run(oracle_gp):
+    from emulator_b200.emulators import GaussianProcessEmulatorMCMC
+
+    spec, params, values = synthetic.make_model(2, 12, 10, seed=101)
+    kwargs = dict(burn_in_steps=6, mcmc_steps=10, walkers=10, seed=3, use_hyperparameter_error=True, samples_for_error=20)
+    emu = GaussianProcessEmulatorMCMC(**kwargs)
+    emu.fit_model(spec, params, values)
+    with oracle_gp():
+        ref = GaussianProcessEmulatorMCMC(**kwargs)
+        ref.fit_model(spec, params, values)
+    # the chains start from BFGS optima that agree at the optimiser's resolution; from there the same decisions
+    assert emu.hyperparameter_samples.shape == ref.hyperparameter_samples.shape == (100, 4)
+    assert np.allclose(emu.hyperparameter_best_fit, ref.hyperparameter_best_fit, rtol=1e-3, atol=1e-3)
+    assert np.allclose(emu.hyperparameter_samples, ref.hyperparameter_samples, rtol=2e-3, atol=2e-3)
+    # predictions at identical hyperparameters, including the hyperparameter-error term (batched on the device)
+    theta = {"p0": 0.42, "p1": 0.61}
+    q = np.linspace(0.05, 0.95, 9)
+    for e in (emu, ref):
+        e.hyperparameter_samples = ref.hyperparameter_samples
+        e.hyperparameter_best_fit = ref.hyperparameter_best_fit
+        e.emulator.set_parameter_vector(ref.hyperparameter_best_fit)
+        e._rng = np.random.default_rng(5)
+    mu, var = emu.predict_values(q, theta)
+    with oracle_gp():
+        ref_mu, ref_var = ref.predict_values(q, theta)
+    amp = 3 * np.exp(ref.hyperparameter_best_fit[0])
+    assert np.max(np.abs(mu - ref_mu)) <= TOL * np.max(np.abs(ref_mu))
+    assert np.max(np.abs(var - ref_var)) <= 1e-8 * max(amp, np.max(ref_var))
+    assert np.array_equal(emu.predict_values_no_error(q, theta), mu)
+
+
+def test_multiple_emulator_matches_oracle_backed_run(oracle_gp):
+    """Region fits and the blend across the overlap, device against the oracle-backed run of the same code
+    (multi_gaussian_process.py:167-177, :241-331)."""
+    from emulator_b200.emulators import MultipleGaussianProcessEmulator
+
+    spec, params, values = synthetic.make_model(2, 14, 12, seed=77)
+    regions = [[None, 0.6], [0.4, None]]
+    emu = MultipleGaussianProcessEmulator(independent_regions=regions)
+    emu.fit_model(spec, params, values)
+    with oracle_gp():
+        ref = MultipleGaussianProcessEmulator(independent_regions=regions)
+        ref.fit_model(spec, params, values)
+    theta = {"p0": 0.37, "p1": 0.58}
+    q = np.linspace(0.0, 1.0, 23)  # both pure regions and the overlap
+    for dev_e, ref_e in zip(emu.emulators, ref.emulators):
+        assert np.allclose(dev_e.emulator.get_parameter_vector(), ref_e.emulator.get_parameter_vector(), rtol=2e-3, atol=2e-3)
+        dev_e.emulator.set_parameter_vector(ref_e.emulator.get_parameter_vector())  # compare the blend at identical parameters
+    mu, var = emu.predict_values(q, theta)
+    ref_mu, ref_var = ref.predict_values(q, theta)
+    amp = max(3 * np.exp(e.emulator.get_parameter_vector()[0]) for e in ref.emulators)
+    assert np.max(np.abs(mu - ref_mu)) <= TOL * np.max(np.abs(ref_mu))
+    assert np.max(np.abs(var - ref_var)) <= TOL * amp
+    assert np.array_equal(emu.predict_values_no_error(q, theta), mu)
+
+
+def test_sobol_indices_on_device_match_oracle_backed_indices(oracle_gp):
+    from emulator_b200.emulators import GaussianProcessEmulator
+    from emulator_b200.sensitivity import sobol_indices
+
+    spec, params, values = synthetic.make_model(3, 40, 8, seed=55)
+    emu = GaussianProcessEmulator()
+    emu.fit_model(spec, params, values)
+    with oracle_gp():
+        ref = GaussianProcessEmulator()
+        ref._build_arrays(spec, params, values)
+        from emulator_b200.emulators.base import build_gp, default_kernel
+
+        ref.kernel = default_kernel(4)
+        ref.emulator = build_gp(ref.kernel, None, ref.independent_variables, ref.dependent_variables, ref.dependent_variable_errors)
+        ref.emulator.set_parameter_vector(emu.emulator.get_parameter_vector())
+        ind = np.linspace(0.1, 0.9, 5)
+        ref_idx = sobol_indices(ref, spec, ind, base_samples=256, seed=11)
+    idx = sobol_indices(emu, spec, ind, base_samples=256, seed=11)
+    assert np.max(np.abs(idx["S1"] - ref_idx["S1"])) <= 1e-7
+    assert np.max(np.abs(idx["ST"] - ref_idx["ST"])) <= 1e-7
