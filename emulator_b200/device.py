@@ -145,6 +145,9 @@ class DeviceProblem:
         return (mu, var) if want_var else mu
 
     # -- device-pointer variants (inputs already in HBM; asynchronous) ----------------------------
+    # `stream` is a cudaStream_t handle as an integer.  0 selects the HANDLE'S OWN stream (not the legacy default
+    # stream, whose handle is also 0 -- torch.cuda.default_stream().cuda_stream == 0): pass a stream created with
+    # torch.cuda.Stream(), or 1 (cudaStreamLegacy) to name the legacy default stream explicitly.
     def evaluate_device(self, p_ptr: int, want_grad: bool, result_ptr: int, stream: int = 0, value_only: bool = False):
         _lib.check(
             self._lib.eb200_gp_eval_device(self._h, c_void_p(p_ptr), _mode(want_grad, value_only), c_void_p(result_ptr), c_void_p(stream)),

@@ -55,6 +55,78 @@ def optimise_gp(gp, y):
     return result
 
 
+def optimise_gp_with_restarts(gp, kernel, mean_model, x, y, yerr, restarts: int, seed: int = 0, spread: float = 1.0,
+                              workers: int = 4):
+    """
+    Optimiser restarts (an extension: the reference runs BFGS once, from the kernel's initial vector,
+    gaussian_process.py:217-221; SURVEY.md section 8e lists restarts among the independent units that shard).
+    Start 0 is that initial vector -- so `restarts=0` IS the reference's fit -- and starts 1..restarts are drawn
+    N(x0, spread^2) from `seed`.  The starts are independent problems: handed out over ranks and host threads
+    (dist.WorkClaimer), each with scipy's BFGS on its own GP over the same data, their likelihood evaluations
+    combined into shared launches (emulator_b200/combine.py).  Every rank ends with `gp` at the best optimum found
+    (lowest negative log-likelihood; ties go to the lowest start index).  Returns that start's OptimizeResult on the
+    rank that ran it and a stub carrying x and fun elsewhere.
+    """
+    import threading
+
+    from scipy.optimize import OptimizeResult
+
+    from .. import dist
+    from ..combine import EvaluationCombiner
+
+    x0 = np.array(gp.get_parameter_vector(), dtype=np.float64)
+    rng = np.random.default_rng(seed)
+    starts = np.vstack([x0, x0 + spread * rng.standard_normal((restarts, len(x0)))])
+    count = len(starts)
+    claimer = dist.WorkClaimer(count)
+    threads = max(1, min(workers, count)) if mean_model is None else 1  # a mean model object is shared state
+    combiner = EvaluationCombiner(threads)
+    results, errors = {}, []
+
+    def work():
+        try:
+            with combiner:
+                while True:
+                    i = claimer.next()
+                    if i is None:
+                        break
+                    if i == 0:
+                        own = gp
+                    else:
+                        own = build_gp(kernel, mean_model, x, y, yerr, device=getattr(gp, "device", None))
+                    own.set_parameter_vector(starts[i])
+                    try:
+                        results[i] = optimise_gp(own, y)
+                    except np.linalg.LinAlgError:  # a start whose matrix cannot be factorised simply loses
+                        results[i] = OptimizeResult(x=starts[i], fun=np.inf, success=False, status=-1, nit=0, nfev=0)
+                    if own is not gp:
+                        own.close()
+        except BaseException as exc:
+            errors.append(exc)
+
+    if threads == 1:
+        work()
+    else:
+        pool = [threading.Thread(target=work, daemon=True) for _ in range(threads)]
+        for t in pool:
+            t.start()
+        for t in pool:
+            t.join()
+    if errors:
+        raise errors[0]
+    table = np.zeros((count, len(x0) + 1))
+    for i, res in results.items():
+        table[i, 0] = res.fun if np.isfinite(res.fun) else 1e300
+        table[i, 1:] = res.x
+    table = dist.all_reduce_sum(table)  # every start was run by exactly one rank
+    best = int(np.argmin(table[:, 0]))
+    gp.set_parameter_vector(table[best, 1:])
+    chosen = results.get(best, OptimizeResult(x=table[best, 1:].copy(), fun=float(table[best, 0]), success=None, status=None))
+    chosen.restart_index = best
+    chosen.restart_funs = table[:, 0].copy()
+    return chosen
+
+
 def optimise_gps_lockstep(gps, ys):
     """
     The same optimisation for many equally shaped GPs at once (per-bin emulators): all problems advance

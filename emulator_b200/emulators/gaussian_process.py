@@ -11,7 +11,9 @@ from typing import Dict, Optional
 import attr
 import numpy as np
 
-from .base import BaseEmulator, build_gp, default_kernel, flatten_model_values, optimise_gp, query_matrix
+from .base import (
+    BaseEmulator, build_gp, default_kernel, flatten_model_values, optimise_gp, optimise_gp_with_restarts, query_matrix,
+)
 
 
 @attr.s
@@ -19,6 +21,10 @@ class GaussianProcessEmulator(BaseEmulator):
     kernel = attr.ib(default=None)
     mean_model = attr.ib(default=None)
     device: Optional[int] = attr.ib(default=None)  # None: this rank's GPU under torchrun, else GPU 0 (dist.resolve_device)
+    #: extra BFGS runs from starts drawn around the initial vector, the best optimum wins (extension; 0 = the
+    #: reference's single run).  Under torchrun the starts are shared out over the ranks.
+    restarts: int = attr.ib(default=0)
+    restart_seed: int = attr.ib(default=0)
 
     def _build_arrays(self, model_specification, model_parameters, model_values):
         self.model_specification = model_specification
@@ -41,7 +47,13 @@ class GaussianProcessEmulator(BaseEmulator):
             self.kernel, self.mean_model, self.independent_variables, self.dependent_variables,
             self.dependent_variable_errors, device=self.device,
         )
-        self.fit_result = optimise_gp(gp, self.dependent_variables)
+        if self.restarts > 0:
+            self.fit_result = optimise_gp_with_restarts(
+                gp, self.kernel, self.mean_model, self.independent_variables, self.dependent_variables,
+                self.dependent_variable_errors, self.restarts, seed=self.restart_seed,
+            )
+        else:
+            self.fit_result = optimise_gp(gp, self.dependent_variables)
         self.emulator = gp
 
     def _require_trained(self):

@@ -446,8 +446,8 @@ class GP:
     def predict_grid_device(self, y, theta_t, independent_t, mean_out, var_out=None, round_f32=True):
         """
         `predict_grid` with everything in device memory: `theta_t` [n_theta, ndim-1], `independent_t` [n_ind] and
-        the outputs `mean_out` / `var_out` [n_theta, n_ind] are CUDA float64 tensors on this GP's device; the work
-        is enqueued on torch's current stream and nothing is copied to the host (sharded sweeps all-gather the
+        the outputs `mean_out` / `var_out` [n_theta, n_ind] are CUDA float64 tensors on this GP's device; the call
+        returns when the results are complete in device memory and nothing is copied to the host (sharded sweeps all-gather the
         results from where they are, emulator_b200/dist.py).  Zero-mean GPs only (a mean model is a host callable).
         """
         import torch
@@ -463,12 +463,15 @@ class GP:
             raise ValueError("Dimension mismatch")
         with self._using_device():
             self._evaluate(want_grad=False, need_state=True)
-            stream = torch.cuda.current_stream(theta_t.device).cuda_stream
+            # inputs written on torch's current stream must be complete; the work then runs on the handle's own stream
+            # (a stream argument of 0 means exactly that in the C ABI -- torch's default stream also has handle 0, so
+            # it cannot be named there) and is complete when this returns: the handle may be released once unpinned
+            torch.cuda.current_stream(theta_t.device).synchronize()
             self._problem.predict_grid_device(
                 n_theta, theta_t.data_ptr(), n_ind, independent_t.data_ptr(), var_out is not None, mean_out.data_ptr(),
-                var_out.data_ptr() if var_out is not None else 0, stream=stream, round_f32=round_f32,
+                var_out.data_ptr() if var_out is not None else 0, stream=0, round_f32=round_f32,
             )
-            torch.cuda.current_stream(theta_t.device).synchronize()  # the handle may be released once unpinned
+            self._problem.synchronize()
 
     # ---- lifetime ---------------------------------------------------------------------------------
     def close(self):

