@@ -53,6 +53,7 @@ class _Residency:
     def __init__(self):
         self.lock = threading.RLock()
         self.lru = collections.OrderedDict()  # id(gp) -> weakref
+        self.releases = 0  # handles released to make room (diagnostics)
 
     @staticmethod
     def needed_bytes(n: int) -> int:
@@ -88,6 +89,7 @@ class _Residency:
                 if other is keep or other.device != device or other._pins > 0 or other._problem is None:
                     continue
                 other._release_locked()
+                self.releases += 1
                 if self.free_bytes(device) >= need + self.RESERVE:
                     return
             # nothing (more) to release: let a request that cannot possibly fit fail here, clearly, instead of
