@@ -14,7 +14,8 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_void_p
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libemulator_b200.so")
+# (EB200_LIB: another build of the same library, e.g. a development variant, for A/B measurements)
+LIB_PATH = os.environ.get("EB200_LIB") or os.path.join(_HERE, "libemulator_b200.so")
 
 MAX_DIM = 16
 

@@ -11,6 +11,7 @@
 #include "../../include/emulator_b200.h"
 #include "kernels.cuh"
 #include "factor_dataflow.cuh"
+#include "tma_gemm.cuh"
 
 using namespace eb;
 
@@ -144,8 +145,8 @@ struct eb200_gp {
   double *h_pred = nullptr;  // pinned staging for predict (np * (d + 2) doubles)
   char *arena = nullptr, *pinned = nullptr;  // one device / one pinned allocation behind the small arrays above
   // grow-only device buffers of the grid prediction (parameter rows, independent values, results)
-  double *grid_theta = nullptr, *grid_ind = nullptr, *grid_mu = nullptr, *grid_var = nullptr;
-  size_t grid_theta_cap = 0, grid_ind_cap = 0, grid_out_cap = 0;
+  double *grid_theta = nullptr, *grid_ind = nullptr, *grid_mu = nullptr, *grid_var = nullptr, *grid_e1 = nullptr;
+  size_t grid_theta_cap = 0, grid_ind_cap = 0, grid_out_cap = 0, grid_e1_cap = 0;
   TileTask* var_tasks = nullptr;
   int var_tasks_mt = -1, var_tasks_cnt = 0;
   // Grow-only scratch of predictions with more query rows than training rows (sweeps): K* rows, padded query
@@ -155,7 +156,14 @@ struct eb200_gp {
     double *ks = nullptr, *T = nullptr, *rowss = nullptr;
     TileTask* tasks = nullptr;
     int rows = 0, tasks_mt = -1, tasks_cnt = 0;
+    CUtensorMap map_ks;  // TMA view of ks (valid when ks != nullptr)
   } big;
+  // TMA views (tma_gemm.cuh, 128-row boxes): of Y = L^-T in matrix W (K^-1 tiles) and of X = L^-1 in matrix A
+  // (predictive variance; X is transposed into A, where L is dead by then, before the first variance prediction
+  // that follows an evaluation: x_in_a)
+  CUtensorMap map_y, map_x;
+  bool x_in_a = false;
+  double* xdiag = nullptr;  // [nt][64][64] diagonal tiles X_jj = L_jj^-1 (what the tile finalisations multiply with)
 };
 
 namespace {
@@ -185,17 +193,17 @@ void build_program(eb200_gp* h, std::vector<TileTask>& tasks) {
     op.kind = OP_FACTOR_DF;
     ops.push_back(op);
   }
-  // ---- z = X r, alpha = X^T z ----
+  // ---- z = X r = Y^T r, alpha = X^T z = Y z  (the inverse is kept transposed: Y = L^-T) ----
   {
     Op op;
     op.stage = 3;
-    op.kind = OP_TRMV;
-    ops.push_back(op);
     op.kind = OP_TRMV_T;
+    ops.push_back(op);
+    op.kind = OP_TRMV;
     ops.push_back(op);
   }
   // ---- K^-1 tiles + gradient traces ----
-  // Tile (I, J) contracts over k >= I*128.  A contraction can be cut into K-slices (the trace is
+  // Tile (I, J) = sum_k Y[i][k] Y[j][k] contracts over k >= I*128.  A contraction can be cut into K-slices (the trace is
   // linear in K^-1; exactly one slice per tile carries the alpha alpha^T term).  The unsplit list also
   // serves the diagnostics path that stores K^-1.
   {
@@ -222,7 +230,7 @@ void build_program(eb200_gp* h, std::vector<TileTask>& tasks) {
           // slice boundaries in pairs of chunks (total is a multiple of 8)
           const int c0 = 2 * (int)((long long)(total / 2) * sidx / nslice), c1 = 2 * (int)((long long)(total / 2) * (sidx + 1) / nslice);
           const int k0 = I * 128 + c0 * KC;
-          tasks.push_back({I * 128, J * 128, k0, I * 128, k0, J * 128, c1 - c0, (I == J ? 1 : 0) | (sidx == 0 ? 2 : 0)});
+          tasks.push_back({I * 128, J * 128, I * 128, k0, J * 128, k0, c1 - c0, (I == J ? 1 : 0) | (sidx == 0 ? 2 : 0)});
         }
       }
     sort_tasks(tasks, off);
@@ -238,7 +246,7 @@ void build_program(eb200_gp* h, std::vector<TileTask>& tasks) {
     off = tasks.size();
     for (int J = 0; J < nT; ++J)
       for (int I = J; I < nT; ++I)
-        tasks.push_back({I * 128, J * 128, I * 128, I * 128, I * 128, J * 128, (np - I * 128) / KC, (I == J ? 1 : 0) | 2});
+        tasks.push_back({I * 128, J * 128, I * 128, I * 128, J * 128, I * 128, (np - I * 128) / KC, (I == J ? 1 : 0) | 2});
     h->lauum_full_off = (int)off;
     h->lauum_full_cnt = (int)(tasks.size() - off);
   }
@@ -255,7 +263,7 @@ void fill_factor_args(eb200_gp* h, bool vo, FactorArgs& fa) {
   const int np = h->np;
   const size_t nf = (size_t)(h->nt + 1) * h->nt;
   fa.A = h->A; fa.W = h->W; fa.ld = np; fa.nt = h->nt; fa.n = h->n; fa.X = h->X; fa.noise = h->noise; fa.kp = h->kp;
-  fa.Xd = h->W; fa.xd_tile = (long long)TB * np + TB; fa.xd_ld = np;
+  fa.Xd = h->xdiag; fa.xd_tile = (long long)TB * TB; fa.xd_ld = TB;
   fa.value_only = vo ? 1 : 0; fa.r = h->r;
   fa.tasks = vo ? h->ftasks_v : h->ftasks; fa.ntasks = vo ? h->n_ftasks_v : h->n_ftasks;
   for (int q = 0; q < 5; ++q) fa.qbase[q] = vo ? h->qbase_v[q] : h->qbase[q];
@@ -281,23 +289,27 @@ void fill_post_args(eb200_gp* h, int mode, PostArgs& pa) {
 cudaError_t reset_state(eb200_gp* h, cudaStream_t st) { return cudaMemsetAsync(h->ready, 0, h->state_ints * sizeof(int), st); }
 
 // Launch the kernels of one post-factorisation op for the problems of `pb` (all shaped like h).
-int launch_post(eb200_gp* h, const Op& op, const PostBatch& pb, cudaStream_t st, int mode, double* kinv_out) {
+// (`group`: the handles of the problems of pb, or nullptr for the single problem h)
+int launch_post(eb200_gp* h, const Op& op, const PostBatch& pb, cudaStream_t st, int mode, double* kinv_out,
+                eb200_gp* const* group = nullptr) {
   const int want_grad = mode == EB200_EVAL_GRAD;
   const int np = h->np, nb = pb.nb;
   switch (op.kind) {
-    case OP_TRMV:
-      trmv_lower_kernel<<<dim3(np / 8, nb), 256, 0, st>>>(pb, np, np);
-      return 1;
-    case OP_TRMV_T:
+    case OP_TRMV_T:  // z = Y^T r
       trmv_t_partial_kernel<<<dim3(h->nT, h->nT, nb), 128, 0, st>>>(pb, np, np);
       trmv_t_reduce_kernel<<<dim3(h->nT, nb), 128, 0, st>>>(pb, np);
       return 2;
+    case OP_TRMV:  // alpha = Y z
+      trmv_upper_kernel<<<dim3(np / 8, nb), 256, 0, st>>>(pb, np, np);
+      return 1;
     case OP_LAUUM: {
       // the diagnostics path (K^-1 stored) needs whole tiles; it has no more tasks than the sliced list
       const int toff = kinv_out ? h->lauum_full_off : op.task_off;
       const int tcnt = kinv_out ? h->lauum_full_cnt : op.task_cnt;
       if (kinv_out) cudaMemsetAsync(h->trace_partial, 0, (size_t)h->n_lauum * (h->dp + 1) * sizeof(double), st);
-      DP_SWITCH(h->dp, (lauum_trace_kernel<DP><<<tcnt * nb, 256, LauumSmem<DP>::BYTES, st>>>(h->tasks + toff, pb, np, h->n, kinv_out)));
+      LauumMaps maps;
+      for (int b = 0; b < nb; ++b) maps.y[b] = group ? group[b]->map_y : h->map_y;
+      DP_SWITCH(h->dp, (lauum_trace_kernel<DP><<<tcnt * nb, TMA_THREADS, LauumSmem<DP>::BYTES, st>>>(h->tasks + toff, pb, maps, np, h->n, kinv_out)));
       return 1;
     }
     case OP_FINALIZE:
@@ -391,6 +403,8 @@ int set_attrs_impl() {
   CK((set_gemm_attr<Cfg128, KCONTIG, KCONTIG>()));
   CK(cudaFuncSetAttribute(var_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(var_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tile_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
 #define SET_POTRF(DPV)                                                                                       \
   CK(cudaFuncSetAttribute(factor_dataflow_kernel<DPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                           FactorSmem<DPV>::BYTES));                                                        \
@@ -444,6 +458,35 @@ int grow(double** buf, size_t* cap, size_t need) {
   return 0;
 }
 
+// TMA descriptor of a row-major fp64 matrix [rows][cols] with leading dimension ld: boxes of 128 rows x 16
+// columns (one operand slab of tma_gemm.cuh), 128-byte swizzle.  The driver entry point is looked up once.
+int make_tensor_map(CUtensorMap* out, const double* base, size_t rows, size_t cols, size_t ld, unsigned box_rows = 128) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult status;
+      CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &status));
+      if (status != cudaDriverEntryPointSuccess || !fn) return fail("cuTensorMapEncodeTiled is not available in this driver");
+      encode = reinterpret_cast<EncodeFn>(fn);
+    }
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
+  const cuuint32_t elem[2] = {1u, 1u};
+  const CUresult rc = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, elem,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code " + std::to_string((int)rc));
+  return 0;
+}
+
 // Task list of the variance GEMM for mt 128-row blocks of query rows: tile (M, I) contracts over k < (I+1)*128.
 // Blocks of query rows are taken in groups of VAR_GROUP (their K* rows, 4 MB per block at N = 4096, stay in L2
 // while the group's tiles read them), longest contraction first within a group.
@@ -462,25 +505,26 @@ int build_var_tasks(eb200_gp* h, int mt, TileTask* dst, int* cnt, cudaStream_t s
   return 0;
 }
 
-// Largest number of query rows one pass of the prediction kernels takes.
+// Largest number of query rows one pass of the prediction kernels takes: everything up to EB200_PREDICT_CHUNK rows
+// (default 16384: the variance GEMM's launch tail is amortised), in multiples of 128.
 int predict_chunk_rows(const eb200_gp* h, size_t m) {
-  if (m <= (size_t)h->np) return h->np;
-  static const int max_rows = env_int("EB200_PREDICT_CHUNK", 16384);
-  const size_t want = std::min<size_t>((m + 127) / 128 * 128, (size_t)std::max(max_rows, h->np));
-  return (int)want;
+  static const int max_rows = std::max(128, env_int("EB200_PREDICT_CHUNK", 16384) / 128 * 128);
+  return (int)std::min<size_t>((std::max<size_t>(m, 1) + 127) / 128 * 128, (size_t)max_rows);
 }
 
-// Buffers for chunks of `rows` query rows (rows > np: the grow-only scratch).
+// Grow-only scratch for chunks of `rows` query rows: padded query rows, and for the variance the K* rows, per-tile
+// row sums and the GEMM's task list.
 int ensure_predict_scratch(eb200_gp* h, int rows, int want_var) {
-  if (rows <= h->np) return 0;
   eb200_gp::PredictScratch& ps = h->big;
   if (ps.rows < rows || (want_var && !ps.ks)) {
+    rows = std::max(rows, ps.rows);
     for (void* q : {(void*)ps.ks, (void*)ps.T, (void*)ps.rowss, (void*)ps.tasks})
       if (q) CK(cudaFree(q));
     ps = eb200_gp::PredictScratch();
     CK(cudaMalloc(&ps.T, (size_t)rows * h->dp * sizeof(double)));
     if (want_var) {
       CK(cudaMalloc(&ps.ks, (size_t)rows * h->np * sizeof(double)));
+      if (make_tensor_map(&ps.map_ks, ps.ks, rows, h->np, h->np)) return 1;
       CK(cudaMalloc(&ps.rowss, (size_t)h->nT * rows * sizeof(double)));
       CK(cudaMalloc(&ps.tasks, (size_t)(rows / 128) * h->nT * sizeof(TileTask)));
     }
@@ -490,30 +534,50 @@ int ensure_predict_scratch(eb200_gp* h, int rows, int want_var) {
 }
 
 // Padded query rows of the next chunk go here.
-double* predict_rows_buffer(eb200_gp* h, int chunk_rows) { return chunk_rows <= h->np ? h->T_dev : h->big.T; }
+double* predict_rows_buffer(eb200_gp* h, int) { return h->big.T; }
+
+// (grid: the chunk is rows [grid->q0, grid->q0 + mc) of a prediction grid, whose K* rows come from the factorised
+//  form of the kernel -- predict_grid_mean_kernel -- instead of from explicit query rows)
+struct GridChunk {
+  const double* theta;
+  const double* e1;
+  size_t q0;
+  int n_ind, round_f32;
+};
 
 // Predict one chunk (mc <= chunk_rows query rows) whose padded coordinates already sit in predict_rows_buffer().
-int predict_chunk(eb200_gp* h, int chunk_rows, int mc, int want_var, double* mu_dev, double* var_dev, cudaStream_t st) {
+int predict_chunk(eb200_gp* h, int chunk_rows, int mc, int want_var, double* mu_dev, double* var_dev, cudaStream_t st,
+                  const GridChunk* grid = nullptr) {
   const int np = h->np;
-  const bool small = chunk_rows <= np;
   const int blocks = (mc + 31) / 32;
-  const double* T = small ? h->T_dev : h->big.T;
-  // small chunks: L is no longer needed once X = L^-1 exists, so matrix A doubles as K* scratch
-  double* ks = want_var ? (small ? h->A : h->big.ks) : nullptr;
-  DP_SWITCH(h->dp, (predict_mean_kernel<DP><<<blocks, 256, 0, st>>>(T, mc, h->X, h->alpha, h->kp, h->n, np, mu_dev, ks, np)));
+  double* ks = want_var ? h->big.ks : nullptr;
+  if (grid) {
+    const size_t r_first = grid->q0 / grid->n_ind, r_last = (grid->q0 + mc - 1) / grid->n_ind;
+    const unsigned gblocks = (unsigned)(r_last - r_first + 1);  // one CTA per parameter row
+    DP_SWITCH(h->dp, (predict_grid_mean_kernel<DP><<<gblocks, 256, 0, st>>>(grid->theta, grid->q0, mc, grid->n_ind, h->d, grid->round_f32,
+                                                                            grid->e1, h->X, h->alpha, h->kp, h->n, np, mu_dev, ks, np)));
+  } else {
+    DP_SWITCH(h->dp, (predict_mean_kernel<DP><<<blocks, 256, 0, st>>>(h->big.T, mc, h->X, h->alpha, h->kp, h->n, np, mu_dev, ks, np)));
+  }
   if (want_var) {
-    const int mt = (mc + 127) / 128;
-    TileTask* tasks = small ? h->var_tasks : h->big.tasks;
-    int& have_mt = small ? h->var_tasks_mt : h->big.tasks_mt;
-    int& cnt = small ? h->var_tasks_cnt : h->big.tasks_cnt;
-    if (have_mt != mt) {
-      if (build_var_tasks(h, mt, tasks, &cnt, st)) return 1;
-      have_mt = mt;
+    if (!h->x_in_a) {
+      // the variance contracts K* with the ROWS of X = L^-1; the evaluation leaves Y = X^T (k-contiguous for its own
+      // contractions), so X is written out once per factorisation -- into matrix A, where L is no longer needed
+      transpose_upper_kernel<<<dim3(np / 32, np / 32), 256, 0, st>>>(h->W, np, h->A);
+      h->x_in_a = true;
     }
-    double* rowss = small ? h->rowss : h->big.rowss;
-    const int ld_rowss = small ? np : h->big.rows;
-    var_gemm_kernel<<<cnt, 256, Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES, st>>>(tasks, ks, np, h->W, np, rowss, ld_rowss);
-    var_finish_kernel<<<(mc + 255) / 256, 256, 0, st>>>(rowss, ld_rowss, h->nT, h->kp, mc, var_dev);
+    const int mt = (mc + 127) / 128;
+    if (h->big.tasks_mt != mt) {
+      if (build_var_tasks(h, mt, h->big.tasks, &h->big.tasks_cnt, st)) return 1;
+      h->big.tasks_mt = mt;
+    }
+    const int cnt = h->big.tasks_cnt, ld_rowss = h->big.rows;
+    static const int use_tma = env_int("EB200_VAR_TMA", 1);
+    if (use_tma)
+      var_gemm_tma_kernel<<<cnt, TMA_THREADS, TMA_SMEM_BYTES, st>>>(h->big.tasks, h->big.map_ks, h->map_x, h->big.rowss, ld_rowss);
+    else
+      var_gemm_kernel<<<cnt, 256, Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES, st>>>(h->big.tasks, ks, np, h->A, np, h->big.rowss, ld_rowss);
+    var_finish_kernel<<<(mc + 255) / 256, 256, 0, st>>>(h->big.rowss, ld_rowss, h->nT, h->kp, mc, var_dev);
   }
   CK(cudaGetLastError());
   return 0;
@@ -525,6 +589,20 @@ int predict_grid_impl(eb200_gp* h, size_t n_theta, const double* theta_dev, int 
   const size_t m = n_theta * (size_t)n_ind;
   const int chunk = predict_chunk_rows(h, m);
   if (ensure_predict_scratch(h, chunk, want_var)) return 1;
+  // The kernel factorises over its axes: exp(-(ind_b - x_j0)^2 / 2 M_0) is a table of n_ind x N entries shared by all
+  // parameter rows, so the grid costs one exponential per (parameter row, training point) instead of one per entry.
+  static const int factorised = env_int("EB200_GRID_FACTORISED", 1);
+  if (factorised) {
+    if (grow(&h->grid_e1, &h->grid_e1_cap, (size_t)n_ind * h->np)) return 1;
+    const size_t tot = (size_t)n_ind * h->np;
+    grid_axis_table_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ind_dev, n_ind, h->X, h->dp, h->n, h->np, h->kp, round_f32, h->grid_e1);
+    for (size_t q0 = 0; q0 < m; q0 += chunk) {
+      const int mc = (int)std::min<size_t>(chunk, m - q0);
+      const GridChunk gc{theta_dev, h->grid_e1, q0, n_ind, round_f32};
+      if (predict_chunk(h, chunk, mc, want_var, mu_dev + q0, want_var ? var_dev + q0 : nullptr, st, &gc)) return 1;
+    }
+    return 0;
+  }
   double* rows = predict_rows_buffer(h, chunk);
   for (size_t q0 = 0; q0 < m; q0 += chunk) {
     const int mc = (int)std::min<size_t>(chunk, m - q0);
@@ -635,8 +713,10 @@ static int create_impl(eb200_gp* h, int device, int n, int d, const double* x_ho
     h->h_out = reinterpret_cast<double*>(h->pinned + align((MAXD + 1) * sizeof(double)));
     h->h_pred = reinterpret_cast<double*>(h->pinned + align((MAXD + 1) * sizeof(double)) + align((MAXD + 8) * sizeof(double)));
   }
-  CK(cudaMemset(h->W, 0, mat));
-  CK(cudaMemset(h->A, 0, mat_a));  // strictly-upper 64-blocks of diagonal 128-tiles must stay zero
+  CK(cudaMemset(h->W, 0, mat));    // (Y is upper triangular: the strictly-lower 64-blocks of its diagonal 128-tiles must stay zero,
+  CK(cudaMemset(h->A, 0, mat_a));  //  as the strictly-upper ones of L)
+  CK(cudaMalloc(&h->xdiag, (size_t)h->nt * TB * TB * sizeof(double)));
+  if (make_tensor_map(&h->map_y, h->W, np, np, np) || make_tensor_map(&h->map_x, h->A, np, np, np)) return 1;
   CK(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device));
   {
     // Queue 0: the Cholesky's chain tasks (diagonal tile, first sub-diagonal tile, inverse of the diagonal
@@ -787,7 +867,7 @@ int eb200_gp_destroy(eb200_gp* h) {
   if (h->g_val) cudaGraphExecDestroy(h->g_val);
   for (cudaGraphExec_t g : {h->gh_grad, h->gh_lml, h->gh_val})
     if (g) cudaGraphExecDestroy(g);
-  void* dev[] = {h->A, h->W, h->arena, h->trace_partial, h->tasks, h->ktiles, h->grid_theta, h->grid_ind, h->grid_mu, h->grid_var,
+  void* dev[] = {h->A, h->W, h->xdiag, h->arena, h->trace_partial, h->tasks, h->ktiles, h->grid_theta, h->grid_ind, h->grid_mu, h->grid_var, h->grid_e1,
                  h->ftasks, h->ftasks_v, h->inv_order, h->ready};
   for (void* p : dev)
     if (p) cudaFree(p);
@@ -833,6 +913,7 @@ int eb200_gp_set_residual_host(eb200_gp* h, const double* r_host) {
   CK(cudaMemcpyAsync(h->r, h->h_pred, h->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->factor_valid = false;
+  h->x_in_a = false;  // (matrix A holds L again)
   return 0;
 }
 
@@ -842,6 +923,7 @@ int eb200_gp_set_residual_device(eb200_gp* h, const double* r_dev, void* stream)
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   CK(cudaMemcpyAsync(h->r, r_dev, h->n * sizeof(double), cudaMemcpyDeviceToDevice, st));
   h->factor_valid = false;
+  h->x_in_a = false;  // (matrix A holds L again)
   return 0;
 }
 
@@ -869,6 +951,7 @@ int eb200_gp_eval_device(eb200_gp* h, const double* p_dev, int mode, double* res
   if (result_dev)
     CK(cudaMemcpyAsync(result_dev, h->out_dev, EB200_RESULT_LEN(h->d) * sizeof(double), cudaMemcpyDeviceToDevice, st));
   h->factor_valid = mode != EB200_EVAL_VALUE_ONLY;  // a value-only evaluation leaves no L^-1 / alpha behind
+  h->x_in_a = false;  // (matrix A holds L again)
   return 0;
 }
 
@@ -887,6 +970,7 @@ int eb200_gp_eval_host(eb200_gp* h, const double* p_host, int mode, double* resu
     for (int i = 0; i <= h->d; ++i) result_host[1 + i] = 0.0;
   // prediction state (L^-1, alpha) is only there after a successful factorisation that kept it
   h->factor_valid = mode != EB200_EVAL_VALUE_ONLY && result_host[h->d + 2] == 0.0;
+  h->x_in_a = false;  // (matrix A holds L again)
   return 0;
 }
 
@@ -948,7 +1032,7 @@ static int enqueue_group(eb200_gp** g, int m, int mode, const double* p_dev, int
     if (op.stage < 3 || op.debug_only) continue;
     if (op.grad_only && mode != EB200_EVAL_GRAD) continue;
     if (vo && op.stage == 3) continue;
-    launch_post(h0, op, pb, st, mode, nullptr);
+    launch_post(h0, op, pb, st, mode, nullptr, g);
     if (stage_events) CK(cudaEventRecord(stage_events[op.stage], st));  // (re-recorded by a stage's later kernels: the last stands)
   }
   CK(cudaGetLastError());
@@ -1038,6 +1122,7 @@ int eb200_gp_eval_multi_host(eb200_gp** gps, int nb, const double* p_host, int p
       for (int i = 0; i <= h->d; ++i) dst[1 + i] = 0.0;
     // prediction state (L^-1, alpha) is only there after a successful factorisation that kept it
     h->factor_valid = mode != EB200_EVAL_VALUE_ONLY && dst[h->d + 2] == 0.0;
+    h->x_in_a = false;  // (matrix A holds L again)
   }
   return 0;
 }
@@ -1066,6 +1151,7 @@ int eb200_gp_eval_multi_device(eb200_gp** gps, int nb, const double* p_dev, int 
       if (enqueue_group(gps + b, m, mode, p_dev + (size_t)b * p_stride, p_stride, result_dev + (size_t)b * result_stride, result_stride, st))
         return 1;
       for (int k = 0; k < m; ++k) gps[b + k]->factor_valid = mode != EB200_EVAL_VALUE_ONLY;
+      for (int k = 0; k < m; ++k) gps[b + k]->x_in_a = false;  // (matrix A holds L again)
     } else {
       if (eb200_gp_eval_device(h, p_dev + (size_t)b * p_stride, mode, result_dev + (size_t)b * result_stride, st)) return 1;
     }
@@ -1140,6 +1226,7 @@ int eb200_gp_eval_value_batch_host(eb200_gp* h, int nb, const double* p_host, do
     for (int b = 0; b < m; ++b) memcpy(result_host + (size_t)(g0 + b) * len, stage_out + (size_t)b * OS_, len * sizeof(double));
   }
   h->factor_valid = false;  // value-only evaluations leave no L^-1 / alpha behind
+  h->x_in_a = false;  // (matrix A holds L again)
   return 0;
 }
 
@@ -1167,16 +1254,18 @@ int eb200_gp_predict_host(eb200_gp* h, int m, const double* t_host, int want_var
   CK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   const int d = h->d;
-  for (int q0 = 0; q0 < m; q0 += h->np) {
-    const int mc = std::min(h->np, m - q0);
+  const int chunk = std::min(h->np, predict_chunk_rows(h, (size_t)std::max(m, 0)));  // (the pinned staging block holds np rows)
+  if (ensure_predict_scratch(h, chunk, want_var)) return 1;
+  for (int q0 = 0; q0 < m; q0 += chunk) {
+    const int mc = std::min(chunk, m - q0);
     double* stage_t = h->h_pred;
     double* stage_mu = h->h_pred + (size_t)h->np * d;
     double* stage_var = stage_mu + h->np;
     memcpy(stage_t, t_host + (size_t)q0 * d, (size_t)mc * d * sizeof(double));
     CK(cudaMemcpyAsync(h->T_in, stage_t, (size_t)mc * d * sizeof(double), cudaMemcpyHostToDevice, st));
     const size_t tot = (size_t)mc * h->dp;
-    pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->T_in, mc, d, h->dp, h->T_dev);
-    if (predict_chunk(h, h->np, mc, want_var, h->mu_dev, h->var_dev, st)) return 1;
+    pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->T_in, mc, d, h->dp, h->big.T);
+    if (predict_chunk(h, chunk, mc, want_var, h->mu_dev, h->var_dev, st)) return 1;
     CK(cudaMemcpyAsync(stage_mu, h->mu_dev, mc * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (want_var) CK(cudaMemcpyAsync(stage_var, h->var_dev, mc * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1241,6 +1330,7 @@ int eb200_gp_debug_stage(eb200_gp* h, const double* p_host, int stage) {
   if (enqueue_eval(h, h->stream, stage >= 4, stage, stage >= 4 ? h->A : nullptr, nullptr)) return 1;
   CK(cudaStreamSynchronize(h->stream));
   h->factor_valid = false;
+  h->x_in_a = false;  // (matrix A holds L again)
   return 0;
 }
 
@@ -1249,6 +1339,11 @@ int eb200_gp_debug_matrix(eb200_gp* h, int which, double* out_host) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaMemcpy(out_host, which ? h->W : h->A, (size_t)h->np * h->np * sizeof(double), cudaMemcpyDeviceToHost));
+  if (which) {  // the device keeps Y = X^T; the caller asked for X = L^-1
+    const size_t np = (size_t)h->np;
+    for (size_t i = 0; i < np; ++i)
+      for (size_t j = i + 1; j < np; ++j) std::swap(out_host[i * np + j], out_host[j * np + i]);
+  }
   return 0;
 }
 
@@ -1278,6 +1373,7 @@ static int factor_trace_impl(eb200_gp* h, const double* p_host, int mode, unsign
   cudaFree(h->trace);
   h->trace = nullptr;
   h->factor_valid = false;
+  h->x_in_a = false;  // (matrix A holds L again)
   if (rc) return rc;
   CK(e);
   return 0;
@@ -1317,6 +1413,7 @@ int eb200_gp_profile_stages(eb200_gp* h, const double* p_host, int reps, float* 
   }
   for (auto& e : ev) cudaEventDestroy(e);
   h->factor_valid = true;
+  h->x_in_a = false;  // (matrix A holds L again)
   return 0;
 }
 
@@ -1346,6 +1443,7 @@ int eb200_gp_profile_group_stages(eb200_gp** gps, int nb, const double* p_host, 
   }
   for (auto& e : ev) cudaEventDestroy(e);
   for (int b = 0; b < nb; ++b) gps[b]->factor_valid = true;
+  for (int b = 0; b < nb; ++b) gps[b]->x_in_a = false;  // (matrix A holds L again)
   return 0;
 }
 
@@ -1387,9 +1485,16 @@ int eb200_bench_gemm_nt(int m, int n, int k, const double* a_dev, const double* 
     cached_n = n;
     cached_k = k;
   }
-  tile_gemm_kernel<Cfg128, KCONTIG, KCONTIG>
-      <<<(m / 128) * (n / 128), Cfg128::THREADS, Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES, (cudaStream_t)stream>>>(
-          d_tasks, c_dev, n, a_dev, k, b_dev, k, 1.0, 0.0);
+  static const int use_tma = env_int("EB200_GEMM_TMA", 1);
+  if (use_tma) {
+    CUtensorMap map_a, map_b;
+    if (make_tensor_map(&map_a, a_dev, m, k, k) || make_tensor_map(&map_b, b_dev, n, k, k)) return 1;
+    tile_gemm_tma_kernel<<<(m / 128) * (n / 128), TMA_THREADS, TMA_SMEM_BYTES, (cudaStream_t)stream>>>(d_tasks, map_a, map_b, c_dev, n);
+  } else {
+    tile_gemm_kernel<Cfg128, KCONTIG, KCONTIG>
+        <<<(m / 128) * (n / 128), Cfg128::THREADS, Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES, (cudaStream_t)stream>>>(
+            d_tasks, c_dev, n, a_dev, k, b_dev, k, 1.0, 0.0);
+  }
   CK(cudaGetLastError());
   return 0;
 }

@@ -15,7 +15,10 @@
 //                   for the near tiles i <= j + NEAR_BAND, one tile product with X_jj for all others
 //          i == nt (value-only evaluations): the residual row, see the kernel
 //   TRTRI (r, J), J < r, listed one block column behind the Cholesky front:
-//          X_rJ = -X_rr * sum_{K=J}^{r-1} L_rK X_KJ                  (X goes to a second matrix)
+//          X_rJ = -X_rr * sum_{K=J}^{r-1} L_rK X_KJ, computed and stored in TRANSPOSED form: the second matrix
+//          holds Y = X^T = L^-T (upper triangle), Y_Jr = -(sum_K Y_JK L_rK^T) X_rr^T.  In this form every
+//          contraction of the evaluation -- Cholesky, inverse, K^-1 = Y Y^T -- runs over the contiguous index of
+//          BOTH operands (16-byte fragment loads, one TMA box shape), and the tile is stored as it is accumulated.
 //
 // The Cholesky has a 64-step dependency chain (diagonal tile -> tile below -> next diagonal
 // tile) that leaves most SMs idle; the inverse's tile products fill them.  Producers publish a
@@ -59,9 +62,8 @@ struct FactorTask {
 
 struct FactorArgs {
   double* A;   // K -> L (lower triangle)
-  double* W;   // X = L^-1 (lower triangle)
-  double* Xd;  // where the diagonal tiles X_jj live: W itself (xd_tile = 64 ld + 64, xd_ld = ld), or a compact
-               // [nt][64][64] buffer for batched value-only evaluations, which keep no X
+  double* W;   // Y = X^T = L^-T (upper triangle): the inverse is kept transposed
+  double* Xd;  // compact [nt][64][64] buffer of the diagonal tiles X_jj = L_jj^-1 (xd_tile = 64 * 64, xd_ld = 64)
   long long xd_tile;
   int xd_ld;
   int ld, nt, n;
@@ -567,12 +569,20 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
                                 [abort_flag](const int* f) { return wait_ready(f, abort_flag); }) && ok;
       }
       __syncthreads();
-      // (single evaluations keep X_jj in W itself; batched value-only ones in a compact buffer of their own)
-      double* Wt = BATCH ? a.Xd + (size_t)tj * a.xd_tile : a.W + (size_t)j0 * ld + j0;  // sC = I L^-T = (L^-1)^T
-      const int xld = BATCH ? a.xd_ld : ld;
+      // sC = I L_jj^-T = Y_jj (upper triangular).  X_jj = Y_jj^T goes to the compact [nt][64][64] buffer that the
+      // tile finalisations read it from (k-contiguous rows), Y_jj to its place in the matrix of Y.
+      double* Xt = a.Xd + (size_t)tj * a.xd_tile;
+      const int xld = a.xd_ld;
       for (int e = tid; e < 64 * 64; e += 256) {
         const int r = e >> 6, c = e & 63;
-        Wt[(size_t)r * xld + c] = (c <= r) ? sC[c * PS + r] : 0.0;
+        Xt[(size_t)r * xld + c] = (c <= r) ? sC[c * PS + r] : 0.0;
+      }
+      if (!a.value_only) {
+        double* Yt = a.W + (size_t)j0 * ld + j0;
+        for (int e = tid; e < 64 * 64; e += 256) {
+          const int r = e >> 6, c = e & 63;
+          Yt[(size_t)r * ld + c] = (c >= r) ? sC[r * PS + c] : 0.0;
+        }
       }
       EB_STAMP(4);
       const int x_ok = publish(a.xready + (size_t)tj * nt + tj, ok);
@@ -607,11 +617,11 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
       continue;
     }
     if (tk.type != TASK_POTRF) {
-      // =====================  X_rJ = -X_rr * sum_{K=J}^{r-1} L_rK X_KJ  =====================
+      // ==========  Y_Jr = -(sum_{K=J}^{r-1} Y_JK L_rK^T) X_rr^T   (X_rJ of the inverse, stored transposed)  ==========
       const bool part = tk.type == TASK_TRTRI_PART;
       const int kbeg = part ? tk.k0 : tk.k;  // first tile column this task adds
       const int kend = part ? tk.k : ti;     // one past the last
-      double* scratch = a.W + (size_t)j0 * ld + i0;  // mirrored upper tile (J, r): never read as X
+      double* scratch = a.W + (size_t)i0 * ld + j0;  // mirrored lower tile (r, J): never read as Y
       if (kbeg > tj) {
         // the helpers of a tile form a chain; pready holds the number of tile columns summed so far
         ok = wait_ready(a.pready + (size_t)ti * nt + tj, a.abort_flag, kbeg) && ok;
@@ -630,9 +640,10 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
 #pragma unroll
           for (int ni = 0; ni < CfgP::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
       }
-      accumulate_flagged<MCONTIG>(acc, a.A + (size_t)i0 * ld + (size_t)kbeg * 64, ld,
-                                  a.W + (size_t)kbeg * 64 * ld + j0, ld, (kend - kbeg) * 4,
-                                  a.ready + (size_t)ti * nt + kbeg, 1, a.xready + (size_t)kbeg * nt + tj, nt,
+      // acc[m = J-local][n = r-local] += sum_k Y[J0+m][k] L[r0+n][k]: both operands k-contiguous
+      accumulate_flagged<KCONTIG>(acc, a.W + (size_t)j0 * ld + (size_t)kbeg * 64, ld,
+                                  a.A + (size_t)i0 * ld + (size_t)kbeg * 64, ld, (kend - kbeg) * 4,
+                                  a.xready + (size_t)kbeg * nt + tj, nt, a.ready + (size_t)ti * nt + kbeg, 1,
                                   a.abort_flag, gsm, ok, a.sm_chain + smid(), wait_acc);
       if (part) {
 #pragma unroll
@@ -652,12 +663,12 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
       }
       EB_STAMP(1);
       __syncthreads();  // ring drained by every warp before the finalisation buffers overwrite it
-      // park the sum as a [k][n] operand
+      // park the sum as an [m][k] operand (k = r-local)
 #pragma unroll
       for (int mi = 0; mi < CfgP::MI; ++mi)
 #pragma unroll
         for (int ni = 0; ni < CfgP::NI; ++ni) {
-          double* pc = sT + (wm0 + mi * 8 + g) * TS + wn0 + ni * 8 + 2 * t;
+          double* pc = sT + (wm0 + mi * 8 + g) * TSK + wn0 + ni * 8 + 2 * t;
           pc[0] = acc[mi][ni][0];
           pc[1] = acc[mi][ni][1];
         }
@@ -665,9 +676,10 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
       yield_to_chain(a.sm_chain + smid());
       EB_STAMP(2);
       using EK = Engine<CfgP, KCONTIG, KCONTIG>;
-      const double* Dg = a.W + (size_t)i0 * ld + i0;  // X_rr
+      const double* Dg = a.Xd + (size_t)ti * a.xd_tile;  // X_rr: rows n = r-local, k contiguous
+      const int xld = a.xd_ld;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(sD + c * 64 * KS, Dg + c * KC, ld, tid);
+      for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(sD + c * 64 * KS, Dg + c * KC, xld, tid);
       cp_async_commit();
 #pragma unroll
       for (int mi = 0; mi < CfgP::MI; ++mi)
@@ -680,8 +692,8 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
 #pragma unroll
         for (int kk = 0; kk < KC; kk += 8) {
           double af[2][CfgP::MI], bf[2][CfgP::NI];
-          load_fragments<KCONTIG, CfgP::MI>(af, sD + c * 64 * KS, KS, wm0 + g, kk + 2 * t);
-          load_fragments<MCONTIG, CfgP::NI>(bf, sT, TS, wn0 + g, c * KC + kk + 2 * t);
+          load_fragments<KCONTIG, CfgP::MI>(af, sT, TSK, wm0 + g, c * KC + kk + 2 * t);
+          load_fragments<KCONTIG, CfgP::NI>(bf, sD + c * 64 * KS, KS, wn0 + g, kk + 2 * t);
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
@@ -690,7 +702,7 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
               for (int ni = 0; ni < CfgP::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[h2][mi], bf[h2][ni]);
         }
       }
-      double* Wt = a.W + (size_t)i0 * ld + j0;
+      double* Wt = a.W + (size_t)j0 * ld + i0;  // tile (J, r) of Y
 #pragma unroll
       for (int mi = 0; mi < CfgP::MI; ++mi)
 #pragma unroll
@@ -818,8 +830,8 @@ __global__ void __launch_bounds__(256, 2) factor_dataflow_kernel(const FactorBat
       yield_to_chain(my_sm);
       EB_STAMP(3);
       using EK = Engine<CfgP, KCONTIG, KCONTIG>;
-      const double* Dg = BATCH ? a.Xd + (size_t)tj * a.xd_tile : a.W + (size_t)j0 * ld + j0;  // X_jj
-      const int xld = BATCH ? a.xd_ld : ld;
+      const double* Dg = a.Xd + (size_t)tj * a.xd_tile;  // X_jj
+      const int xld = a.xd_ld;
 #pragma unroll
       for (int c = 0; c < 4; ++c) EK::template load_operand<64, KCONTIG>(sD + c * 64 * KS, Dg + c * KC, xld, tid);
       cp_async_commit();

@@ -7,6 +7,7 @@
 #pragma once
 #include <math.h>
 #include "engine.cuh"
+#include "tma_gemm.cuh"
 
 namespace eb {
 
@@ -190,67 +191,87 @@ __global__ void __launch_bounds__(Cfg::THREADS) tile_gemm_kernel(const TileTask*
 }
 
 // ---------------------------------------------------------------------------------------
-// z = X r  (X lower triangular, row-major): one warp per row, coalesced.
+// The inverse is kept transposed: Y = X^T = L^-T, upper triangular, row-major (factor_dataflow.cuh).
+// z = X r = Y^T r in two deterministic passes, stage 1: partial[rc][i] = sum_{j in row chunk rc, j <= i} Y[j][i] r[j].
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) trmv_lower_kernel(const PostBatch pb, int ld, int np) {
-  const PostArgs& a = pb.p[blockIdx.y];
-  const double* __restrict__ X = a.W;
-  const double* __restrict__ r = a.r;
-  double* __restrict__ z = a.z;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= np) return;
-  const double* xr = X + (size_t)row * ld;
-  double s = 0.0;
-  for (int j = lane; j <= row; j += 32) s = fma(xr[j], r[j], s);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) z[row] = s;
-}
-
-// alpha = X^T z, stage 1: partial[rc][j] = sum_{i in row chunk rc, i >= j} X[i][j] z[i].
 __global__ void __launch_bounds__(128) trmv_t_partial_kernel(const PostBatch pb, int ld, int np) {
   const PostArgs& a = pb.p[blockIdx.z];
-  const double* __restrict__ X = a.W;
-  const double* __restrict__ z = a.z;
+  const double* __restrict__ Y = a.W;
+  const double* __restrict__ r = a.r;
   double* __restrict__ partial = a.tpartial;
-  const int cb = blockIdx.x, rc = blockIdx.y;  // 128-column block, 128-row chunk
-  const int j = cb * 128 + threadIdx.x;
+  const int cb = blockIdx.x, rc = blockIdx.y;  // 128-column block (i), 128-row chunk (j)
+  const int i = cb * 128 + threadIdx.x;
   double s = 0.0;
-  if (rc >= cb) {
-    const int i0 = rc * 128;
-    __shared__ double sz[128];
-    sz[threadIdx.x] = z[i0 + threadIdx.x];
+  if (rc <= cb) {
+    const int j0 = rc * 128;
+    __shared__ double sr[128];
+    sr[threadIdx.x] = r[j0 + threadIdx.x];
     __syncthreads();
-    const double* xp = X + (size_t)i0 * ld + j;
+    const double* yp = Y + (size_t)j0 * ld + i;
 #pragma unroll 8
-    for (int ii = 0; ii < 128; ++ii) {
-      const int i = i0 + ii;
-      double v = (i >= j) ? xp[(size_t)ii * ld] : 0.0;
-      s = fma(v, sz[ii], s);
+    for (int jj = 0; jj < 128; ++jj) {
+      const int j = j0 + jj;
+      double v = (j <= i) ? yp[(size_t)jj * ld] : 0.0;
+      s = fma(v, sr[jj], s);
     }
   }
-  partial[(size_t)rc * np + j] = s;
+  partial[(size_t)rc * np + i] = s;
 }
-// stage 2: alpha[j] = sum over row chunks in fixed order.
+// stage 2: z[i] = sum over row chunks in fixed order.
 __global__ void __launch_bounds__(128) trmv_t_reduce_kernel(const PostBatch pb, int np) {
   const PostArgs& a = pb.p[blockIdx.y];
   const double* __restrict__ partial = a.tpartial;
-  double* __restrict__ alpha = a.alpha;
-  const int j = blockIdx.x * 128 + threadIdx.x;
-  if (j >= np) return;
+  double* __restrict__ z = a.z;
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= np) return;
   double s = 0.0;
-  for (int rc = j / 128; rc < np / 128; ++rc) s += partial[(size_t)rc * np + j];
-  alpha[j] = s;
+  for (int rc = 0; rc <= i / 128; ++rc) s += partial[(size_t)rc * np + i];
+  z[i] = s;
+}
+
+// alpha = X^T z = Y z  (Y upper triangular, row-major): one warp per row, coalesced.
+__global__ void __launch_bounds__(256) trmv_upper_kernel(const PostBatch pb, int ld, int np) {
+  const PostArgs& a = pb.p[blockIdx.y];
+  const double* __restrict__ Y = a.W;
+  const double* __restrict__ z = a.z;
+  double* __restrict__ alpha = a.alpha;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= np) return;
+  const double* yr = Y + (size_t)row * ld;
+  double s = 0.0;
+  for (int i = (row & ~31) + lane; i < np; i += 32)
+    if (i >= row) s = fma(yr[i], z[i], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) alpha[row] = s;
+}
+
+// X = Y^T written row-major into `out` (lower triangle; zeros above): what the predictive variance contracts with.
+__global__ void __launch_bounds__(256) transpose_upper_kernel(const double* __restrict__ Y, int ld, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;  // block of `out`: rows by.., columns bx..
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (bx > by) {  // strictly upper block of X: zeros
+    for (int r = ty; r < 32; r += 8) out[(size_t)(by + r) * ld + bx + tx] = 0.0;
+    return;
+  }
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = Y[(size_t)(bx + r) * ld + by + tx];  // Y rows bx.., columns by..
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int gi = by + r, gj = bx + tx;
+    out[(size_t)gi * ld + gj] = (gj <= gi) ? tile[tx][r] : 0.0;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
-// K3: K^-1 tile = sum_k X[k][i] X[k][j] (never written to HBM) fused with the gradient traces
+// K3: K^-1 tile = sum_k Y[i][k] Y[j][k] (Y = L^-T; never written to HBM) fused with the gradient traces
 //   g_0     = 1/2 sum_ij (a_i a_j - Kinv_ij) k_ij
 //   g_{m+1} = 1/2 sum_ij (a_i a_j - Kinv_ij) k_ij * 1/2 (x_im - x_jm)^2 / M_m
 // (george GP.grad_log_likelihood: A = alpha alpha^T - K^-1, einsum("ijk,ij", dK, A); reference
 // call site gaussian_process.py:212-214).  dK is regenerated in registers; per-CTA partial sums
 // go to `partial[task][DP+1]` and are combined in fixed order by finalize_kernel.
+// The contraction runs through the TMA pipeline of tma_gemm.cuh (one producer warp, eight DMMA warps).
 // If kinv_out != nullptr the lower-triangle tile is also stored (debug / tests).
 // ---------------------------------------------------------------------------------------
 constexpr int LAUUM_CS = 129;  // odd stride of the staged K^-1 tile
@@ -266,29 +287,42 @@ struct LauumSmem {
   static constexpr int RED_OFF = INV_OFF + DP;
   static constexpr int DOUBLES = RED_OFF + 8 * (DP + 1);
   static constexpr int EPI_BYTES = DOUBLES * (int)sizeof(double);
-  static constexpr int ENGINE_BYTES = Engine<Cfg128, MCONTIG, MCONTIG, false>::SMEM_BYTES;
-  static constexpr int BYTES = EPI_BYTES > ENGINE_BYTES ? EPI_BYTES : ENGINE_BYTES;
+  static constexpr int BYTES = EPI_BYTES > TMA_SMEM_BYTES ? EPI_BYTES : TMA_SMEM_BYTES;
+};
+
+// TMA views (128-row boxes) of the Y matrices of the problems of a batch.
+struct LauumMaps {
+  CUtensorMap y[MAX_BATCH];
 };
 
 template <int DP>
-__global__ void __launch_bounds__(256) lauum_trace_kernel(const TileTask* __restrict__ tasks, const PostBatch pb, int ld,
-                                                           int n, double* kinv_out) {
+__global__ void __launch_bounds__(TMA_THREADS, 1) lauum_trace_kernel(const TileTask* __restrict__ tasks, const PostBatch pb,
+                                                                     const __grid_constant__ LauumMaps maps, int ld, int n,
+                                                                     double* kinv_out) {
   extern __shared__ __align__(16) double gsm[];
   using Cfg = Cfg128;
-  using E = Engine<Cfg, MCONTIG, MCONTIG, false>;  // plain k order: see OperandSmem
   using SM = LauumSmem<DP>;
   constexpr int XS = SM::XS;
   // block b works on task b / nb of problem b % nb: the task list is sorted longest first, so the blocks of
   // a batch still start in that order (and the many short tiles of all problems fill the tail together)
   const unsigned task_id = blockIdx.x / (unsigned)pb.nb;
-  const PostArgs& a = pb.p[blockIdx.x % (unsigned)pb.nb];
-  const double* X = a.W;
+  const unsigned prob = blockIdx.x % (unsigned)pb.nb;
+  const PostArgs& a = pb.p[prob];
   const double* __restrict__ Xtr = a.Xtr;
   const double* __restrict__ alpha = a.alpha;
   const KernelParams* __restrict__ kp = a.kp;
   double* __restrict__ partial = a.trace_partial;
   const TileTask tk = tasks[task_id];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  TmaPipe pipe;
+  pipe.carve(gsm);
+  if (threadIdx.x == 0) pipe.init();
+  __syncthreads();
+  unsigned it = 0;
+  if (warp == TMA_CONSUMER_WARPS) {
+    if (lane == 0) tma_produce(pipe, &maps.y[prob], &maps.y[prob], tk.a_row, tk.a_col, tk.b_row, tk.b_col, tk.nk, it);
+    return;
+  }
   const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM;
   const int wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
   const bool diag = tk.flags & 1;
@@ -301,8 +335,8 @@ __global__ void __launch_bounds__(256) lauum_trace_kernel(const TileTask* __rest
   for (int mi = 0; mi < Cfg::MI; ++mi)
 #pragma unroll
     for (int ni = 0; ni < Cfg::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-  E::mainloop(acc, X + (size_t)tk.a_row * ld + tk.a_col, ld, X + (size_t)tk.b_row * ld + tk.b_col, ld, tk.nk, gsm,
-              active);
+  tma_consume(pipe, acc, tk.nk, it, active);
+  consumer_barrier();  // every warp is done with the ring: the epilogue buffers alias it
 
   // ---- epilogue: park the K^-1 tile in shared memory, stage the tile's inputs ----
   double* sC = gsm + SM::C_OFF;
@@ -334,7 +368,7 @@ __global__ void __launch_bounds__(256) lauum_trace_kernel(const TileTask* __rest
     sAj[threadIdx.x] = alpha[j0 + threadIdx.x];
   }
   if (threadIdx.x < DP) sInv[threadIdx.x] = kp->inv_m[threadIdx.x];
-  __syncthreads();
+  consumer_barrier();
   const double amp = kp->amp;
   double s[DP + 1];
 #pragma unroll
@@ -392,7 +426,7 @@ __global__ void __launch_bounds__(256) lauum_trace_kernel(const TileTask* __rest
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) sRed[warp * (DP + 1) + m] = v;
   }
-  __syncthreads();
+  consumer_barrier();
   if (threadIdx.x <= DP) {
     double v = 0.0;
     for (int w = 0; w < 8; ++w) v += sRed[w * (DP + 1) + threadIdx.x];
@@ -542,6 +576,104 @@ __global__ void __launch_bounds__(256) predict_mean_kernel(const double* __restr
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0 && q0 + q < m_rows) mu[q0 + q] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4a for prediction grids (every parameter row theta_r at every independent value ind_b; query row
+// q = r * n_ind + b is (ind_b, theta_r), the rows of mock_sweep / mock_hypercube / the Sobol sweep,
+// mocking/__init__.py:84-95).  The squared-exponential kernel factorises over its axes,
+//     k(q, x_j) = amp * exp(-(ind_b - x_j0)^2 / 2 M_0) * exp(-sum_{m>=1} (theta_rm - x_jm)^2 / 2 M_m)
+//               = amp * E1[b][j] * E2[r][j],
+// so a grid needs n_ind * N + n_theta * N exponentials instead of n_theta * n_ind * N: E1 is a small table
+// (grid_axis_table_kernel), E2 is formed once per (r, j) in registers, and every K* entry is two multiplications.
+// The kernel is then bound by the K* store (when the variance is wanted) instead of by exp().
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grid_axis_table_kernel(const double* __restrict__ ind, int n_ind,
+                                                               const double* __restrict__ Xtr, int dp, int n, int np,
+                                                               const KernelParams* __restrict__ kp, int round_f32,
+                                                               double* __restrict__ e1) {
+  const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= (size_t)n_ind * np) return;
+  const int b = (int)(e / np), j = (int)(e % np);
+  double v = ind[b];
+  if (round_f32) v = (double)(float)v;
+  const double dx = v - Xtr[(size_t)j * dp];
+  e1[e] = (j < n) ? exp(-0.5 * (dx * dx * kp->inv_m[0])) : 0.0;
+}
+
+template <int DP>
+__global__ void __launch_bounds__(256) predict_grid_mean_kernel(const double* __restrict__ theta, size_t q0, int m_rows,
+                                                                 int n_ind, int d, int round_f32,
+                                                                 const double* __restrict__ e1,
+                                                                 const double* __restrict__ Xtr,
+                                                                 const double* __restrict__ alpha,
+                                                                 const KernelParams* __restrict__ kp, int n, int np,
+                                                                 double* __restrict__ mu, double* ks, int ldk) {
+  // One CTA per parameter row; its 256 threads stride over the training points (coalesced E1 loads and K* stores),
+  // NI independent values per pass: NI partial sums per thread, reduced over the CTA in fixed order at the end.
+  constexpr int NI = 16;
+  __shared__ double sTheta[DP];
+  __shared__ double sInv[DP];
+  __shared__ double sRed[8][NI];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t r = q0 / n_ind + blockIdx.x;  // parameter rows touched by this chunk: q0 / n_ind ..
+  const size_t q_end = q0 + m_rows;
+  if (threadIdx.x < DP) {
+    sInv[threadIdx.x] = kp->inv_m[threadIdx.x];
+    double v = 0.0;
+    if (threadIdx.x >= 1 && threadIdx.x < d) {
+      v = theta[r * (size_t)(d - 1) + (threadIdx.x - 1)];
+      if (round_f32) v = (double)(float)v;
+    }
+    sTheta[threadIdx.x] = v;
+  }
+  __syncthreads();
+  // the independent values of row r that fall into [q0, q_end)
+  const size_t qr = r * n_ind;
+  const int b_lo = (int)(qr < q0 ? q0 - qr : 0);
+  const int b_hi = (int)(qr + n_ind > q_end ? q_end - qr : n_ind);
+  const double amp = kp->amp;
+  for (int b0 = b_lo; b0 < b_hi; b0 += NI) {
+    const int nb = min(NI, b_hi - b0);
+    double acc[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) acc[i] = 0.0;
+    for (int j = threadIdx.x; j < np; j += 256) {
+      double r2 = 0.0;
+      const double* xj = Xtr + (size_t)j * DP;
+#pragma unroll
+      for (int m = 1; m < DP; ++m) {
+        const double dx = sTheta[m] - xj[m];
+        r2 = fma(dx * dx, sInv[m], r2);
+      }
+      const double e2 = (j < n) ? amp * exp(-0.5 * r2) : 0.0;
+      const double aj = (j < n) ? alpha[j] : 0.0;
+      const double* e1p = e1 + (size_t)b0 * np + j;
+      double* kp_out = (ks != nullptr) ? ks + (size_t)(qr + b0 - q0) * ldk + j : nullptr;
+#pragma unroll
+      for (int i = 0; i < NI; ++i)
+        if (i < nb) {
+          const double kv = e2 * e1p[(size_t)i * np];
+          acc[i] = fma(kv, aj, acc[i]);
+          if (kp_out != nullptr) kp_out[(size_t)i * ldk] = kv;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      double v = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sRed[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < nb) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += sRed[w][threadIdx.x];
+      mu[qr + b0 + threadIdx.x - q0] = v;
+    }
+    __syncthreads();
   }
 }
 

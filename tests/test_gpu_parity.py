@@ -83,8 +83,10 @@ def test_prediction_matches_oracle(n, d, m):
 
 @pytest.mark.parametrize("n,d,n_theta,n_ind", [(300, 4, 7, 5), (640, 9, 300, 32), (200, 2, 1, 1), (1000, 3, 4097, 3)])
 def test_grid_prediction_equals_row_by_row_prediction(n, d, n_theta, n_ind):
-    """Query rows formed on the device (float32-rounded like the emulators' query points) must give
-    exactly what predict gives on the same rows built on the host."""
+    """The grid form (float32-rounded like the emulators' query points) must give what predict gives on the same
+    rows built on the host.  The grid evaluates the kernel in its factorised form, exp(a) * exp(b) instead of
+    exp(a + b) -- one exponential per (parameter row, training point) instead of one per entry -- so the two agree to
+    a few rounding units of the kernel values, not bit for bit."""
     x, y, diag = problem(n, d, seed=n + n_theta)
     gp = device_problem(x, diag, y)
     p = orc.default_parameter_vector(d) + 0.15
@@ -98,7 +100,7 @@ def test_grid_prediction_equals_row_by_row_prediction(n, d, n_theta, n_ind):
     mu_ref, var_ref = gp.predict(rows.astype(np.float64), True)
     mu, var = gp.predict_grid(theta, ind, True)
     assert mu.shape == (n_theta, n_ind)
-    assert np.array_equal(mu.ravel(), mu_ref) and np.array_equal(var.ravel(), var_ref)
+    assert relmax(mu.ravel(), mu_ref) <= 1e-11 and np.max(np.abs(var.ravel() - var_ref)) <= 1e-12 * orc.amplitude(p, d)
     assert np.array_equal(gp.predict_grid(theta, ind, False), mu)
     # unrounded rows: against the oracle
     k = min(3, n_theta)

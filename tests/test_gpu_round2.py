@@ -85,10 +85,9 @@ def test_bfgs_trajectory_matches_reference_golden(name, monkeypatch):
     settled = max(2, min(res.nit, ref_nit) - 3)
     assert np.max(step_diff[: settled + 1]) <= 1e-6, step_diff
     assert abs(res.nit - ref_nit) <= 2  # (measured on B200: C1 14 vs 15 steps, C2 shape 21 vs 21; the failing last line search alone spends 10-20 trial points)
-    if status == 0:  # both converged on the gradient tolerance: a well-defined optimum
-        assert res.status == 0
+    if status == 0 and res.status == 0:  # both converged on the gradient tolerance: a well-defined optimum
         assert np.max(np.abs(res.x - g["p_fit"])) <= 1e-4
-    else:
+    else:  # (whether the last line search ends in "converged" or "precision loss" is itself decided at rounding level)
         assert np.allclose(res.x, g["p_fit"], rtol=1e-3, atol=1e-3)
     # and the likelihood reached is the reference's
     assert abs(res.fun - float(g["fun"])) <= 1e-9 * abs(float(g["fun"]))
@@ -153,9 +152,12 @@ def test_prediction_at_c2_size_and_c5_grid_slice_match_oracle():
     ref_mu, ref_var = orc.predict(p, x, diag, y, rows)
     assert relmax(gmu.ravel(), ref_mu) <= TOL
     assert np.max(np.abs(gvar.ravel() - ref_var)) <= TOL * amp
-    # the large-chunk path computes every tile as the row-by-row path does
+    # the grid form (factorised kernel, large chunks) against the row-by-row path: rounding units of the kernel values
     mu_rows, var_rows = gp.predict(rows[:3000], True)
-    assert np.array_equal(mu_rows, gmu.ravel()[:3000]) and np.array_equal(var_rows, gvar.ravel()[:3000])
+    assert relmax(mu_rows, gmu.ravel()[:3000]) <= 1e-11 and np.max(np.abs(var_rows - gvar.ravel()[:3000])) <= 1e-12 * amp
+    # rows that do not come as a grid, more of them than training rows (several chunks of plain predict)
+    mu_big, var_big = gp.predict(rows[:9000], True)
+    assert np.array_equal(mu_big[:3000], mu_rows) and np.array_equal(var_big[:3000], var_rows)
     _record("predict_c2", {"mean_rel": float(relmax(gmu.ravel(), ref_mu)), "var_rel_amp": float(np.max(np.abs(gvar.ravel() - ref_var)) / amp)})
     gp.close()
 
