@@ -243,7 +243,11 @@ def block_sweep_c5(torch, td, world, rank, local, dev, peak_tflops, log2_rows):
         design = np.vstack([design, extra])
     theta = np.ascontiguousarray(design[:rows])
     ind = np.linspace(0.0, 1.0, SWEEP_IND)
+    from emulator_b200 import dist
+
     sobol.sweep_predict(emu, theta[: 1 << 12], ind, want_var=True)  # warm-up: factorisation, allocations, NCCL
+    # host staging of the two result arrays pinned ahead of time -- what any sweep after a process's first one finds
+    dist.pinned_pool.reserve((rows, SWEEP_IND), 2)
     sampler = ClockSampler(local)
     sampler.start()
     (mean, var), ev_ms, wall_ms = timed_collective_region(torch, td, world, dev, lambda: sobol.sweep_predict(emu, theta, ind, want_var=True))

@@ -153,9 +153,10 @@ struct eb200_gp {
   // rows, per-tile row sums and the variance GEMM's task list for chunks of up to `rows` query rows.  Smaller
   // predictions use the handle's resident buffers (K* goes to matrix A, dead once X = L^-1 exists).
   struct PredictScratch {
-    double *ks = nullptr, *T = nullptr, *rowss = nullptr;
+    double *ks = nullptr, *T = nullptr, *rowss = nullptr, *e2 = nullptr;
     TileTask* tasks = nullptr;
     int rows = 0, tasks_mt = -1, tasks_cnt = 0;
+    size_t e2_rows = 0;  // parameter rows the E2 table of fused grid predictions holds
     CUtensorMap map_ks;  // TMA view of ks (valid when ks != nullptr)
   } big;
   // TMA views (tma_gemm.cuh, 128-row boxes): of Y = L^-T in matrix W (K^-1 tiles) and of X = L^-1 in matrix A
@@ -405,6 +406,7 @@ int set_attrs_impl() {
                           Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(var_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
   CK(cudaFuncSetAttribute(tile_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(var_grid_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
 #define SET_POTRF(DPV)                                                                                       \
   CK(cudaFuncSetAttribute(factor_dataflow_kernel<DPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                           FactorSmem<DPV>::BYTES));                                                        \
@@ -514,21 +516,27 @@ int predict_chunk_rows(const eb200_gp* h, size_t m) {
 
 // Grow-only scratch for chunks of `rows` query rows: padded query rows, and for the variance the K* rows, per-tile
 // row sums and the GEMM's task list.
-int ensure_predict_scratch(eb200_gp* h, int rows, int want_var) {
+int ensure_predict_scratch(eb200_gp* h, int rows, int want_var, bool need_ks = true) {
   eb200_gp::PredictScratch& ps = h->big;
-  if (ps.rows < rows || (want_var && !ps.ks)) {
+  if (ps.rows < rows || (want_var && !ps.rowss)) {
     rows = std::max(rows, ps.rows);
     for (void* q : {(void*)ps.ks, (void*)ps.T, (void*)ps.rowss, (void*)ps.tasks})
       if (q) CK(cudaFree(q));
+    double* keep_e2 = ps.e2;
+    const size_t keep_e2_rows = ps.e2_rows;
     ps = eb200_gp::PredictScratch();
+    ps.e2 = keep_e2;
+    ps.e2_rows = keep_e2_rows;
     CK(cudaMalloc(&ps.T, (size_t)rows * h->dp * sizeof(double)));
     if (want_var) {
-      CK(cudaMalloc(&ps.ks, (size_t)rows * h->np * sizeof(double)));
-      if (make_tensor_map(&ps.map_ks, ps.ks, rows, h->np, h->np)) return 1;
       CK(cudaMalloc(&ps.rowss, (size_t)h->nT * rows * sizeof(double)));
       CK(cudaMalloc(&ps.tasks, (size_t)(rows / 128) * h->nT * sizeof(TileTask)));
     }
     ps.rows = rows;
+  }
+  if (want_var && need_ks && !ps.ks) {  // K* rows: only predictions that are not fused grids need them
+    CK(cudaMalloc(&ps.ks, (size_t)ps.rows * h->np * sizeof(double)));
+    if (make_tensor_map(&ps.map_ks, ps.ks, ps.rows, h->np, h->np)) return 1;
   }
   return 0;
 }
@@ -543,6 +551,7 @@ struct GridChunk {
   const double* e1;
   size_t q0;
   int n_ind, round_f32;
+  bool fused;  // the variance kernel rebuilds K* = E1 * E2 in shared memory (no K* rows in global memory)
 };
 
 // Predict one chunk (mc <= chunk_rows query rows) whose padded coordinates already sit in predict_rows_buffer().
@@ -550,12 +559,21 @@ int predict_chunk(eb200_gp* h, int chunk_rows, int mc, int want_var, double* mu_
                   const GridChunk* grid = nullptr) {
   const int np = h->np;
   const int blocks = (mc + 31) / 32;
-  double* ks = want_var ? h->big.ks : nullptr;
+  const bool fused = grid && grid->fused && want_var;
+  double* ks = (want_var && !fused) ? h->big.ks : nullptr;
   if (grid) {
     const size_t r_first = grid->q0 / grid->n_ind, r_last = (grid->q0 + mc - 1) / grid->n_ind;
     const unsigned gblocks = (unsigned)(r_last - r_first + 1);  // one CTA per parameter row
+    if (fused && h->big.e2_rows < gblocks) {
+      if (h->big.e2) CK(cudaFree(h->big.e2));
+      h->big.e2 = nullptr;
+      h->big.e2_rows = 0;
+      CK(cudaMalloc(&h->big.e2, (size_t)gblocks * np * sizeof(double)));
+      h->big.e2_rows = gblocks;
+    }
     DP_SWITCH(h->dp, (predict_grid_mean_kernel<DP><<<gblocks, 256, 0, st>>>(grid->theta, grid->q0, mc, grid->n_ind, h->d, grid->round_f32,
-                                                                            grid->e1, h->X, h->alpha, h->kp, h->n, np, mu_dev, ks, np)));
+                                                                            grid->e1, h->X, h->alpha, h->kp, h->n, np, mu_dev, ks, np,
+                                                                            fused ? h->big.e2 : nullptr)));
   } else {
     DP_SWITCH(h->dp, (predict_mean_kernel<DP><<<blocks, 256, 0, st>>>(h->big.T, mc, h->X, h->alpha, h->kp, h->n, np, mu_dev, ks, np)));
   }
@@ -573,7 +591,10 @@ int predict_chunk(eb200_gp* h, int chunk_rows, int mc, int want_var, double* mu_
     }
     const int cnt = h->big.tasks_cnt, ld_rowss = h->big.rows;
     static const int use_tma = env_int("EB200_VAR_TMA", 1);
-    if (use_tma)
+    if (fused)
+      var_grid_fused_kernel<<<cnt, FUSED_THREADS, TMA_SMEM_BYTES, st>>>(h->big.tasks, h->map_x, grid->e1, h->big.e2, np, grid->q0, mc,
+                                                                        grid->n_ind, h->big.rowss, ld_rowss);
+    else if (use_tma)
       var_gemm_tma_kernel<<<cnt, TMA_THREADS, TMA_SMEM_BYTES, st>>>(h->big.tasks, h->big.map_ks, h->map_x, h->big.rowss, ld_rowss);
     else
       var_gemm_kernel<<<cnt, 256, Engine<Cfg128, KCONTIG, KCONTIG>::SMEM_BYTES, st>>>(h->big.tasks, ks, np, h->A, np, h->big.rowss, ld_rowss);
@@ -588,7 +609,9 @@ int predict_grid_impl(eb200_gp* h, size_t n_theta, const double* theta_dev, int 
                       int want_var, double* mu_dev, double* var_dev, cudaStream_t st) {
   const size_t m = n_theta * (size_t)n_ind;
   const int chunk = predict_chunk_rows(h, m);
-  if (ensure_predict_scratch(h, chunk, want_var)) return 1;
+  static const int factorised_env = env_int("EB200_GRID_FACTORISED", 1), fused_env = env_int("EB200_GRID_FUSED", 1);
+  const bool fused = factorised_env && fused_env && want_var;
+  if (ensure_predict_scratch(h, chunk, want_var, !fused)) return 1;
   // The kernel factorises over its axes: exp(-(ind_b - x_j0)^2 / 2 M_0) is a table of n_ind x N entries shared by all
   // parameter rows, so the grid costs one exponential per (parameter row, training point) instead of one per entry.
   static const int factorised = env_int("EB200_GRID_FACTORISED", 1);
@@ -598,7 +621,7 @@ int predict_grid_impl(eb200_gp* h, size_t n_theta, const double* theta_dev, int 
     grid_axis_table_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ind_dev, n_ind, h->X, h->dp, h->n, h->np, h->kp, round_f32, h->grid_e1);
     for (size_t q0 = 0; q0 < m; q0 += chunk) {
       const int mc = (int)std::min<size_t>(chunk, m - q0);
-      const GridChunk gc{theta_dev, h->grid_e1, q0, n_ind, round_f32};
+      const GridChunk gc{theta_dev, h->grid_e1, q0, n_ind, round_f32, fused};
       if (predict_chunk(h, chunk, mc, want_var, mu_dev + q0, want_var ? var_dev + q0 : nullptr, st, &gc)) return 1;
     }
     return 0;
@@ -879,7 +902,7 @@ int eb200_gp_destroy(eb200_gp* h) {
       if (q) cudaFree(q);
     if (bs.h_stage) cudaFreeHost(bs.h_stage);
   }
-  for (void* q : {(void*)h->big.ks, (void*)h->big.T, (void*)h->big.rowss, (void*)h->big.tasks})
+  for (void* q : {(void*)h->big.ks, (void*)h->big.T, (void*)h->big.rowss, (void*)h->big.tasks, (void*)h->big.e2})
     if (q) cudaFree(q);
   if (h->group.p_dev) cudaFree(h->group.p_dev);
   if (h->group.out_dev) cudaFree(h->group.out_dev);

@@ -609,7 +609,10 @@ __global__ void __launch_bounds__(256) predict_grid_mean_kernel(const double* __
                                                                  const double* __restrict__ Xtr,
                                                                  const double* __restrict__ alpha,
                                                                  const KernelParams* __restrict__ kp, int n, int np,
-                                                                 double* __restrict__ mu, double* ks, int ldk) {
+                                                                 double* __restrict__ mu, double* ks, int ldk,
+                                                                 double* e2_out) {
+  // (e2_out != nullptr: the per-row factor E2[r - r_first][j] = amp * exp(..) is kept for the fused variance kernel,
+  //  var_grid_fused_kernel, which rebuilds K* = E1 * E2 tile by tile in shared memory; no K* row is stored then)
   // One CTA per parameter row; its 256 threads stride over the training points (coalesced E1 loads and K* stores),
   // NI independent values per pass: NI partial sums per thread, reduced over the CTA in fixed order at the end.
   constexpr int NI = 16;
@@ -648,6 +651,7 @@ __global__ void __launch_bounds__(256) predict_grid_mean_kernel(const double* __
         r2 = fma(dx * dx, sInv[m], r2);
       }
       const double e2 = (j < n) ? amp * exp(-0.5 * r2) : 0.0;
+      if (e2_out != nullptr && b0 == b_lo) e2_out[(size_t)blockIdx.x * np + j] = e2;
       const double aj = (j < n) ? alpha[j] : 0.0;
       const double* e1p = e1 + (size_t)b0 * np + j;
       double* kp_out = (ks != nullptr) ? ks + (size_t)(qr + b0 - q0) * ldk + j : nullptr;

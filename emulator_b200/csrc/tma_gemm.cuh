@@ -83,9 +83,10 @@ struct TmaPipe {
     full = reinterpret_cast<unsigned long long*>(a + (size_t)TMA_STAGES * TMA_STAGE_BYTES);
     empty = full + TMA_STAGES;
   }
-  __device__ __forceinline__ void init() {  // one thread; followed by a CTA barrier in the caller
+  // (full_arrivals: 1 = the TMA-issuing thread; more when other warps write part of a stage themselves)
+  __device__ __forceinline__ void init(unsigned full_arrivals = 1) {  // one thread; followed by a CTA barrier in the caller
     for (int s = 0; s < TMA_STAGES; ++s) {
-      mbar_init(full + s, 1);
+      mbar_init(full + s, full_arrivals);
       mbar_init(empty + s, TMA_CONSUMER_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -161,6 +162,104 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) var_gemm_tma_kernel(const Tile
   unsigned it = 0;
   if (warp == TMA_CONSUMER_WARPS) {
     if (lane == 0) tma_produce(pipe, &mapK, &mapX, tk.a_row, tk.a_col, tk.b_row, tk.b_col, tk.nk, it);
+    return;
+  }
+  double acc[Cfg::MI][Cfg::NI][2];
+#pragma unroll
+  for (int mi = 0; mi < Cfg::MI; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < Cfg::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  tma_consume(pipe, acc, tk.nk, it);
+  const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM;
+  const int g = lane >> 2, t = lane & 3;
+  const int wn = warp % Cfg::WARPS_N;
+#pragma unroll
+  for (int mi = 0; mi < Cfg::MI; ++mi) {
+    double v = 0.0;
+#pragma unroll
+    for (int ni = 0; ni < Cfg::NI; ++ni) {
+      v = fma(acc[mi][ni][0], acc[mi][ni][0], v);
+      v = fma(acc[mi][ni][1], acc[mi][ni][1], v);
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (t == 0) sRow[wn * 128 + wm0 + mi * 8 + g] = v;
+  }
+  consumer_barrier();
+  if (threadIdx.x < 128) {
+    const double v = sRow[threadIdx.x] + sRow[128 + threadIdx.x] + sRow[256 + threadIdx.x] + sRow[384 + threadIdx.x];
+    rowss[(size_t)(tk.c_col / 128) * ld_rowss + tk.c_row + threadIdx.x] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Predictive variance of a prediction GRID with the cross-covariance built and consumed in one kernel: K* never
+// exists in global memory.  The kernel factorises over its axes (kernels.cuh, predict_grid_mean_kernel):
+// K*[q][j] = E1[b(q)][j] * E2[r(q)][j] with q = r * n_ind + b, E1 a table of n_ind x N entries and E2 one row of N
+// entries per parameter row.  Four generator warps (one lane per query row of the 128-row tile) form each 128 x 16
+// slab of K* from the two tables straight into the pipeline stage, in the layout TMA would have written (dense
+// 128-byte rows, 16-byte chunk c of row R at position c ^ (R & 7)); the slab of X = L^-1 comes by TMA; the eight
+// DMMA warps consume both.  Per 16384-row chunk the DRAM traffic falls from 537 MB written + several GB re-read
+// (K*) to the 16 MB of E2.
+// ---------------------------------------------------------------------------------------
+constexpr int FUSED_GEN_WARPS = 4;
+constexpr int FUSED_THREADS = (TMA_CONSUMER_WARPS + FUSED_GEN_WARPS) * 32;
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1) var_grid_fused_kernel(const TileTask* __restrict__ tasks,
+                                                                          const __grid_constant__ CUtensorMap mapX,
+                                                                          const double* __restrict__ e1, const double* __restrict__ e2,
+                                                                          int np, size_t q0, int m_rows, int n_ind,
+                                                                          double* __restrict__ rowss, int ld_rowss) {
+  extern __shared__ __align__(16) double gsm[];
+  __shared__ double sRow[4 * 128];
+  using Cfg = Cfg128;
+  TmaPipe pipe;
+  pipe.carve(gsm);
+  if (threadIdx.x == 0) pipe.init(1 + FUSED_GEN_WARPS);
+  __syncthreads();
+  const TileTask tk = tasks[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned it = 0;
+  if (warp >= TMA_CONSUMER_WARPS) {
+    // ---- generators: lane <-> query row of the tile; warp 8's lane 0 also issues the TMA of the X slab ----
+    const int row = (warp - TMA_CONSUMER_WARPS) * 32 + lane;
+    const size_t q = q0 + (size_t)tk.a_row + row;
+    const bool live = tk.a_row + row < m_rows;
+    const size_t r_first = q0 / n_ind;
+    const double* e1p = e1 + (size_t)(q % n_ind) * np + tk.a_col;
+    const double* e2p = e2 + (size_t)(q / n_ind - r_first) * np + tk.a_col;
+    const bool tma_lane = warp == TMA_CONSUMER_WARPS && lane == 0;
+    // the products of the NEXT chunk are formed while this one's stage is still in use (the table loads are L2
+    // round trips): when the stage is released, the slab is written at once
+    double2 nxt[8];
+    auto form = [&](int kt) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        nxt[c] = make_double2(0.0, 0.0);
+        if (live && kt < tk.nk) {
+          const double2 a = __ldg(reinterpret_cast<const double2*>(e1p + kt * KC + 2 * c));
+          const double2 b = __ldg(reinterpret_cast<const double2*>(e2p + kt * KC + 2 * c));
+          nxt[c].x = a.x * b.x;
+          nxt[c].y = a.y * b.y;
+        }
+      }
+    };
+    form(0);
+    for (int kt = 0; kt < tk.nk; ++kt, ++it) {
+      const unsigned stage = it % TMA_STAGES, round = it / TMA_STAGES;
+      if (round > 0) mbar_wait(pipe.empty + stage, (round - 1) & 1);
+      double* dst = pipe.slabs + (size_t)stage * (TMA_STAGE_BYTES / 8);
+      if (tma_lane) {
+        mbar_expect_tx(pipe.full + stage, TMA_SLAB_BYTES);
+        tma_load_2d(dst + TMA_SLAB_BYTES / 8, &mapX, tk.b_col + kt * KC, tk.b_row, pipe.full + stage);
+      }
+      char* out = reinterpret_cast<char*>(dst) + row * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<double2*>(out + ((c ^ (row & 7)) << 4)) = nxt[c];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pipe.full + stage);
+      form(kt + 1);
+    }
     return;
   }
   double acc[Cfg::MI][Cfg::NI][2];

@@ -25,6 +25,14 @@ Self-checks that stand in for the missing known-answer tests live in
 ``tests/test_oracle.py`` (finite-difference gradient, slogdet / solve cross-checks, symmetry,
 variance >= 0, row-permutation invariance) and in the committed ``tests/golden`` vectors.
 
+What narrows "unpinned": ``tests/test_oracle_vs_sklearn.py`` checks this file against an independently written
+implementation of the same quantities, scikit-learn's ``GaussianProcessRegressor`` with
+``ConstantKernel(d e^p0) * RBF(length_scale = sqrt(M))``, ``alpha`` = george's diagonal term, ``optimizer=None``:
+log marginal likelihood, its gradient (chain rule d/dlog M = 1/2 d/dlog l), predictive mean and variance agree to
+1e-13 .. 2e-11 on seven shapes (d = 1 .. 16, N up to 1024), asserted at 1e-10.  It remains unpinned against george
+ITSELF (george's own conventions -- amp = d e^p0, the sqrt(yerr^2 + TINY)^2 diagonal, no noise in the predictive
+variance -- are restated from its published source, not executed).
+
 Everything is IEEE fp64 through numpy / scipy.linalg (LAPACK dpotrf / dpotrs), exactly the
 libraries george's BasicSolver calls.
 """

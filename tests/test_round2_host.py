@@ -250,3 +250,29 @@ def test_restarts_keep_the_reference_run_as_start_zero_and_never_do_worse(oracle
     again = GaussianProcessEmulator(restarts=3, restart_seed=2)
     again.fit_model(spec, params, values)
     assert np.array_equal(again.fit_result.restart_funs, funs)  # seeded
+
+
+# ---- recycled host buffers ------------------------------------------------------------------------------------------
+def test_pinned_pool_recycles_a_buffer_only_when_nothing_refers_to_it():
+    import gc
+
+    pool = dist.PinnedPool()
+    a1 = pool.take((4, 3)).numpy()
+    a1[:] = 1
+    a2 = pool.take((4, 3)).numpy()
+    a2[:] = 2
+    assert a1.sum() == 12 and a2.sum() == 24 and len(pool._entries) == 2  # two live results, two buffers
+    piece = a1[:2]
+    del a1
+    gc.collect()
+    pool.take((4, 3))
+    assert len(pool._entries) == 3  # a slice of the first result still lives: not recycled
+    assert piece.sum() == 6
+    del piece, a2
+    gc.collect()
+    before = len(pool._entries)
+    v = pool.take((2, 3))
+    assert len(pool._entries) == before  # everything was released: a buffer is reused
+    del v
+    pool.reserve((100,), 2)
+    assert sum(e.numel() >= 100 for e in pool._entries) >= 2
