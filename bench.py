@@ -262,9 +262,11 @@ def block_sweep_c5(torch, td, world, rank, local, dev, peak_tflops, log2_rows):
         "timed": "sensitivity.sobol.sweep_predict between barriers: H2D of this rank's parameter rows, query rows formed on the device, "
                  "mean + variance kernels, NCCL all-gather of both results from device memory, one D2H copy each; CUDA events, max over ranks",
         "h2d_bytes": int(theta.nbytes // world + ind.nbytes), "d2h_bytes": int(2 * m * 8),
-        "roofline": {"bound": "tensor", "kernel": "var_gemm_kernel (V = K* L^-T reduced to row norms; DMMA.8x8x4 128x128 tiles)",
+        "roofline": {"bound": "tensor", "kernel": "var_grid_fused_kernel (K* rebuilt in shared memory from the factorised tables, V = K* L^-T by TMA-fed "
+                     "DMMA.8x8x4 128x128 tiles, reduced to row norms; K* and V never in global memory)",
                      "flops": flops, "achieved": flops / ev_ms / 1e9 / world, "peak": peak_tflops, "unit": "TFLOP/s per GPU",
-                     "frac": flops / ev_ms / 1e9 / world / peak_tflops},
+                     "frac": flops / ev_ms / 1e9 / world / peak_tflops, "traffic": ncu_traffic("var_grid_fused")[0],
+                     "note": "N^2 flop per query row over the WHOLE sweep (host copies, mean kernel, all-gather included)"},
         "checksum": float(mean.sum() + var.sum()), "clocks": clocks,
     }
     if world == 1 and rank == 0:
@@ -457,7 +459,10 @@ def run_ours(args):
         roofline = {
             "bound": "tensor", "kernel": kernel_names.get(dominant, names[dominant]) + " -- DMMA.8x8x4 tile engine, one launch per group of 4 evaluations",
             "achieved": achieved_stage, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_stage / peak_tflops,
-            "traffic": traffic, "traffic_source": f"profiles/{traffic_src} (ncu --set full, bytes per launch)" if traffic_src else None,
+            "launch": {"evaluations": group, "flops": stage_flops[dominant] * group, "ms": float(stage_ms[dominant] * group),
+                       "note": "achieved = flops / ms of one launch of the dominant kernel (a group of 4 evaluations), CUDA events"},
+            "traffic": traffic, "traffic_source": f"profiles/{traffic_src} (ncu --set full, DRAM bytes per launch of 4 evaluations; algorithmic: "
+                                                  "4 x 134 MB of L and Y written once -- four interleaved problems no longer fit the 126 MB L2)" if traffic_src else None,
             "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; MEASURED_PEAKS.json has no fp64 entry",
             "whole_eval": {"flops": n3, "ms": eval_ms, "achieved": achieved_eval, "frac": achieved_eval / peak_tflops},
             "stage_ms_per_eval_grouped": {k: float(v) for k, v in zip(names, stage_ms)},

@@ -59,6 +59,7 @@ SIGNATURES = {
     "eb200_gp_eval_launches": (c_int, [c_void_p, c_int]),
     "eb200_gp_debug_factor_trace": (c_int, [c_void_p, _dp, POINTER(ctypes.c_ulonglong), POINTER(c_int)]),
     "eb200_gp_factor_tasks": (c_int, [c_void_p]),
+    "eb200_gp_debug_group_trace": (c_int, [POINTER(c_void_p), c_int, _dp, c_int, POINTER(ctypes.c_ulonglong), POINTER(c_int)]),
     "eb200_gp_debug_value_trace": (c_int, [c_void_p, _dp, POINTER(ctypes.c_ulonglong), POINTER(c_int)]),
     "eb200_gp_value_tasks": (c_int, [c_void_p]),
     "eb200_gp_profile_stages": (c_int, [c_void_p, _dp, c_int, POINTER(ctypes.c_float)]),

@@ -1014,7 +1014,7 @@ static int ensure_group_state(eb200_gp* h) {
 // result vector to out_dev + b * out_stride (device pointers).  Results equal stand-alone evaluations bit for
 // bit: every tile and every reduction is computed by the same code in the same order whoever claims it.
 static int enqueue_group(eb200_gp** g, int m, int mode, const double* p_dev, int p_stride, double* out_dev, int out_stride,
-                         cudaStream_t st, cudaEvent_t* stage_events = nullptr) {
+                         cudaStream_t st, cudaEvent_t* stage_events = nullptr, unsigned long long* const* traces = nullptr) {
   eb200_gp* h0 = g[0];
   const int nt = h0->nt;
   const bool vo = mode == EB200_EVAL_VALUE_ONLY;
@@ -1040,7 +1040,7 @@ static int enqueue_group(eb200_gp** g, int m, int mode, const double* p_dev, int
     FactorArgs& fa = fb.p[b];
     fill_factor_args(h, vo, fa);
     fa.sm_chain = fb.p[0].sm_chain;  // one priority flag per SM for the whole launch
-    fa.trace = nullptr;
+    fa.trace = traces ? traces[b] : nullptr;
     fa.n_chain_sms = n_chain;
     fill_post_args(h, mode, pb.p[b]);
     pb.p[b].out = out_dev + (size_t)b * out_stride;
@@ -1406,6 +1406,40 @@ int eb200_gp_debug_factor_trace(eb200_gp* h, const double* p_host, unsigned long
 }
 int eb200_gp_debug_value_trace(eb200_gp* h, const double* p_host, unsigned long long* out_host, int* tasks_out) {
   return factor_trace_impl(h, p_host, EB200_EVAL_VALUE_ONLY, out_host, tasks_out);
+}
+// The same stamps for a GROUP of equally shaped handles sharing one factorisation launch: out_host[nb][tasks][10].
+int eb200_gp_debug_group_trace(eb200_gp** gps, int nb, const double* p_host, int p_stride, unsigned long long* out_host, int* tasks_out) {
+  if (!gps || !p_host || !out_host || !tasks_out || nb < 1 || nb > MAX_BATCH) return fail("group_trace: bad argument");
+  if (check_distinct(gps, nb, "group_trace")) return 1;
+  eb200_gp* h = gps[0];
+  for (int b = 0; b < nb; ++b)
+    if (!same_shape(gps[b], h)) return fail("group_trace: the handles must share one shape");
+  CK(cudaSetDevice(h->device));
+  if (ensure_group_state(h)) return 1;
+  const int PS_ = MAXD + 1, OS_ = MAXD + 8;
+  const size_t per = (size_t)h->n_ftasks * TRACE_SLOTS;
+  unsigned long long* dev = nullptr;
+  CK(cudaMalloc(&dev, nb * per * sizeof(unsigned long long)));
+  CK(cudaMemset(dev, 0, nb * per * sizeof(unsigned long long)));
+  unsigned long long* ptrs[MAX_BATCH];
+  for (int b = 0; b < nb; ++b) {
+    ptrs[b] = dev + b * per;
+    memcpy(h->group.h_stage + (size_t)b * PS_, p_host + (size_t)b * p_stride, (h->d + 1) * sizeof(double));
+  }
+  CK(cudaMemcpyAsync(h->group.p_dev, h->group.h_stage, (size_t)nb * PS_ * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  int rc = 0;
+  for (int rep = 0; rep < 2 && !rc; ++rep)  // (the second run is the one kept: warm caches)
+    rc = enqueue_group(gps, nb, EB200_EVAL_LML, h->group.p_dev, PS_, h->group.out_dev, OS_, h->stream, nullptr, ptrs);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (!rc && e == cudaSuccess) {
+    e = cudaMemcpy(out_host, dev, nb * per * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(tasks_out, h->ftasks, (size_t)h->n_ftasks * sizeof(FactorTask), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(dev);
+  for (int b = 0; b < nb; ++b) { gps[b]->factor_valid = false; gps[b]->x_in_a = false; }
+  if (rc) return rc;
+  CK(e);
+  return 0;
 }
 int eb200_gp_factor_tasks(const eb200_gp* h) { return h ? h->n_ftasks : -1; }
 int eb200_gp_value_tasks(const eb200_gp* h) { return h ? h->n_ftasks_v : -1; }

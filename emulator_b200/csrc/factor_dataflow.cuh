@@ -124,7 +124,10 @@ constexpr int TRACE_SLOTS = 10;  // 6 stamps, SM id, CTA id, ns waited for flags
 
 // Flags are polled with a relaxed gpu-scope load: an acquire load would make ptxas emit
 // CCTL.IVALL (L1 invalidate + drain of every outstanding load, including the cp.async ring) on
-// every poll.
+// every poll.  INVARIANT this relies on: tile data published under a flag is only ever read with instructions
+// that bypass L1 -- cp.async.cg, ld.global.cg (__ldcg) -- so there is no stale L1 line to invalidate and the producer's
+// __threadfence + release store make the data visible in L2 before the flag.  A plain ld.global of tile data
+// anywhere in this kernel would break it (the parity suite at ragged sizes is what would notice).
 __device__ __forceinline__ int ld_flag(const int* p) {
   int v;
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -140,18 +143,27 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 }
 
 // Lane 0 of every warp polls; returns false if the watchdog fired.
+// The watchdog's budget is TIME (globaltimer), not a spin count: a CTA may legitimately wait long when several
+// persistent launches share the device (refits from host threads, overlapping graphs, a profiler's replay).
+constexpr unsigned long long WATCHDOG_NS = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s without progress = a lost dependency
+__device__ __forceinline__ bool watchdog_expired(unsigned long long& t0, const int* abort_flag) {
+  if (ld_flag(abort_flag) != 0) return true;  // somebody else gave up: follow
+  const unsigned long long now = gtime();
+  if (t0 == 0ull) t0 = now;  // (first checkpoint, ~1024 polls in: the clock is only read by waits that are already long)
+  return now - t0 > WATCHDOG_NS;
+}
+
 __device__ __forceinline__ bool wait_ready(const int* flag, int* abort_flag, int need = 1) {
   bool ok = true;
   if ((threadIdx.x & 31) == 0) {
-    long long spins = 0;
+    unsigned spins = 0;
+    unsigned long long t0 = 0ull;
     while (ld_flag(flag) < need) {
       __nanosleep(20);
-      if ((++spins & 0x3ff) == 0) {
-        if (spins > (1ll << 24) || ld_flag(abort_flag) != 0) {  // ~1 s
-          atomicExch(abort_flag, 1);
-          ok = false;
-          break;
-        }
+      if ((++spins & 0x3ff) == 0 && watchdog_expired(t0, abort_flag)) {
+        atomicExch(abort_flag, 1);
+        ok = false;
+        break;
       }
     }
   }
@@ -163,18 +175,17 @@ __device__ __forceinline__ bool wait_ready(const int* flag, int* abort_flag, int
 __device__ __forceinline__ bool wait_ready2(const int* f1, const int* f2, int* abort_flag) {
   bool ok = true;
   if ((threadIdx.x & 31) == 0) {
-    long long spins = 0;
+    unsigned spins = 0;
+    unsigned long long t0 = 0ull;
     for (;;) {
       const int v1 = ld_flag(f1);
       const int v2 = (f2 != nullptr) ? ld_flag(f2) : 1;
       if (v1 != 0 && v2 != 0) break;
       __nanosleep(20);
-      if ((++spins & 0x3ff) == 0) {
-        if (spins > (1ll << 24) || ld_flag(abort_flag) != 0) {
-          atomicExch(abort_flag, 1);
-          ok = false;
-          break;
-        }
+      if ((++spins & 0x3ff) == 0 && watchdog_expired(t0, abort_flag)) {
+        atomicExch(abort_flag, 1);
+        ok = false;
+        break;
       }
     }
   }

@@ -327,6 +327,13 @@ class GP:
         vectors = np.atleast_2d(np.asarray(vectors, dtype=np.float64))
         with self._using_device():
             self._sync_residual()
+            # the batch factorises up to eight vectors at once, each in a matrix of its own (allocated on first use
+            # and kept by the handle): make room for those too
+            extra = max(0, min(len(vectors), 8) - 1)
+            if extra and not getattr(self._problem, "_batch_slots_reserved", False):
+                npad = -(-len(self._x) // 128) * 128
+                _residency.make_room(self.device, extra * (npad + 64) * npad * 8, keep=self)
+                self._problem._batch_slots_reserved = True
             lml, info, _, _ = self._problem.evaluate_value_batch(vectors)
         self.n_device_evaluations += len(vectors)
         self._device_p = None  # no prediction state survives

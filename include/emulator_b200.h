@@ -135,6 +135,9 @@ int eb200_gp_eval_launches(const eb200_gp* gp, int mode);
  * tile row, tile column, 0).  The number of tasks is eb200_gp_factor_tasks(). */
 int eb200_gp_debug_factor_trace(eb200_gp* gp, const double* p_host, unsigned long long* out_host, int* tasks_out);
 int eb200_gp_factor_tasks(const eb200_gp* gp);
+/* the same for a group of nb equally shaped handles sharing one factorisation launch: out[nb][task][10] */
+int eb200_gp_debug_group_trace(eb200_gp** gps, int nb, const double* p_host, int p_stride, unsigned long long* out_host,
+                               int* tasks_out);
 /* the same for a value-only evaluation (Cholesky tiles + the residual row, tile row nt) */
 int eb200_gp_debug_value_trace(eb200_gp* gp, const double* p_host, unsigned long long* out_host, int* tasks_out);
 int eb200_gp_value_tasks(const eb200_gp* gp);
