@@ -10,7 +10,7 @@ One "step" = one pass of the hot path over a batch of BATCH independent hyperpar
 build, Cholesky, triangular inverse, alpha, K^-1 tiles fused with the gradient traces, final reduction) -- what
 the reference does as one `fun(p)` + one `jac(p)` call per vector
 (swiftemulator/emulators/gaussian_process.py:208-221).  The vectors of a step are independent (optimiser
-restarts, leave-one-out refits): they are evaluated on BATCH GP handles holding the same data, four at a time
+restarts, leave-one-out refits): they are evaluated on BATCH GP handles holding the same data, all eight
 sharing launches (eb200_gp_eval_multi_*: interleaved factorisations; bit-identical to stand-alone evaluations,
 asserted below).
 
@@ -443,7 +443,7 @@ def run_ours(args):
     peak_tflops = float(pk.cpu()[0])
     if rank == 0:
         # ---- roofline of the dominant stage, live: per-stage CUDA-event times of one group + cuBLAS DGEMM peak ----
-        group = 4
+        group = BATCH  # the eight evaluations of a step share their launches
         stage_ms = profile_group_stages(gps[:group], ps[:group], reps=3) / group  # per evaluation
         single_ms = gps[0].profile_stages(ps[0], reps=3)
         names = ["params", "kbuild_cholesky_inverse", "alpha", "kinv_traces", "finalize"]
@@ -454,15 +454,15 @@ def run_ours(args):
         achieved_eval = n3 / eval_ms / 1e9
         achieved_stage = stage_flops[dominant] / stage_ms[dominant] / 1e9 if stage_ms[dominant] > 0 else 0.0
         traffic, traffic_src = ncu_traffic("factor_dataflow" if dominant == 1 else "lauum_trace")
-        kernel_names = {1: "factor_dataflow_kernel<9,true> (K build + Cholesky + triangular inverse of 4 interleaved problems)",
+        kernel_names = {1: f"factor_dataflow_kernel<9,true> (K build + Cholesky + triangular inverse of {group} interleaved problems)",
                         3: "lauum_trace_kernel (K^-1 tiles + traces)"}
         roofline = {
-            "bound": "tensor", "kernel": kernel_names.get(dominant, names[dominant]) + " -- DMMA.8x8x4 tile engine, one launch per group of 4 evaluations",
+            "bound": "tensor", "kernel": kernel_names.get(dominant, names[dominant]) + f" -- DMMA.8x8x4 tile engine, one launch per group of {group} evaluations",
             "achieved": achieved_stage, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_stage / peak_tflops,
             "launch": {"evaluations": group, "flops": stage_flops[dominant] * group, "ms": float(stage_ms[dominant] * group),
-                       "note": "achieved = flops / ms of one launch of the dominant kernel (a group of 4 evaluations), CUDA events"},
-            "traffic": traffic, "traffic_source": f"profiles/{traffic_src} (ncu --set full, DRAM bytes per launch of 4 evaluations; algorithmic: "
-                                                  "4 x 134 MB of L and Y written once -- four interleaved problems no longer fit the 126 MB L2)" if traffic_src else None,
+                       "note": f"achieved = flops / ms of one launch of the dominant kernel (a group of {group} evaluations), CUDA events"},
+            "traffic": traffic, "traffic_source": f"profiles/{traffic_src} (ncu --set full, DRAM bytes per launch of {group} evaluations; algorithmic: "
+                                                  f"{group} x 134 MB of L and Y written once -- interleaved problems no longer fit the 126 MB L2)" if traffic_src else None,
             "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; MEASURED_PEAKS.json has no fp64 entry",
             "whole_eval": {"flops": n3, "ms": eval_ms, "achieved": achieved_eval, "frac": achieved_eval / peak_tflops},
             "stage_ms_per_eval_grouped": {k: float(v) for k, v in zip(names, stage_ms)},

@@ -1027,8 +1027,7 @@ static int enqueue_group(eb200_gp** g, int m, int mode, const double* p_dev, int
   const int grid = (int)std::min<long long>(2ll * h0->n_sms, (long long)m * ntasks);
   // chain CTAs per problem: a CTA of the chain queue claims in order and waits inside its task, so it is a
   // CTA slot that mostly idles -- as few as keep the chain fed
-  // (measured at N = 4096, ms per evaluation, groups of 4: 1 chain CTA per problem 2.91, 2: 2.80, 3: 2.82, 6: 2.86;
-  //  stand-alone evaluations 2.98)
+  // (measured at N = 4096: see groups_pay)
   static const int chain_env = env_int("EB200_GROUP_CHAIN", 0);
   int n_chain = std::max(1, std::min({6, nt / 4, (grid / m) / 4}));
   if (nt > 32) n_chain = std::min(n_chain, 2);
@@ -1067,17 +1066,18 @@ static bool same_shape(const eb200_gp* a, const eb200_gp* b) {
 }
 
 // Whether handles shaped like h share factorisation launches when several are evaluated together.
-// (measured, 64 handles, us per evaluation, own graphs vs shared launches: N=256 12 vs 38, N=640 65 vs 77,
-//  N=768 107 vs 99, N=1000 ~430 vs 117: below ~14 tile rows the handles' own graphs overlap well enough)
-// (the same at larger sizes, stand-alone vs groups: N=2048 0.91 vs 0.46 ms (groups of 8), N=4096 2.98 vs 2.80 (groups of 4;
-//  2.93 in groups of 8), N=8176 20.0 vs 20.5: a factorisation of 128 tile rows keeps the device busy by itself)
+// Measured on B200, ms per LML+grad evaluation, stand-alone -> grouped (d = 9 unless noted):
+//   N = 256 (d = 8) 0.012 vs 0.038 and N = 640 0.065 vs 0.077 with the handles' own graphs overlapping on their streams:
+//   below ~14 tile rows that is the better way;  N = 1000 (d = 3) 0.405 -> 0.109;  2048: 0.88 -> 0.42;  3072: 1.51 -> 1.16;
+//   4096: 2.92 -> 2.56 in groups of eight (2.58 in groups of four; 2 chain CTAs per problem: 1 -> 2.57 / 2.83, 3 -> 2.58);
+//   6144: 8.62 -> 8.06 and 8176: 19.26 -> 18.50 in groups of four (18.60 in pairs).
 static bool groups_pay(const eb200_gp* h, int mode) {
-  static const int lo = env_int("EB200_GROUP_MIN_NT", 14), hi = env_int("EB200_GROUP_MAX_NT", 96);
+  static const int lo = env_int("EB200_GROUP_MIN_NT", 14), hi = env_int("EB200_GROUP_MAX_NT", 160);
   return mode != EB200_EVAL_VALUE_ONLY && h->nt >= lo && h->nt <= hi;
 }
 static int group_size(const eb200_gp* h) {
   static const int env = env_int("EB200_GROUP_SIZE", 0);
-  const int m = env > 0 ? env : (h->nt <= 32 ? MAX_BATCH : 4);
+  const int m = env > 0 ? env : (h->nt <= 64 ? MAX_BATCH : 4);
   return std::max(1, std::min((int)MAX_BATCH, m));
 }
 
@@ -1507,6 +1507,8 @@ int eb200_gp_profile_group_stages(eb200_gp** gps, int nb, const double* p_host, 
 int eb200_bench_accumulate(int m, int n, int k, int b_mcontig, int grid, const double* a_dev, const double* b_dev,
                            double* c_dev, void* stream) {
   if (m % 64 || n % 64 || k % 64) return fail("bench_accumulate: m, n, k must be multiples of 64");
+  static std::mutex mu;  // (the cached device state below is shared by all callers)
+  std::lock_guard<std::mutex> lock(mu);
   static int* ones = nullptr;
   if (!ones) {
     CK(cudaMalloc(&ones, 2 * sizeof(int)));
@@ -1529,6 +1531,8 @@ int eb200_bench_accumulate(int m, int n, int k, int b_mcontig, int grid, const d
 int eb200_bench_gemm_nt(int m, int n, int k, const double* a_dev, const double* b_dev, double* c_dev, void* stream) {
   if (m % 128 || n % 128 || k % (2 * KC)) return fail("bench_gemm_nt: m, n must be multiples of 128 and k of 32");
   if (set_attrs()) return 1;
+  static std::mutex mu;  // (the cached task list below is shared by all callers)
+  std::lock_guard<std::mutex> lock(mu);
   static TileTask* d_tasks = nullptr;
   static int cached_m = -1, cached_n = -1, cached_k = -1;
   if (cached_m != m || cached_n != n || cached_k != k) {

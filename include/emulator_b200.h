@@ -71,7 +71,7 @@ int eb200_gp_eval_device(eb200_gp* gp, const double* p_dev, int mode, double* re
 /* One evaluation (any mode) on each of nb DISTINCT handles -- the per-bin GPs of GaussianProcessEmulatorBins
  * (gaussian_process_bins.py:206-262), the leave-one-out refits of CrossCheck (sensitivity/cross_check.py:98-114),
  * optimiser restarts: problems the reference works through one after the other.  Equally shaped problems of
- * 14 or more 64-row tile rows share launches, up to 8 at a time: their Cholesky dependency chains are
+ * 14 or more 64-row tile rows share launches, up to 8 at a time (4 above 4096 rows): their Cholesky dependency chains are
  * interleaved in one factorisation launch (one chain cannot feed 148 SMs, several can) and every later stage is
  * one launch over the group; smaller problems are enqueued on the handles' own streams.  Results are
  * bit-identical to eb200_gp_eval_host on each handle.  Problem b reads p_host + b * p_stride and writes

@@ -190,8 +190,8 @@ def test_grid_prediction_in_device_memory_equals_host_path():
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,nb", [(4096, 5), (8176, 2)])
 def test_multi_handle_evaluation_equals_single_evaluations_at_full_size(n, nb):
-    """C2 size: groups of four share launches (five handles: one group plus a stand-alone evaluation); C4 size: a
-    factorisation of 128 tile rows keeps the device busy alone, the handles' own graphs are used.  Bit-identical."""
+    """Grouped evaluations (interleaved factorisations, one launch per later stage over the group) at C2 size, five
+    handles in one group, and at C4 size, a pair: bit-identical to each handle's stand-alone evaluation."""
     import torch
 
     from emulator_b200.device import evaluate_many, evaluate_many_device
