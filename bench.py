@@ -44,7 +44,8 @@ import time
 
 # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core,
 # and BLAS reads the variable when numpy is imported.
-if os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+# (only that arm: eight ranks of OUR arm with 16 BLAS threads each would fight over the host cores their optimisers need)
+if os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ and "reference" in sys.argv:
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
 
 import numpy as np
@@ -84,12 +85,14 @@ class ClockSampler(threading.Thread):
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        # (rank 0 only: every nvidia-smi call takes the driver's global lock for milliseconds -- eight ranks polling five
+        #  times a second stretched the launch -> synchronise round trips of the leave-one-out block several-fold)
+        self.index, self.samples, self._stop_evt, self.enabled = index, [], threading.Event(), enabled
 
     def run(self):
-        while not self._stop_evt.is_set():
+        while self.enabled and not self._stop_evt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -97,7 +100,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([f.strip() for f in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.5)
 
     def stop(self):
         self._stop_evt.set()
@@ -248,7 +251,7 @@ def block_sweep_c5(torch, td, world, rank, local, dev, peak_tflops, log2_rows):
     sobol.sweep_predict(emu, theta[: 1 << 12], ind, want_var=True)  # warm-up: factorisation, allocations, NCCL
     # host staging of the two result arrays pinned ahead of time -- what any sweep after a process's first one finds
     dist.pinned_pool.reserve((rows, SWEEP_IND), 2)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, enabled=rank == 0)
     sampler.start()
     (mean, var), ev_ms, wall_ms = timed_collective_region(torch, td, world, dev, lambda: sobol.sweep_predict(emu, theta, ind, want_var=True))
     clocks = sampler.stop()
@@ -302,20 +305,23 @@ def block_loo_c4(torch, td, world, rank, local, dev, peak_tflops, refits):
     spec, params, values = synthetic.make_config("C4")
     uids = list(values.model_values.keys())[:refits]
     cc = CrossCheck(device=local, leave_out=uids)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, enabled=rank == 0)
     sampler.start()
     _, ev_ms, wall_ms = timed_collective_region(torch, td, world, dev, lambda: cc.build_emulators(spec, params, values))
     clocks = sampler.stop()
     stats = cc.build_stats
     totals = dist.all_reduce_sum(np.array([stats["device_evaluations"], stats["combined_calls"], stats["refits"]], dtype=np.float64))
+    native_s = dist.all_reduce_sum(np.eye(world)[rank] * stats["combined_seconds"])
     per_rank = dist.all_reduce_sum(np.eye(world)[rank] * stats["refits"])
-    n_loo = len(next(iter(cc.cross_emulators.values())).independent_variables)
+    sizes = [len(v["independent"]) for v in values.model_values.values()]
+    n_loo = sum(sizes) - sizes[0]  # training rows of one leave-one-out refit
     flops = totals[0] * float(n_loo) ** 3
     out = {
         "workload": f"C4: CrossCheck.build_emulators, {refits} of the 512 leave-one-out refits at N={n_loo} (d=9), scipy BFGS each",
         "metric": "LOO refits/s", "value": refits / (ev_ms / 1e3), "unit": "refits/s", "seconds": ev_ms / 1e3, "wall_seconds": wall_ms / 1e3,
         "scaling": "strong", "n_gpus": world, "refits": refits, "refits_per_rank": [int(v) for v in per_rank],
         "device_evaluations": int(totals[0]), "combined_native_calls": int(totals[1]),
+        "seconds_inside_native_calls_per_rank": [round(float(v), 3) for v in native_s],
         "timed": "CrossCheck.build_emulators between barriers: array building, handle creation, BFGS (host), likelihood evaluations "
                  "(device, concurrent refits share launches), all-reduce of the optima; CUDA events on an idle stream = wall clock, max over ranks",
         "roofline": {"bound": "tensor", "flops": flops, "achieved": flops / ev_ms / 1e9 / world, "peak": peak_tflops, "unit": "TFLOP/s per GPU",
@@ -326,7 +332,7 @@ def block_loo_c4(torch, td, world, rank, local, dev, peak_tflops, refits):
     if world == 1 and rank == 0:
         from oracle import gp_oracle
 
-        emu = next(iter(cc.cross_emulators.values()))
+        emu = cc.cross_emulators.built_items()[0][1]
         x, y = emu.independent_variables.astype(np.float64), emu.dependent_variables.astype(np.float64)
         diag = gp_oracle.noise_diagonal(emu.dependent_variable_errors)
         # (not at the optimum, where the gradient is ~0 and a relative comparison means nothing)
@@ -343,7 +349,7 @@ def block_loo_c4(torch, td, world, rank, local, dev, peak_tflops, refits):
         grad = emu.emulator.grad_log_likelihood(emu.dependent_variables)
         out["parity_on_cpu_sample"] = {"lml_rel": float(abs(lml - ref_lml) / abs(ref_lml)),
                                        "grad_rel": float(np.max(np.abs(grad - ref_grad)) / np.max(np.abs(ref_grad)))}
-    for e in cc.cross_emulators.values():
+    for _, e in cc.cross_emulators.built_items():
         e.emulator.close()
     return out
 
@@ -401,7 +407,7 @@ def run_ours(args):
     for w in range(args.warmup):
         step_device(w)
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, enabled=rank == 0)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)

@@ -17,6 +17,7 @@ one parked, the last to arrive issues ONE native call for all of them and hands 
 from __future__ import annotations
 
 import threading
+import time
 from typing import List, Optional
 
 import numpy as np
@@ -40,6 +41,7 @@ class EvaluationCombiner:
         self._pending: List[dict] = []
         self.calls = 0        # native calls issued
         self.evaluations = 0  # evaluations they carried
+        self.seconds = 0.0    # wall time spent inside those calls (device work + launch + synchronisation)
 
     # ---- thread membership ------------------------------------------------------------------------
     def __enter__(self):
@@ -91,7 +93,9 @@ class EvaluationCombiner:
             keys = sorted({(r["grad"], r["problem"].d) for r in batch})
             for want_grad, d in keys:
                 part = [r for r in batch if r["grad"] == want_grad and r["problem"].d == d]
+                t0 = time.perf_counter()
                 lml, grad, info = evaluate_many([r["problem"] for r in part], np.array([r["p"] for r in part]), want_grad=want_grad)
+                self.seconds += time.perf_counter() - t0
                 for k, r in enumerate(part):
                     r["out"] = (float(lml[k]), grad[k].copy(), int(info[k]))
                 self.calls += 1

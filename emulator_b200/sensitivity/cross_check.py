@@ -13,6 +13,7 @@ the one simulation removed and the caller's container is never mutated.
 from __future__ import annotations
 
 import threading
+from collections.abc import Mapping
 from typing import Dict, Hashable, List, Optional
 
 import attr
@@ -24,6 +25,30 @@ from ..combine import EvaluationCombiner
 from ..emulators.base import build_gp, default_kernel, optimise_gps_lockstep
 from ..emulators.gaussian_process import GaussianProcessEmulator
 from ..emulators.gaussian_process_bins import GaussianProcessEmulatorBins
+
+
+class _LazyEmulators(Mapping):
+    """{uid: emulator} over `order`: entries this rank fitted are there, the others are built on first access."""
+
+    def __init__(self, order, built, build):
+        self._order, self._built, self._build = list(order), dict(built), build
+
+    def __getitem__(self, uid):
+        if uid not in self._built:
+            if uid not in self._order:
+                raise KeyError(uid)
+            self._built[uid] = self._build(uid)
+        return self._built[uid]
+
+    def __iter__(self):
+        return iter(self._order)
+
+    def __len__(self):
+        return len(self._order)
+
+    def built_items(self):
+        """The entries that exist already (no construction)."""
+        return list(self._built.items())
 
 
 def _without(model_values: ModelValues, uid) -> ModelValues:
@@ -88,7 +113,7 @@ class CrossCheck(object):
 
         if self.fit_mode not in ("scipy", "lockstep"):
             raise ValueError("fit_mode must be 'scipy' or 'lockstep'")
-        stats = {"combined_calls": 0, "combined_evaluations": 0}
+        stats = {"combined_calls": 0, "combined_evaluations": 0, "combined_seconds": 0.0}
         if self.fit_mode == "lockstep" and self.kernel is None and self.mean_model is None:
             # all refits of this rank advance together (emulator_b200/optimise.py): one batched device call
             # per optimiser round.  Every refit has the same shape (one simulation left out).
@@ -112,7 +137,8 @@ class CrossCheck(object):
             claimer = dist.WorkClaimer(count, dynamic=self.dynamic_claim)
             # shared kernel / mean-model objects are mutated by fit_model: those refits stay sequential
             threads = max(1, self.workers) if (self.kernel is None and self.mean_model is None) else 1
-            threads = min(threads, max(1, count))
+            # few refits per rank: fewer concurrent ones, so that the ranks that finish theirs early can still claim more
+            threads = min(threads, max(1, -(-count // (2 * dist.world_size()))))
             done, errors = [], []
             combiner = EvaluationCombiner(threads)
 
@@ -138,6 +164,7 @@ class CrossCheck(object):
             if errors:
                 raise errors[0]
             stats["combined_calls"], stats["combined_evaluations"] = combiner.calls, combiner.evaluations
+            stats["combined_seconds"] = combiner.seconds
         owner = np.zeros(count)
         for i, uid, emulator in done:
             fitted[i] = emulator.emulator.get_parameter_vector()
@@ -151,10 +178,10 @@ class CrossCheck(object):
         if not np.all(dist.all_reduce_sum(owner) == 1.0):
             raise RuntimeError("leave-one-out refits were not each done exactly once")
         self.cross_fit_parameters = fitted
-        # refits done on other ranks: rebuild the GP at the gathered optimum (no optimisation)
-        for i, uid in enumerate(self.leave_out_order):
-            if uid in emulators:
-                continue
+        # refits done on other ranks: the GP at the gathered optimum (no optimisation) is built when somebody asks for
+        # it -- constructing 500 emulator objects nobody may look at costs more host time than a refit's share of the GPU
+        def rebuild(uid):
+            i = self.leave_out_order.index(uid)
             emulator = GaussianProcessEmulator(kernel=self.kernel, mean_model=self.mean_model, device=self.device)
             emulator._build_arrays(model_specification, model_parameters, _without(model_values, uid))
             if emulator.kernel is None:
@@ -165,8 +192,9 @@ class CrossCheck(object):
             )
             gp.set_parameter_vector(fitted[i])
             emulator.emulator = gp
-            emulators[uid] = emulator
-        self.cross_emulators = {uid: emulators[uid] for uid in self.leave_out_order}
+            return emulator
+
+        self.cross_emulators = _LazyEmulators(self.leave_out_order, emulators, rebuild)
 
     def _require_built(self):
         if self.cross_emulators is None:

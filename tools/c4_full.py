@@ -36,7 +36,7 @@ dist.barrier(); t0 = time.perf_counter()
 total, per_model = cc.get_mean_squared()
 dist.barrier(); t_score = time.perf_counter() - t0
 out = {
-    "world": world, "refits": len(cc.leave_out_order), "n_per_refit": len(next(iter(cc.cross_emulators.values())).independent_variables),
+    "world": world, "refits": len(cc.leave_out_order), "n_per_refit": sum(len(v["independent"]) for v in values.model_values.values()) - 16,
     "build_emulators_s": t_build, "refits_per_s": len(cc.leave_out_order) / t_build, "device_evaluations": int(totals[0]),
     "combined_native_calls": int(totals[1]), "refits_per_rank": [int(v) for v in per_rank],
     "get_mean_squared_s": t_score, "mean_squared": float(total),
@@ -46,7 +46,7 @@ out = {
 }
 if dist.rank() == 0:
     print(json.dumps(out), flush=True)
-for e in cc.cross_emulators.values():
+for _, e in cc.cross_emulators.built_items():
     e.emulator.close()
 if world > 1:
     td.barrier()
