@@ -66,7 +66,7 @@ CONFIG = {
     "cache": "working set 2 x 134 MB per problem exceeds the 126 MB L2 (inputs larger than L2)",
 }
 SWEEP_LOG2_ROWS, SWEEP_IND = 20, 32
-LOO_REFITS = 32
+LOO_REFITS = 64  # 8 per rank on 8 GPUs (C4 itself: 64 per rank); BFGS takes 30 .. 100+ evaluations per refit, so fewer per rank mostly measures that spread
 
 
 def make_inputs(seed_offset=0):
