@@ -77,6 +77,7 @@ class CrossCheck(object):
     #: store) instead of i mod world: BFGS takes 60-80 evaluations per refit, a fixed split leaves ranks idle
     dynamic_claim: bool = attr.ib(default=True)
     lockstep_result = None
+    _fitted_here = frozenset()
     #: diagnostics of the last build: refits done by this rank, their device evaluations, combined native calls
     build_stats: Optional[Dict[str, float]] = None
 
@@ -198,43 +199,59 @@ class CrossCheck(object):
             emulator.emulator = gp
             return emulator
 
+        self._fitted_here = set(emulators.keys())
         self.cross_emulators = _LazyEmulators(self.leave_out_order, emulators, rebuild)
 
     def _require_built(self):
         if self.cross_emulators is None:
             raise AttributeError("You need to build the emulators before the prediction step.")
 
-    def build_mocked_model_values_original_independent(self) -> ModelValues:
+    def _leave_one_out_predictions(self, independent_of):
+        """
+        {uid: (emulated, variance)} of every left-out simulation at `independent_of(uid)`, each predicted by the
+        emulator that never saw it.  Sharded like the refits: every rank predicts with the emulators it fitted itself
+        (their device state is still there), the rows are collected with one all-reduce (each simulation has exactly
+        one owner, the others hold zeros), and nobody re-creates -- and re-factorises -- the emulators of other ranks.
+        """
         self._require_built()
+        order = self.leave_out_order
+        points = [np.asarray(independent_of(uid)) for uid in order]
+        width = max((len(x) for x in points), default=0)
+        table = np.zeros((len(order), 2, max(width, 1)))
+        mine = self._fitted_here if dist.world_size() > 1 else set(order)
+        for k, uid in enumerate(order):
+            if uid in mine and len(points[k]):
+                emulated, variance = self.cross_emulators[uid].predict_values(
+                    independent=points[k], model_parameters=self.model_parameters.model_parameters[uid]
+                )
+                table[k, 0, : len(points[k])], table[k, 1, : len(points[k])] = emulated, variance
+        table = dist.all_reduce_sum(table)
+        return {uid: (table[k, 0, : len(points[k])].copy(), table[k, 1, : len(points[k])].copy()) for k, uid in enumerate(order)}
+
+    def build_mocked_model_values_original_independent(self) -> ModelValues:
+        predicted = self._leave_one_out_predictions(lambda uid: self.model_values.model_values[uid]["independent"])
         out = {}
         for uid in self.leave_out_order:
-            independent = self.model_values[uid]["independent"]
-            emulated, variance = self.cross_emulators[uid].predict_values(
-                independent=independent, model_parameters=self.model_parameters[uid]
-            )
-            out[uid] = {"independent": independent, "dependent": emulated, "dependent_error": np.sqrt(variance)}
+            emulated, variance = predicted[uid]
+            out[uid] = {"independent": self.model_values.model_values[uid]["independent"], "dependent": emulated,
+                        "dependent_error": np.sqrt(variance)}
         return ModelValues(out)
 
     def build_mocked_model_values(self, emulate_at: np.array) -> ModelValues:
-        self._require_built()
+        predicted = self._leave_one_out_predictions(lambda uid: emulate_at)
         out = {}
         for uid in self.leave_out_order:
-            emulated, variance = self.cross_emulators[uid].predict_values(
-                independent=emulate_at, model_parameters=self.model_parameters[uid]
-            )
+            emulated, variance = predicted[uid]
             out[uid] = {"independent": emulate_at, "dependent": emulated, "dependent_error": np.sqrt(variance)}
         return ModelValues(out)
 
     def get_mean_squared(self, use_dependent_error: bool = False, use_y_as_error: bool = False,
                          use_squared_difference: bool = True):
-        self._require_built()
+        predicted = self._leave_one_out_predictions(lambda uid: self.model_values.model_values[uid]["independent"])
         per_model, everything = {}, []
-        for uid in self.cross_emulators.keys():
-            x_model = self.model_values.model_values[uid]["independent"]
+        for uid in self.leave_out_order:
             y_model = self.model_values.model_values[uid]["dependent"]
-            emulated, _ = self.cross_emulators[uid].predict_values(
-                independent=x_model, model_parameters=self.model_parameters.model_parameters[uid]
-            )
+            emulated, _ = predicted[uid]
             if use_y_as_error:
                 weight = y_model
             else:
