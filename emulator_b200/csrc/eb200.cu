@@ -91,7 +91,6 @@ cudaError_t set_gemm_attr() {
 struct eb200_gp {
   int device = 0, n = 0, d = 0, dp = 0, np = 0, nt = 0, nT = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t batch_done = nullptr;  // batched multi-handle evaluations: the shared factorisation launch has finished
   double *A = nullptr, *W = nullptr, *X = nullptr, *noise = nullptr, *r = nullptr, *z = nullptr, *alpha = nullptr;
   double *logdet_part = nullptr, *tpartial = nullptr, *trace_partial = nullptr;
   double *p_dev = nullptr, *out_dev = nullptr;
@@ -141,14 +140,12 @@ struct eb200_gp {
   int launches_grad = 0, launches_lml = 0, launches_val = 0;
   bool factor_valid = false;
   // prediction scratch
-  double *T_dev = nullptr, *mu_dev = nullptr, *var_dev = nullptr, *rowss = nullptr, *T_in = nullptr;
+  double *mu_dev = nullptr, *var_dev = nullptr, *T_in = nullptr;  // staging of the host-pointer predict (np rows)
   double *h_pred = nullptr;  // pinned staging for predict (np * (d + 2) doubles)
   char *arena = nullptr, *pinned = nullptr;  // one device / one pinned allocation behind the small arrays above
   // grow-only device buffers of the grid prediction (parameter rows, independent values, results)
   double *grid_theta = nullptr, *grid_ind = nullptr, *grid_mu = nullptr, *grid_var = nullptr, *grid_e1 = nullptr;
   size_t grid_theta_cap = 0, grid_ind_cap = 0, grid_out_cap = 0, grid_e1_cap = 0;
-  TileTask* var_tasks = nullptr;
-  int var_tasks_mt = -1, var_tasks_cnt = 0;
   // Grow-only scratch of predictions with more query rows than training rows (sweeps): K* rows, padded query
   // rows, per-tile row sums and the variance GEMM's task list for chunks of up to `rows` query rows.  Smaller
   // predictions use the handle's resident buffers (K* goes to matrix A, dead once X = L^-1 exists).
@@ -541,9 +538,6 @@ int ensure_predict_scratch(eb200_gp* h, int rows, int want_var, bool need_ks = t
   return 0;
 }
 
-// Padded query rows of the next chunk go here.
-double* predict_rows_buffer(eb200_gp* h, int) { return h->big.T; }
-
 // (grid: the chunk is rows [grid->q0, grid->q0 + mc) of a prediction grid, whose K* rows come from the factorised
 //  form of the kernel -- predict_grid_mean_kernel -- instead of from explicit query rows)
 struct GridChunk {
@@ -554,7 +548,7 @@ struct GridChunk {
   bool fused;  // the variance kernel rebuilds K* = E1 * E2 in shared memory (no K* rows in global memory)
 };
 
-// Predict one chunk (mc <= chunk_rows query rows) whose padded coordinates already sit in predict_rows_buffer().
+// Predict one chunk (mc <= chunk_rows query rows) whose padded coordinates already sit in the scratch's row buffer (big.T).
 int predict_chunk(eb200_gp* h, int chunk_rows, int mc, int want_var, double* mu_dev, double* var_dev, cudaStream_t st,
                   const GridChunk* grid = nullptr) {
   const int np = h->np;
@@ -626,7 +620,7 @@ int predict_grid_impl(eb200_gp* h, size_t n_theta, const double* theta_dev, int 
     }
     return 0;
   }
-  double* rows = predict_rows_buffer(h, chunk);
+  double* rows = h->big.T;
   for (size_t q0 = 0; q0 < m; q0 += chunk) {
     const int mc = (int)std::min<size_t>(chunk, m - q0);
     const size_t tot = (size_t)mc * h->dp;
@@ -691,7 +685,6 @@ static int create_impl(eb200_gp* h, int device, int n, int d, const double* x_ho
   const int np = h->np, dp = h->dp;
   const size_t mat = (size_t)np * np * sizeof(double);
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&h->batch_done, cudaEventDisableTiming));
   const size_t mat_a = mat + (size_t)TB * np * sizeof(double);  // + the residual tile row of value-only evaluations
   CK(cudaMalloc(&h->A, mat_a));
   CK(cudaMalloc(&h->W, mat));
@@ -711,12 +704,9 @@ static int create_impl(eb200_gp* h, int device, int n, int d, const double* x_ho
         {(void**)&h->p_dev, (MAXD + 1) * sizeof(double)},
         {(void**)&h->out_dev, (MAXD + 8) * sizeof(double)},
         {(void**)&h->kp, sizeof(KernelParams)},
-        {(void**)&h->T_dev, (size_t)np * dp * sizeof(double)},
         {(void**)&h->T_in, (size_t)np * d * sizeof(double)},
         {(void**)&h->mu_dev, np * sizeof(double)},
         {(void**)&h->var_dev, np * sizeof(double)},
-        {(void**)&h->rowss, (size_t)h->nT * np * sizeof(double)},
-        {(void**)&h->var_tasks, (size_t)h->nT * h->nT * sizeof(TileTask)},
         {(void**)&h->rdiag, (size_t)np * sizeof(double)},
     };
     auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
@@ -908,7 +898,6 @@ int eb200_gp_destroy(eb200_gp* h) {
   if (h->group.out_dev) cudaFree(h->group.out_dev);
   if (h->group.h_stage) cudaFreeHost(h->group.h_stage);
   if (h->pinned) cudaFreeHost(h->pinned);
-  if (h->batch_done) cudaEventDestroy(h->batch_done);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -1261,7 +1250,7 @@ int eb200_gp_predict_device(eb200_gp* h, int m, const double* t_dev, int want_va
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   const int chunk = predict_chunk_rows(h, (size_t)std::max(m, 0));
   if (ensure_predict_scratch(h, chunk, want_var)) return 1;
-  double* rows = predict_rows_buffer(h, chunk);
+  double* rows = h->big.T;
   for (int q0 = 0; q0 < m; q0 += chunk) {
     const int mc = std::min(chunk, m - q0);
     const size_t tot = (size_t)mc * h->dp;

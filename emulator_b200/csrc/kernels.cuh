@@ -2,8 +2,9 @@
 //
 // Matrix storage: two row-major (Np x Np) fp64 buffers per GP handle, Np = N rounded up to a
 // multiple of 128; rows/columns >= N carry the identity so every kernel works on whole tiles.
-// `A` receives the Cholesky factor L (factor_dataflow.cuh) and is reused as K* scratch by
-// prediction; `W` receives X = L^-1, which the gradient and the predictive variance consume.
+// `A` receives the Cholesky factor L (factor_dataflow.cuh); `W` receives the inverse in TRANSPOSED form,
+// Y = L^-T (upper triangle), which the gradient consumes as it is (K^-1 = Y Y^T); before the first variance
+// prediction that follows an evaluation X = L^-1 is written row-major into `A` (L is dead by then).
 #pragma once
 #include <math.h>
 #include "engine.cuh"
