@@ -38,18 +38,32 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return done != 0;
+}
+// Wait for a phase of the barrier.  A stage that never completes (a transfer that cannot be made) would hang the
+// launch: after 20 s without progress the kernel traps instead, which the host sees as a launch failure.
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned spins = 0;
+  unsigned long long t0 = 0ull;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xfffffu) == 0u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0ull) t0 = now;
+      else if (now - t0 > 20ull * 1000ull * 1000ull * 1000ull) __trap();
+    }
+  }
 }
 // 2-D tiled TMA load: box (16 doubles of k, 128 rows) at coordinates (k0, row0) -> dst, completion on `bar`.
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int k0, int row0, unsigned long long* bar) {

@@ -222,27 +222,37 @@ class PinnedPool:
         self.keep_bytes = keep_bytes
 
     @staticmethod
-    def _free(base) -> bool:
-        """Nobody outside the pool shares the buffer's storage (views, numpy arrays made from them, slices of those
-        all hold the storage).  Without torch's storage use count the answer is "in use": nothing is ever recycled."""
+    def _use_count(base):
+        """How many tensors share the buffer's storage (views, numpy arrays made from them, slices of those all hold
+        the storage), or None when this torch build does not say."""
         import torch
 
         try:
-            # (the base tensor and the temporary storage handle account for 2)
-            return torch._C._storage_Use_Count(base.untyped_storage()._cdata) <= 2
+            return int(torch._C._storage_Use_Count(base.untyped_storage()._cdata))
         except Exception:  # pragma: no cover - private API moved
-            return False
+            return None
+
+    @classmethod
+    def _free(cls, base) -> bool:
+        count = cls._use_count(base)
+        return count is not None and count <= 2  # the base tensor and the temporary storage handle
 
     def take(self, shape):
         import torch
 
         need = int(np.prod(shape))
+        pinned = torch.cuda.is_available()
+        probe = torch.empty(1, dtype=torch.float64)
+        if self._use_count(probe) is None:
+            # no way to tell when a buffer is free again: hand out fresh ones and keep no reference (nothing is recycled,
+            # nothing accumulates)
+            return torch.empty(need, dtype=torch.float64, pin_memory=pinned).view(*shape)
         best = None
         for base in self._entries:
             if base.numel() >= need and (best is None or base.numel() < best.numel()) and self._free(base):
                 best = base
         if best is None:
-            best = torch.empty(need, dtype=torch.float64, pin_memory=torch.cuda.is_available())
+            best = torch.empty(need, dtype=torch.float64, pin_memory=pinned)
             self._entries.append(best)
             if sum(e.numel() * 8 for e in self._entries) > self.keep_bytes:
                 # forget free buffers (they are unpinned when collected)
