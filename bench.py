@@ -85,8 +85,9 @@ class ClockSampler(threading.Thread):
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, enabled=True):
+    def __init__(self, index, enabled=True, interval=0.2):
         super().__init__(daemon=True)
+        self.interval = interval
         # (rank 0 only: every nvidia-smi call takes the driver's global lock for milliseconds -- eight ranks polling five
         #  times a second stretched the launch -> synchronise round trips of the leave-one-out block several-fold)
         self.index, self.samples, self._stop_evt, self.enabled = index, [], threading.Event(), enabled
@@ -100,7 +101,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([f.strip() for f in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.5)
+            self._stop_evt.wait(self.interval)
 
     def stop(self):
         self._stop_evt.set()
@@ -251,7 +252,7 @@ def block_sweep_c5(torch, td, world, rank, local, dev, peak_tflops, log2_rows):
     sobol.sweep_predict(emu, theta[: 1 << 12], ind, want_var=True)  # warm-up: factorisation, allocations, NCCL
     # host staging of the two result arrays pinned ahead of time -- what any sweep after a process's first one finds
     dist.pinned_pool.reserve((rows, SWEEP_IND), 2)
-    sampler = ClockSampler(local, enabled=rank == 0)
+    sampler = ClockSampler(local, enabled=rank == 0, interval=0.2 if world == 1 else 0.5)
     sampler.start()
     (mean, var), ev_ms, wall_ms = timed_collective_region(torch, td, world, dev, lambda: sobol.sweep_predict(emu, theta, ind, want_var=True))
     clocks = sampler.stop()
@@ -305,7 +306,7 @@ def block_loo_c4(torch, td, world, rank, local, dev, peak_tflops, refits):
     spec, params, values = synthetic.make_config("C4")
     uids = list(values.model_values.keys())[:refits]
     cc = CrossCheck(device=local, leave_out=uids)
-    sampler = ClockSampler(local, enabled=rank == 0)
+    sampler = ClockSampler(local, enabled=rank == 0, interval=0.2 if world == 1 else 0.5)
     sampler.start()
     _, ev_ms, wall_ms = timed_collective_region(torch, td, world, dev, lambda: cc.build_emulators(spec, params, values))
     clocks = sampler.stop()
@@ -407,7 +408,7 @@ def run_ours(args):
     for w in range(args.warmup):
         step_device(w)
     barrier()
-    sampler = ClockSampler(local, enabled=rank == 0)
+    sampler = ClockSampler(local, enabled=rank == 0, interval=0.2 if world == 1 else 0.5)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
