@@ -276,3 +276,44 @@ def test_pinned_pool_recycles_a_buffer_only_when_nothing_refers_to_it():
     del v
     pool.reserve((100,), 2)
     assert sum(e.numel() >= 100 for e in pool._entries) >= 2
+
+
+# ---- leave-one-out post-processing ---------------------------------------------------------------------------------------
+def test_lazy_emulators_build_on_first_access_only():
+    from emulator_b200.sensitivity.cross_check import _LazyEmulators
+
+    built = []
+
+    def build(uid):
+        built.append(uid)
+        return f"emulator-{uid}"
+
+    lazy = _LazyEmulators(["a", "b", "c"], {"b": "fitted-b"}, build)
+    assert list(lazy.keys()) == ["a", "b", "c"] and len(lazy) == 3 and built == []
+    assert lazy["b"] == "fitted-b" and built == []
+    assert lazy["c"] == "emulator-c" and lazy["c"] == "emulator-c" and built == ["c"]  # built once
+    assert [uid for uid, _ in lazy.built_items()] == ["b", "c"]
+    with pytest.raises(KeyError):
+        lazy["nope"]
+    assert dict(lazy.items())["a"] == "emulator-a" and built == ["c", "a"]
+
+
+def test_leave_one_out_predictions_with_ragged_independents(oracle_backend):
+    """Simulations with different numbers of points: the sharded collection pads per simulation and cuts back."""
+    spec, params, values = synthetic.make_model(2, 6, 5, seed=34)
+    raw = {uid: dict(v) for uid, v in values.model_values.items()}
+    first = next(iter(raw))
+    raw[first] = {k: np.asarray(v)[:3] for k, v in raw[first].items()}  # one simulation has only three points
+    from emulator_b200.backend import ModelValues
+
+    ragged = ModelValues(model_values=raw)
+    cc = CrossCheck(workers=2)
+    cc.build_emulators(spec, params, ragged)
+    total, per_model = cc.get_mean_squared()
+    assert len(per_model[first]) == 3 and all(len(per_model[uid]) == 5 for uid in raw if uid != first)
+    mocked = cc.build_mocked_model_values_original_independent()
+    for uid in raw:
+        direct, var = cc.cross_emulators[uid].predict_values(raw[uid]["independent"], params.model_parameters[uid])
+        assert np.array_equal(mocked.model_values[uid]["dependent"], direct)
+        assert np.array_equal(mocked.model_values[uid]["dependent_error"], np.sqrt(var))
+    assert np.isclose(total, np.mean(np.concatenate([per_model[uid] for uid in raw])))
