@@ -13,7 +13,7 @@ Rows are split contiguously over ranks and all-gathered once.
 
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict
 
 import numpy as np
 from scipy.stats import qmc
