@@ -146,6 +146,48 @@ def golden_cross_check(name, n_par, sims, bins, seed):
     print(name, "mean squared =", total)
 
 
+def golden_multi(name, n_par, sims, bins, seed):
+    """The reference's multi-region emulator (emulators/multi_gaussian_process.py:163-330): one GP per region of the
+    independent axis, fitted one after the other, blended linearly where consecutive regions overlap.  Two layouts:
+    regions that overlap (means are pinned everywhere; inside the overlap the reference takes the right-hand ERROR
+    from the left emulator's output list, :312-314 -- recorded, and next to it the per-region outputs the documented
+    formula needs) and regions that only touch."""
+    spec, params, values = synthetic.make_model(n_par, sims, bins, seed=seed)
+    rspec, rparams, rvalues = to_reference(spec, params, values)
+    lo = np.array(spec.parameter_limits)[:, 0]
+    theta = {nm: float(lo[i]) + 0.33 + 0.06 * i for i, nm in enumerate(spec.parameter_names)}
+    xs = values.model_values[next(iter(values.model_values))]["independent"]
+    query = np.sort(np.concatenate([xs, 0.5 * (xs[1:] + xs[:-1])]))
+    out = dict(n_par=n_par, sims=sims, bins=bins, seed=seed, query=query,
+               theta=np.array([theta[nm] for nm in spec.parameter_names]))
+    for label, regions in (("overlap", [[None, 0.62], [0.38, None]]), ("touch", [[None, 0.5], [0.5, None]]),
+                           ("three", [[None, 0.45], [0.3, 0.8], [0.65, None]])):
+        emu = RefMulti(independent_regions=regions)
+        emu.fit_model(rspec, rparams, rvalues)
+        # (points that fall in no region -- exactly on a touching boundary -- are left out: the reference fails there)
+        inside = np.zeros(len(query), dtype=bool)
+        for low, high in regions:
+            inside |= np.logical_and(query > low if low is not None else True, query < high if high is not None else True)
+        q = query[inside]
+        mu, err = emu.predict_values(q, theta)
+        out[label + "_regions"] = np.array([[np.nan if v is None else v for v in r] for r in regions])
+        out[label + "_query"] = q
+        out[label + "_mu"] = mu
+        out[label + "_err"] = err
+        out[label + "_p_fit"] = np.array([e.emulator.get_parameter_vector() for e in emu.emulators])
+        out[label + "_rows"] = np.array([len(e.dependent_variables) for e in emu.emulators])
+        for index, e in enumerate(emu.emulators):  # each region's own prediction over the points it covers
+            low, high = regions[index]
+            mask = np.logical_and(q > low if low is not None else True, q < high if high is not None else True)
+            m, v = e.predict_values(q[mask], theta)
+            full_m, full_v = np.full(len(q), np.nan), np.full(len(q), np.nan)
+            full_m[mask], full_v[mask] = m, v
+            out[f"{label}_region{index}_mu"] = full_m
+            out[f"{label}_region{index}_err"] = full_v
+    np.savez(os.path.join(HERE, name + ".npz"), **out)
+    print(name, {k: out[k] for k in ("overlap_rows", "touch_rows", "three_rows")})
+
+
 class MinimizeRecorder:
     """Stands in for `scipy.optimize.minimize` inside a reference module (they do `from scipy.optimize import minimize`):
     the same call plus a callback that records the iterates x_k -- a callback does not change what BFGS does."""
@@ -297,6 +339,9 @@ def golden_penalties(name):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "penalties":
         golden_penalties("penalties")
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "multi":
+        golden_multi("multi_regions", 2, 14, 12, seed=108)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "round2":  # the vectors added in round 2 only
         golden_trajectory("trajectory_c1", 2, 50, 20, seed=1235)       # BASELINE configuration C1: N = 1000, d = 3

@@ -14,7 +14,7 @@ from emulator_b200.emulators import (
 )
 from emulator_b200.mean_models import LinearMeanModel, OffsetMeanModel
 from emulator_b200.sensitivity import CrossCheck, sobol_indices
-from test_host_logic import fixture_data, golden_inputs, load, theta_dict
+from test_host_logic import _regions, check_multi_against_reference, fixture_data, golden_inputs, load, theta_dict
 
 pytestmark = pytest.mark.gpu
 
@@ -55,6 +55,23 @@ def test_gpe_fit_and_predict_match_reference_golden(name, mean_model):
     amp = len(g["p_fit"][1:]) * np.exp(g["p_fit"][0])
     assert np.max(np.abs(var - g["var"])) <= 1e-9 * amp
     assert np.array_equal(emu.predict_values_no_error(g["query_x"], theta_dict(spec, g)), mu)
+
+
+@pytest.mark.parametrize("label", ["overlap", "three"])
+def test_multi_region_emulator_matches_reference_golden(label):
+    """The reference's per-region loop (multi_gaussian_process.py:167-177) on the device: every region's GP reaches
+    the reference's optimum at the optimiser's resolution; predictions are compared at the reference's optima."""
+    g = load("multi_regions")
+    spec, params, values = golden_inputs(g)
+    emu = MultipleGaussianProcessEmulator(independent_regions=_regions(g, label))
+    emu.fit_model(spec, params, values)
+    for region, p_ref in zip(emu.emulators, g[label + "_p_fit"]):
+        assert np.allclose(region.fit_result.x, p_ref, rtol=1e-3, atol=1e-3)
+        region.emulator.set_parameter_vector(p_ref)
+        lml_at_golden = region.emulator.log_likelihood(region.dependent_variables)
+        assert abs(-region.fit_result.fun - lml_at_golden) <= 1e-7 * abs(lml_at_golden)
+    amp = max(len(p) - 1 for p in g[label + "_p_fit"]) * np.exp(np.max(g[label + "_p_fit"][:, 0]))
+    assert check_multi_against_reference(g, label, emu, theta_dict(spec, g), 1e-9, 1e-9 * amp) > 0
 
 
 def test_bins_emulator_matches_reference_golden():

@@ -146,6 +146,47 @@ def test_multi_region_blends_linearly(oracle_backend):
     assert np.all(np.isfinite(err))
 
 
+def _regions(g, label):
+    return [[None if np.isnan(v) else float(v) for v in row] for row in g[label + "_regions"]]
+
+
+def check_multi_against_reference(g, label, emu, theta, mean_tol, err_tol):
+    """Predictions of a fitted multi-region emulator against what the reference's own code produced (golden
+    `multi_regions`): means everywhere; errors wherever one region answers; inside an overlap the documented
+    weighted square sum of BOTH regions' errors, formed here from the reference's per-region outputs (the
+    reference itself reads the right-hand error from the left emulator there, multi_gaussian_process.py:312-314)."""
+    q = g[label + "_query"]
+    mu, err = emu.predict_values(q, theta)
+    scale = np.max(np.abs(g[label + "_mu"]))
+    assert np.max(np.abs(mu - g[label + "_mu"])) <= mean_tol * scale
+    assert np.max(np.abs(emu.predict_values_no_error(q, theta) - g[label + "_mu"])) <= mean_tol * scale
+    regions = _regions(g, label)
+    covered = np.array([~np.isnan(g[f"{label}_region{i}_mu"]) for i in range(len(regions))])
+    single = covered.sum(axis=0) == 1
+    assert single.any()
+    assert np.max(np.abs(err[single] - g[label + "_err"][single])) <= err_tol
+    for i in np.where(~single)[0]:
+        left, right = np.where(covered[:, i])[0]
+        low, high = regions[right][0], regions[left][1]
+        wl, wr = (high - q[i]) / (high - low), (q[i] - low) / (high - low)
+        el, er = g[f"{label}_region{left}_err"][i], g[f"{label}_region{right}_err"][i]
+        assert err[i] == pytest.approx(np.sqrt(wl * el * el + wr * er * er), abs=err_tol)
+    return int((~single).sum())
+
+
+@pytest.mark.parametrize("label", ["overlap", "touch", "three"])
+def test_multi_region_matches_reference_flow(oracle_backend, label):
+    g = load("multi_regions")
+    spec, params, values = golden_inputs(g)
+    emu = MultipleGaussianProcessEmulator(independent_regions=_regions(g, label))
+    emu.fit_model(spec, params, values)
+    assert [len(e.dependent_variables) for e in emu.emulators] == list(g[label + "_rows"])
+    got = np.array([e.emulator.get_parameter_vector() for e in emu.emulators])
+    assert np.allclose(got, g[label + "_p_fit"], rtol=1e-9, atol=1e-9)
+    blended = check_multi_against_reference(g, label, emu, theta_dict(spec, g), 1e-9, 1e-10)
+    assert (blended > 0) == (label != "touch")
+
+
 def test_mcmc_emulator_runs_and_is_seeded(oracle_backend):
     spec, params, values = fixture_data(6)
     a = GaussianProcessEmulatorMCMC(burn_in_steps=2, mcmc_steps=3, walkers=10, seed=4)
