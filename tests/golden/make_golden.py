@@ -188,6 +188,59 @@ def golden_multi(name, n_par, sims, bins, seed):
     print(name, {k: out[k] for k in ("overlap_rows", "touch_rows", "three_rows")})
 
 
+def golden_mocking(name, n_par, sims, bins, seed):
+    """The reference's prediction sweeps (mocking/__init__.py:17-97 mock_hypercube, :100-200 mock_sweep): one
+    `predict_values` call per parameter row, at every independent value of the training data."""
+    from swiftemulator.mocking import mock_hypercube as ref_hypercube, mock_sweep as ref_sweep
+
+    spec, params, values = synthetic.make_model(n_par, sims, bins, seed=seed)
+    rspec, rparams, rvalues = to_reference(spec, params, values)
+    emu = RefGPE()
+    emu.fit_model(rspec, rparams, rvalues)
+    np.random.seed(seed)  # the reference draws its cube from numpy's global generator (design/random.py:53)
+    cube_values, cube_parameters = ref_hypercube(emu, rspec, 9)
+    lo, hi = np.array(spec.parameter_limits)[:, 0], np.array(spec.parameter_limits)[:, 1]
+    center = {nm: float(lo[i] + (0.4 + 0.1 * i) * (hi[i] - lo[i])) for i, nm in enumerate(spec.parameter_names)}
+    swept = spec.parameter_names[1]
+    sweep_values, sweep_parameters = ref_sweep(emu, rspec, 7, swept, center)
+
+    def pack(vals, pars):
+        uids = list(pars.model_parameters.keys())
+        return (np.array([[pars.model_parameters[u][nm] for nm in spec.parameter_names] for u in uids]),
+                np.array([vals.model_values[u]["dependent"] for u in uids]),
+                np.array([vals.model_values[u]["dependent_error"] for u in uids]),
+                vals.model_values[uids[0]]["independent"], np.array(uids))
+
+    cube = pack(cube_values, cube_parameters)
+    sweep = pack(sweep_values, sweep_parameters)
+    np.savez(os.path.join(HERE, name + ".npz"), n_par=n_par, sims=sims, bins=bins, seed=seed,
+             p_fit=emu.emulator.get_parameter_vector(), center=np.array([center[nm] for nm in spec.parameter_names]),
+             swept=swept, cube_theta=cube[0], cube_mu=cube[1], cube_err=cube[2], independent=cube[3], cube_uids=cube[4],
+             sweep_theta=sweep[0], sweep_mu=sweep[1], sweep_err=sweep[2], sweep_uids=sweep[4])
+    print(name, cube[1].shape, sweep[1].shape)
+
+
+def golden_cross_check_bins(name, n_par, sims, bins, seed):
+    """The reference's leave-one-out loop over per-bin emulators (sensitivity/cross_check_bins.py:94-109): one
+    GaussianProcessEmulatorBins per left-out simulation.  (Its post-processing is broken in the reference --
+    :142-148, :224-229 unpack three values from a two-value predict -- so only the fits are pinned.)"""
+    from swiftemulator.sensitivity.cross_check_bins import CrossCheckBins as RefCrossCheckBins
+
+    spec, params, values = synthetic.make_model(n_par, sims, bins, seed=seed)
+    rspec, rparams, rvalues = to_reference(spec, params, values)
+    cc = RefCrossCheckBins()
+    cc.build_emulators(rspec, rparams, rvalues)
+    p_fit = np.array([[gp.get_parameter_vector() for gp in cc.cross_emulators[uid].bin_gaussian_process]
+                      for uid in cc.leave_out_order])
+    theta = {nm: 0.37 + 0.09 * i for i, nm in enumerate(spec.parameter_names)}
+    centers = np.array(cc.cross_emulators[cc.leave_out_order[0]].bin_centers)
+    pred = np.array([cc.cross_emulators[uid].predict_values(centers, theta) for uid in cc.leave_out_order])
+    np.savez(os.path.join(HERE, name + ".npz"), n_par=n_par, sims=sims, bins=bins, seed=seed, p_fit=p_fit,
+             order=np.array(cc.leave_out_order), centers=centers, theta=np.array([theta[nm] for nm in spec.parameter_names]),
+             mu=pred[:, 0], var=pred[:, 1])
+    print(name, p_fit.shape)
+
+
 class MinimizeRecorder:
     """Stands in for `scipy.optimize.minimize` inside a reference module (they do `from scipy.optimize import minimize`):
     the same call plus a callback that records the iterates x_k -- a callback does not change what BFGS does."""
@@ -339,6 +392,12 @@ def golden_penalties(name):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "penalties":
         golden_penalties("penalties")
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "cross_check_bins":
+        golden_cross_check_bins("cross_check_bins_small", 2, 9, 4, seed=110)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "mocking":
+        golden_mocking("mocking_small", 3, 16, 9, seed=109)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "multi":
         golden_multi("multi_regions", 2, 14, 12, seed=108)

@@ -13,8 +13,8 @@ from emulator_b200.emulators import (
     MultipleGaussianProcessEmulator,
 )
 from emulator_b200.mean_models import LinearMeanModel, OffsetMeanModel
-from emulator_b200.sensitivity import CrossCheck, sobol_indices
-from test_host_logic import _regions, check_multi_against_reference, fixture_data, golden_inputs, load, theta_dict
+from emulator_b200.sensitivity import CrossCheck, CrossCheckBins, sobol_indices
+from test_host_logic import _regions, check_mocking_against_reference, check_multi_against_reference, fixture_data, golden_inputs, load, theta_dict
 
 pytestmark = pytest.mark.gpu
 
@@ -74,6 +74,19 @@ def test_multi_region_emulator_matches_reference_golden(label):
     assert check_multi_against_reference(g, label, emu, theta_dict(spec, g), 1e-9, 1e-9 * amp) > 0
 
 
+def test_mocking_matches_reference_golden():
+    """The reference's prediction sweeps on the device: one grid prediction (query rows never formed, K* rebuilt inside
+    the variance GEMM) against the reference's one-`predict_values`-call-per-row loops, at the reference's optimum."""
+    g = load("mocking_small")
+    spec, params, values = golden_inputs(g)
+    emu = GaussianProcessEmulator()
+    emu.fit_model(spec, params, values)
+    assert np.allclose(emu.fit_result.x, g["p_fit"], rtol=1e-3, atol=1e-3)
+    emu.emulator.set_parameter_vector(g["p_fit"])
+    amp = (len(g["p_fit"]) - 1) * np.exp(g["p_fit"][0])
+    check_mocking_against_reference(g, emu, spec, 1e-9, 1e-9 * amp)
+
+
 def test_bins_emulator_matches_reference_golden():
     g = load("bins_small")
     spec, params, values = golden_inputs(g)
@@ -108,6 +121,27 @@ def test_cross_check_matches_reference_golden():
     total, per_model = cc.get_mean_squared()
     assert np.allclose(cc.cross_fit_parameters, g["p_fit"], rtol=2e-3, atol=2e-3)
     assert total == pytest.approx(float(g["total"]), rel=5e-3)
+
+
+def test_cross_check_bins_matches_reference_golden():
+    """Leave-one-out over per-bin emulators on the device (cross_check_bins.py:94-109): 9 x 4 small GPs, optima at the
+    optimiser's resolution, predictions compared at the reference's optima."""
+    g = load("cross_check_bins_small")
+    spec, params, values = golden_inputs(g)
+    cc = CrossCheckBins()
+    cc.build_emulators(spec, params, values)
+    assert list(cc.leave_out_order) == list(g["order"])
+    theta = theta_dict(spec, g)
+    for k, uid in enumerate(cc.leave_out_order):
+        emulator = cc.cross_emulators[uid]
+        got = np.array([gp.get_parameter_vector() for gp in emulator.bin_gaussian_process])
+        assert np.allclose(got, g["p_fit"][k], rtol=2e-3, atol=2e-3)
+        for gp, p_ref in zip(emulator.bin_gaussian_process, g["p_fit"][k]):
+            gp.set_parameter_vector(p_ref)
+        mu, var = emulator.predict_values(g["centers"], theta)
+        amp = np.max((g["p_fit"].shape[2] - 1) * np.exp(g["p_fit"][k][:, 0]))
+        assert np.max(np.abs(mu - g["mu"][k])) <= 1e-9 * np.max(np.abs(g["mu"]))
+        assert np.max(np.abs(var - g["var"][k])) <= 1e-9 * amp
 
 
 def test_reference_smoke_tests_shape():

@@ -187,6 +187,35 @@ def test_multi_region_matches_reference_flow(oracle_backend, label):
     assert (blended > 0) == (label != "touch")
 
 
+def check_mocking_against_reference(g, emu, spec, mean_tol, err_tol):
+    """`mock_hypercube` / `mock_sweep` over a fitted emulator against what the reference's own loops produced
+    (golden `mocking_small`; mocking/__init__.py:84-95, :187-198): same unique identifiers, same parameter rows (the
+    reference's cube comes from numpy's global generator, seeded the same here), same predictions."""
+    np.random.seed(int(g["seed"]))
+    cube_values, cube_parameters = mocking.mock_hypercube(emu, spec, 9)
+    center = {name: float(v) for name, v in zip(spec.parameter_names, g["center"])}
+    sweep_values, sweep_parameters = mocking.mock_sweep(emu, spec, 7, str(g["swept"]), center)
+    for label, vals, pars in (("cube", cube_values, cube_parameters), ("sweep", sweep_values, sweep_parameters)):
+        uids = list(pars.model_parameters.keys())
+        assert uids == [str(u) for u in g[label + "_uids"]]
+        theta = np.array([[pars.model_parameters[u][name] for name in spec.parameter_names] for u in uids])
+        assert np.array_equal(theta, g[label + "_theta"])
+        mu = np.array([vals.model_values[u]["dependent"] for u in uids])
+        err = np.array([vals.model_values[u]["dependent_error"] for u in uids])
+        assert np.array_equal(vals.model_values[uids[0]]["independent"], g["independent"])
+        assert np.max(np.abs(mu - g[label + "_mu"])) <= mean_tol * np.max(np.abs(g[label + "_mu"]))
+        assert np.max(np.abs(err - g[label + "_err"])) <= err_tol
+
+
+def test_mocking_matches_reference_flow(oracle_backend):
+    g = load("mocking_small")
+    spec, params, values = golden_inputs(g)
+    emu = GaussianProcessEmulator()
+    emu.fit_model(spec, params, values)
+    assert np.allclose(emu.emulator.get_parameter_vector(), g["p_fit"], rtol=1e-9, atol=1e-9)
+    check_mocking_against_reference(g, emu, spec, 1e-8, 1e-9)
+
+
 def test_mcmc_emulator_runs_and_is_seeded(oracle_backend):
     spec, params, values = fixture_data(6)
     a = GaussianProcessEmulatorMCMC(burn_in_steps=2, mcmc_steps=3, walkers=10, seed=4)
@@ -281,6 +310,23 @@ def test_cross_check_bins_builds_and_scores(oracle_backend):
     assert np.isfinite(total) and set(per_model) == set(values.keys())
     with pytest.raises(AttributeError):
         CrossCheckBins().get_mean_squared()
+
+
+def test_cross_check_bins_matches_reference_flow(oracle_backend):
+    """The fits of the reference's CrossCheckBins.build_emulators (cross_check_bins.py:94-109; golden
+    `cross_check_bins_small`) and each leave-one-out emulator's predictions at the bin centres."""
+    g = load("cross_check_bins_small")
+    spec, params, values = golden_inputs(g)
+    cc = CrossCheckBins()
+    cc.build_emulators(spec, params, values)
+    assert list(cc.leave_out_order) == list(g["order"])
+    got = np.array([[gp.get_parameter_vector() for gp in cc.cross_emulators[uid].bin_gaussian_process]
+                    for uid in cc.leave_out_order])
+    assert np.allclose(got, g["p_fit"], rtol=1e-8, atol=1e-8)
+    theta = theta_dict(spec, g)
+    pred = np.array([cc.cross_emulators[uid].predict_values(g["centers"], theta) for uid in cc.leave_out_order])
+    assert np.allclose(pred[:, 0], g["mu"], rtol=1e-9, atol=1e-11)
+    assert np.allclose(pred[:, 1], g["var"], rtol=1e-7, atol=1e-12)
 
 
 def test_ensemble_sampler_recovers_a_gaussian():
