@@ -64,8 +64,32 @@ def reference_test_fixture(seed):
     return spec, params, ModelValues(model_values=values)
 
 
+def ragged_fixture(seed):
+    """Simulations with DIFFERENT numbers of points at different independent values (the reference flattens whatever
+    each simulation holds, emulators/gaussian_process.py:89-131), one of them without errors."""
+    from emulator_b200.backend import ModelParameters, ModelSpecification, ModelValues
+
+    rng = np.random.default_rng(seed)
+    names = ["a", "b", "c"]
+    spec = ModelSpecification(number_of_parameters=3, parameter_names=names, parameter_limits=[[0.0, 1.0], [-1.0, 1.0], [2.0, 4.0]])
+    lengths = [4, 9, 6, 11, 7, 1, 8, 5, 10, 3, 12, 6, 9, 2, 7, 8]
+    params, values = {}, {}
+    for uid, n in enumerate(lengths):
+        theta = {"a": float(rng.random()), "b": float(2 * rng.random() - 1), "c": float(2 + 2 * rng.random())}
+        params[f"run{uid}"] = theta
+        x = np.sort(2.0 * rng.random(n))
+        y = np.sin(1.5 * x + 2.0 * theta["a"]) * theta["c"] + theta["b"] * x * x + 0.01 * rng.standard_normal(n)
+        entry = {"independent": x, "dependent": y}
+        if uid != 5:  # (the single-point simulation: an error-less one with close points would put cond(K) at 1e13)
+            entry["dependent_error"] = 0.02 + 0.02 * rng.random(n)
+        values[f"run{uid}"] = entry
+    return spec, ModelParameters(model_parameters=params), ModelValues(model_values=values)
+
+
 def golden_gpe(name, n_par, sims, bins, seed, mean_model=None, fixture=False):
-    if fixture:
+    if fixture == 2:
+        spec, params, values = ragged_fixture(seed)
+    elif fixture:
         spec, params, values = reference_test_fixture(seed)
     else:
         spec, params, values = synthetic.make_model(n_par, sims, bins, seed=seed)
@@ -89,7 +113,7 @@ def golden_gpe(name, n_par, sims, bins, seed, mean_model=None, fixture=False):
         lml.append(gp.log_likelihood(y)); grad.append(gp.grad_log_likelihood(y))
     emu.fit_model(rspec, rparams, rvalues)
     p_fit = emu.emulator.get_parameter_vector()
-    query_x = np.linspace(0.05, 0.95, 7) if not fixture else np.arange(10, dtype=np.float64)
+    query_x = np.linspace(0.05, 0.95, 7) if not fixture else (np.linspace(0.0, 2.0, 9) if fixture == 2 else np.arange(10, dtype=np.float64))
     lo = np.array(spec.parameter_limits)[:, 0]
     theta = {nm: float(lo[i]) + 0.37 + 0.05 * i for i, nm in enumerate(spec.parameter_names)}
     mu, var = emu.predict_values(query_x, theta)
@@ -392,6 +416,13 @@ def golden_penalties(name):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "penalties":
         golden_penalties("penalties")
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ragged":
+        golden_gpe("gpe_ragged", 3, 6, 0, seed=112, fixture=2)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "polynomial":
+        from swiftemulator.mean_models.polynomial import PolynomialMeanModel as RefPolynomial
+        golden_gpe("gpe_polynomial_mean", 3, 18, 8, seed=111, mean_model=RefPolynomial(degree=2))
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "cross_check_bins":
         golden_cross_check_bins("cross_check_bins_small", 2, 9, 4, seed=110)

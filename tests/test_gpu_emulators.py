@@ -12,7 +12,7 @@ from emulator_b200.emulators import (
     GaussianProcessEmulator, GaussianProcessEmulator1D, GaussianProcessEmulatorBins, GaussianProcessEmulatorMCMC,
     MultipleGaussianProcessEmulator,
 )
-from emulator_b200.mean_models import LinearMeanModel, OffsetMeanModel
+from emulator_b200.mean_models import LinearMeanModel, OffsetMeanModel, PolynomialMeanModel
 from emulator_b200.sensitivity import CrossCheck, CrossCheckBins, sobol_indices
 from test_host_logic import _regions, check_mocking_against_reference, check_multi_against_reference, fixture_data, golden_inputs, load, theta_dict
 
@@ -21,7 +21,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize(
     "name,mean_model",
-    [("gpe_small", None), ("gpe_noerr", None), ("gpe_linear_mean", LinearMeanModel()), ("gpe_offset_mean", OffsetMeanModel())],
+    [("gpe_small", None), ("gpe_noerr", None), ("gpe_ragged", None), ("gpe_linear_mean", LinearMeanModel()), ("gpe_offset_mean", OffsetMeanModel()),
+     ("gpe_polynomial_mean", PolynomialMeanModel(degree=2))],
 )
 def test_gpe_fit_and_predict_match_reference_golden(name, mean_model):
     g = load(name)

@@ -38,7 +38,28 @@ def fixture_data(seed):
     return spec, params, ModelValues(model_values=values)
 
 
+def ragged_data(seed):
+    """Simulations with different numbers of points at different independent values, one without errors (the same
+    construction as tests/golden/make_golden.py::ragged_fixture)."""
+    rng = np.random.default_rng(seed)
+    spec = ModelSpecification(number_of_parameters=3, parameter_names=["a", "b", "c"],
+                              parameter_limits=[[0.0, 1.0], [-1.0, 1.0], [2.0, 4.0]])
+    params, values = {}, {}
+    for uid, n in enumerate([4, 9, 6, 11, 7, 1, 8, 5, 10, 3, 12, 6, 9, 2, 7, 8]):
+        theta = {"a": float(rng.random()), "b": float(2 * rng.random() - 1), "c": float(2 + 2 * rng.random())}
+        params[f"run{uid}"] = theta
+        x = np.sort(2.0 * rng.random(n))
+        y = np.sin(1.5 * x + 2.0 * theta["a"]) * theta["c"] + theta["b"] * x * x + 0.01 * rng.standard_normal(n)
+        entry = {"independent": x, "dependent": y}
+        if uid != 5:  # (the single-point simulation: an error-less one with close points would put cond(K) at 1e13)
+            entry["dependent_error"] = 0.02 + 0.02 * rng.random(n)
+        values[f"run{uid}"] = entry
+    return spec, ModelParameters(model_parameters=params), ModelValues(model_values=values)
+
+
 def golden_inputs(g):
+    if "fixture" in g.files and int(g["fixture"]) == 2:
+        return ragged_data(int(g["seed"]))
     if "fixture" in g.files and int(g["fixture"]):
         return fixture_data(int(g["seed"]))
     return synthetic.make_model(int(g["n_par"]), int(g["sims"]), int(g["bins"]), seed=int(g["seed"]))
@@ -50,7 +71,8 @@ def theta_dict(spec, g):
 
 @pytest.mark.parametrize(
     "name,mean_model",
-    [("gpe_small", None), ("gpe_noerr", None), ("gpe_linear_mean", LinearMeanModel()), ("gpe_offset_mean", OffsetMeanModel())],
+    [("gpe_small", None), ("gpe_noerr", None), ("gpe_ragged", None), ("gpe_linear_mean", LinearMeanModel()), ("gpe_offset_mean", OffsetMeanModel()),
+     ("gpe_polynomial_mean", PolynomialMeanModel(degree=2))],
 )
 def test_gpe_matches_reference_flow(oracle_backend, name, mean_model):
     g = load(name)
